@@ -1,0 +1,516 @@
+// C ABI of libspiht_b200.so (see include/spiht_b200.h).
+#include <math.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+#include "kernels.cuh"
+#include "wavelets.cuh"
+
+namespace spihtb {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+static int dwt_max_level(int n, int f)
+{
+    // pywt.dwt_max_level: floor(log2(n / (f - 1))), 0 when n < f - 1
+    if (f < 2 || n < f - 1) return 0;
+    int q = n / (f - 1), l = 0;
+    while ((q >> (l + 1)) > 0) ++l;
+    return l;
+}
+
+static int coeff_len(int n, int f, int mode) { return mode == SPIHTB_MODE_PERIODIZATION ? (n + 1) / 2 : (n + f - 1) / 2; }
+
+// every LL-root offspring (encoder_decoder.rs:50-62) must lie inside the array
+static int check_coder_geom(int c, int h, int w, int ll_h, int ll_w)
+{
+    if (c <= 0 || h <= 0 || w <= 0) {
+        set_error("coefficient array shape must be positive, got (%d,%d,%d)", c, h, w);
+        return SPIHTB_EINVAL;
+    }
+    if (ll_h <= 1 || ll_w <= 1) {
+        set_error("assertion failed: ll_h > 1 && ll_w > 1 (got %d, %d)", ll_h, ll_w);
+        return SPIHTB_ELL;
+    }
+    if (2LL * ll_h + (ll_h & 1) > h || 2LL * ll_w + (ll_w & 1) > w) {
+        set_error("LL band %dx%d too large for a %dx%d array: root offspring out of bounds", ll_h, ll_w, h, w);
+        return SPIHTB_EGEOM;
+    }
+    KeyFmt kf;
+    if (!make_keyfmt(c, h, w, &kf)) {
+        set_error("shape c=%d h=%d w=%d does not fit a 31-bit packed list entry", c, h, w);
+        return SPIHTB_ESHAPE;
+    }
+    return SPIHTB_OK;
+}
+
+struct PyrBufs {
+    uint8_t *dp, *lp, *dpll, *lpll;
+    uint32_t *maxabs;
+};
+
+static int alloc_pyr(spihtb_ctx *ctx, int B, int C, int H, int W, int ll_h, int ll_w, PyrBufs *pb)
+{
+    const size_t nz = (size_t)B * C;
+    const size_t nodes = ((nz * (H / 2) * (W / 2) + 255) / 256) * 256;
+    const size_t roots = ((nz * ll_h * ll_w + 255) / 256) * 256;
+    const size_t total = 2 * nodes + 2 * roots + (size_t)B * 4 + 256;
+    int rc = ctx->ensure(ctx->pyr, total);
+    if (rc) return rc;
+    uint8_t *p = static_cast<uint8_t *>(ctx->pyr.p);
+    pb->dp = p;
+    pb->lp = p + nodes;
+    pb->dpll = p + 2 * nodes;
+    pb->lpll = p + 2 * nodes + roots;
+    pb->maxabs = reinterpret_cast<uint32_t *>(p + 2 * nodes + 2 * roots);
+    return SPIHTB_OK;
+}
+
+static uint64_t lis_shape_bound(int c, int h, int w, int ll_h, int ll_w)
+{
+    return (uint64_t)c * (h / 2 + 2) * (w / 2 + 2) * 5 / 4 + (uint64_t)c * ll_h * ll_w;
+}
+
+// bits a full encode can take when the top plane is `planes - 1`
+static uint64_t stream_bits_bound(int c, int h, int w, int ll_h, int ll_w, int planes)
+{
+    const uint64_t chw = (uint64_t)c * h * w;
+    return (uint64_t)planes * (chw + (uint64_t)c * ll_h * ll_w + lis_shape_bound(c, h, w, ll_h, ll_w)) + chw + 64;
+}
+
+static int fill_xform(XformArgs *x, int B, int C, const spihtb_geom *g, int color, const double *ch_scales, double q,
+                      int pixel_dtype)
+{
+    if (!g || B <= 0 || C <= 0 || C > 8) {
+        set_error("bad batch/channel count (B=%d, C=%d; C must be 1..8)", B, C);
+        return SPIHTB_EINVAL;
+    }
+    if (color != SPIHTB_COLOR_NONE && color != SPIHTB_COLOR_IPT) {
+        set_error("unknown colour model id %d", color);
+        return SPIHTB_EINVAL;
+    }
+    if (pixel_dtype != SPIHTB_F32 && pixel_dtype != SPIHTB_F64) {
+        set_error("unknown pixel dtype %d", pixel_dtype);
+        return SPIHTB_EINVAL;
+    }
+    x->B = B;
+    x->C = C;
+    x->g = *g;
+    x->color = color;
+    for (int c = 0; c < 8; ++c) x->scale[c] = (ch_scales && c < C) ? ch_scales[c] : 1.0;
+    x->q = q;
+    x->pixel_dtype = pixel_dtype;
+    return SPIHTB_OK;
+}
+
+}  // namespace spihtb
+
+using namespace spihtb;
+
+int spihtb_ctx::ensure(DevBuf &b, size_t bytes)
+{
+    if (b.cap >= bytes) return SPIHTB_OK;
+    if (b.p) {
+        cudaError_t e = cudaStreamSynchronize(stream);
+        if (e == cudaSuccess) e = cudaFree(b.p);
+        if (e != cudaSuccess) {
+            set_error("cudaFree failed: %s", cudaGetErrorString(e));
+            return SPIHTB_ECUDA;
+        }
+        b.p = nullptr;
+        b.cap = 0;
+    }
+    size_t want = bytes + bytes / 8;  // grow with headroom
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        want = bytes;
+        e = cudaMalloc(&b.p, want);
+    }
+    if (e != cudaSuccess) {
+        b.p = nullptr;
+        set_error("cudaMalloc(%zu bytes) failed: %s", want, cudaGetErrorString(e));
+        return SPIHTB_ENOMEM;
+    }
+    b.cap = want;
+    return SPIHTB_OK;
+}
+
+extern "C" {
+
+int spihtb_version(void) { return SPIHTB_VERSION; }
+const char *spihtb_last_error(void) { return g_err; }
+
+int spihtb_create(int device, spihtb_ctx **out)
+{
+    if (!out) {
+        set_error("ctx out pointer is null");
+        return SPIHTB_EINVAL;
+    }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        set_error("no usable CUDA device (%s); libspiht_b200 has no CPU fallback",
+                  e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+        cudaGetLastError();
+        return SPIHTB_ECUDA;
+    }
+    if (device < 0 || device >= ndev) {
+        set_error("device %d out of range (0..%d)", device, ndev - 1);
+        return SPIHTB_EINVAL;
+    }
+    SPIHTB_CUDA_CHECK(cudaSetDevice(device));
+    spihtb_ctx *c = new spihtb_ctx();
+    c->device = device;
+    int sms = 0;
+    SPIHTB_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    c->sm_count = sms > 0 ? sms : 148;
+    c->stream = nullptr;
+    *out = c;
+    return SPIHTB_OK;
+}
+
+int spihtb_destroy(spihtb_ctx *ctx)
+{
+    if (!ctx) return SPIHTB_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    DevBuf *bufs[] = {&ctx->pyr, &ctx->lists, &ctx->misc, &ctx->tmpa, &ctx->tmpb, &ctx->io, &ctx->io2};
+    for (DevBuf *b : bufs)
+        if (b->p) cudaFree(b->p);
+    delete ctx;
+    return SPIHTB_OK;
+}
+
+int spihtb_set_stream(spihtb_ctx *ctx, void *cuda_stream)
+{
+    if (!ctx) {
+        set_error("ctx is null");
+        return SPIHTB_EINVAL;
+    }
+    ctx->stream = static_cast<cudaStream_t>(cuda_stream);
+    return SPIHTB_OK;
+}
+
+int spihtb_sync(spihtb_ctx *ctx)
+{
+    if (!ctx) {
+        set_error("ctx is null");
+        return SPIHTB_EINVAL;
+    }
+    SPIHTB_CUDA_CHECK(cudaSetDevice(ctx->device));
+    SPIHTB_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    return SPIHTB_OK;
+}
+
+int64_t spihtb_launch_count(spihtb_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int spihtb_plan(int32_t h, int32_t w, int32_t wavelet, int32_t mode, int32_t level, spihtb_geom *g)
+{
+    if (!g) {
+        set_error("geom out pointer is null");
+        return SPIHTB_EINVAL;
+    }
+    const int F = wavelet_flen(wavelet);
+    if (F == 0) {
+        set_error("unknown wavelet id %d", wavelet);
+        return SPIHTB_EINVAL;
+    }
+    if (mode != SPIHTB_MODE_REFLECT && mode != SPIHTB_MODE_SYMMETRIC && mode != SPIHTB_MODE_PERIODIZATION) {
+        set_error("unknown mode id %d", mode);
+        return SPIHTB_EINVAL;
+    }
+    if (h <= 0 || w <= 0) {
+        set_error("image size must be positive, got %dx%d", h, w);
+        return SPIHTB_EINVAL;
+    }
+    const int maxlev = std::min(dwt_max_level(h, F), dwt_max_level(w, F));
+    int L = level < 0 ? maxlev : level;
+    if (L == 0) {
+        set_error("decomposition level is 0 for a %dx%d image with filter length %d: no detail band to code", h, w, F);
+        return SPIHTB_ELEVEL;
+    }
+    if (L > SPIHTB_MAX_LEVELS) {
+        set_error("level %d exceeds the supported maximum %d", L, SPIHTB_MAX_LEVELS);
+        return SPIHTB_ELEVEL;
+    }
+    memset(g, 0, sizeof(*g));
+    g->h = h;
+    g->w = w;
+    g->wavelet = wavelet;
+    g->mode = mode;
+    g->levels = L;
+    int ch = h, cw = w;
+    for (int l = 0; l < L; ++l) {
+        g->in_h[l] = ch;
+        g->in_w[l] = cw;
+        ch = coeff_len(ch, F, mode);
+        cw = coeff_len(cw, F, mode);
+        g->band_h[l] = ch;
+        g->band_w[l] = cw;
+    }
+    g->ll_h = ch;
+    g->ll_w = cw;
+    int sh = ch, sw = cw;
+    for (int l = L - 1; l >= 0; --l) {
+        g->off_h[l] = sh;
+        g->off_w[l] = sw;
+        sh += g->band_h[l];
+        sw += g->band_w[l];
+    }
+    g->enc_h = sh;
+    g->enc_w = sw;
+    const bool per = mode == SPIHTB_MODE_PERIODIZATION;
+    g->rec_h = per ? 2 * g->band_h[0] : 2 * g->band_h[0] - F + 2;
+    g->rec_w = per ? 2 * g->band_w[0] : 2 * g->band_w[0] - F + 2;
+    return SPIHTB_OK;
+}
+
+uint64_t spihtb_stream_bound(int32_t c, int32_t h, int32_t w, int32_t ll_h, int32_t ll_w)
+{
+    const uint64_t bits = stream_bits_bound(c, h, w, ll_h, ll_w, 31);
+    return ((bits + 7) / 8 + 15) / 8 * 8;
+}
+
+int spihtb_encode_coeffs(spihtb_ctx *ctx, const int32_t *dev_coeffs, int32_t B, int32_t c, int32_t h, int32_t w,
+                         int32_t ll_h, int32_t ll_w, uint64_t max_bits, const uint64_t *dev_max_bits,
+                         uint8_t *dev_out, uint64_t out_stride, uint64_t *dev_nbits, int32_t *dev_max_n,
+                         int32_t *dev_status)
+{
+    if (!ctx || !dev_coeffs || !dev_out || !dev_nbits || !dev_max_n || B <= 0) {
+        set_error("null pointer or empty batch");
+        return SPIHTB_EINVAL;
+    }
+    int rc = check_coder_geom(c, h, w, ll_h, ll_w);
+    if (rc) return rc;
+    SPIHTB_CUDA_CHECK(cudaSetDevice(ctx->device));
+    PyrBufs pb;
+    rc = alloc_pyr(ctx, B, c, h, w, ll_h, ll_w, &pb);
+    if (rc) return rc;
+    rc = launch_pyramid(ctx, dev_coeffs, B, c, h, w, ll_h, ll_w, pb.dp, pb.lp, pb.dpll, pb.lpll, pb.maxabs);
+    if (rc) return rc;
+    EncArgs a;
+    a.coeffs = dev_coeffs;
+    a.B = B; a.C = c; a.H = h; a.W = w; a.ll_h = ll_h; a.ll_w = ll_w;
+    a.dp = pb.dp; a.lp = pb.lp; a.dpll = pb.dpll; a.lpll = pb.lpll;
+    a.maxabs = pb.maxabs;
+    a.max_bits = max_bits;
+    a.dev_max_bits = dev_max_bits;
+    a.out = dev_out;
+    a.out_stride = out_stride;
+    a.nbits = dev_nbits;
+    a.max_n = dev_max_n;
+    a.status = dev_status;
+    return launch_encode(ctx, a);
+}
+
+int spihtb_decode_coeffs(spihtb_ctx *ctx, const uint8_t *dev_in, uint64_t in_stride, const uint64_t *dev_nbytes,
+                         const int32_t *dev_n, int32_t B, int32_t c, int32_t h, int32_t w, int32_t ll_h,
+                         int32_t ll_w, int32_t *dev_coeffs_out)
+{
+    if (!ctx || !dev_in || !dev_nbytes || !dev_n || !dev_coeffs_out || B <= 0) {
+        set_error("null pointer or empty batch");
+        return SPIHTB_EINVAL;
+    }
+    int rc = check_coder_geom(c, h, w, ll_h, ll_w);
+    if (rc) return rc;
+    SPIHTB_CUDA_CHECK(cudaSetDevice(ctx->device));
+    DecArgs a;
+    a.in = dev_in;
+    a.in_stride = in_stride;
+    a.nbytes = dev_nbytes;
+    a.n = dev_n;
+    a.B = B; a.C = c; a.H = h; a.W = w; a.ll_h = ll_h; a.ll_w = ll_w;
+    a.out = dev_coeffs_out;
+    return launch_decode(ctx, a);
+}
+
+int spihtb_encode(spihtb_ctx *ctx, const int32_t *host_coeffs, int32_t c, int32_t h, int32_t w, int32_t ll_h,
+                  int32_t ll_w, uint64_t max_bits, const uint8_t **out_bytes, uint64_t *out_nbits,
+                  int32_t *out_max_n)
+{
+    if (!ctx || !host_coeffs || !out_bytes || !out_nbits || !out_max_n) {
+        set_error("null pointer");
+        return SPIHTB_EINVAL;
+    }
+    int rc = check_coder_geom(c, h, w, ll_h, ll_w);
+    if (rc) return rc;
+    SPIHTB_CUDA_CHECK(cudaSetDevice(ctx->device));
+    const size_t n = (size_t)c * h * w;
+    rc = ctx->ensure(ctx->io, n * sizeof(int32_t) + 256);
+    if (rc) return rc;
+    int32_t *d_coeffs = static_cast<int32_t *>(ctx->io.p);
+    SPIHTB_CUDA_CHECK(cudaMemcpyAsync(d_coeffs, host_coeffs, n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+
+    PyrBufs pb;
+    rc = alloc_pyr(ctx, 1, c, h, w, ll_h, ll_w, &pb);
+    if (rc) return rc;
+    rc = launch_pyramid(ctx, d_coeffs, 1, c, h, w, ll_h, ll_w, pb.dp, pb.lp, pb.dpll, pb.lpll, pb.maxabs);
+    if (rc) return rc;
+    // size the stream: the budget, or the worst case for the top plane found
+    uint32_t maxabs = 0;
+    SPIHTB_CUDA_CHECK(cudaMemcpyAsync(&maxabs, pb.maxabs, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    SPIHTB_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    int planes = 2;
+    while (planes < 33 && (maxabs >> (planes - 1)) != 0) ++planes;  // floor(log2 max) + 2 >= max_n + 1
+    uint64_t bits = stream_bits_bound(c, h, w, ll_h, ll_w, planes);
+    if (max_bits != 0 && max_bits < bits) bits = max_bits;
+    const uint64_t stride = ((bits + 7) / 8 + 15) / 8 * 8;
+    rc = ctx->ensure(ctx->io2, stride + 64);
+    if (rc) return rc;
+    uint8_t *d_out = static_cast<uint8_t *>(ctx->io2.p);
+    uint64_t *d_nbits = reinterpret_cast<uint64_t *>(d_out + stride);
+    int32_t *d_max_n = reinterpret_cast<int32_t *>(d_out + stride + 8);
+    int32_t *d_status = d_max_n + 1;
+
+    EncArgs a;
+    a.coeffs = d_coeffs;
+    a.B = 1; a.C = c; a.H = h; a.W = w; a.ll_h = ll_h; a.ll_w = ll_w;
+    a.dp = pb.dp; a.lp = pb.lp; a.dpll = pb.dpll; a.lpll = pb.lpll;
+    a.maxabs = pb.maxabs;
+    a.max_bits = max_bits;
+    a.dev_max_bits = nullptr;
+    a.out = d_out;
+    a.out_stride = stride;
+    a.nbits = d_nbits;
+    a.max_n = d_max_n;
+    a.status = d_status;
+    rc = launch_encode(ctx, a);
+    if (rc) return rc;
+    struct { uint64_t nbits; int32_t max_n; int32_t status; } res;
+    SPIHTB_CUDA_CHECK(cudaMemcpyAsync(&res, d_nbits, sizeof(res), cudaMemcpyDeviceToHost, ctx->stream));
+    SPIHTB_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    if (res.status & 1) {
+        set_error("internal: stream bound %llu bits too small", (unsigned long long)bits);
+        return SPIHTB_ECAP;
+    }
+    const size_t nbytes = (size_t)((res.nbits + 7) / 8);
+    ctx->host_out.resize(nbytes ? nbytes : 1);
+    if (nbytes) {
+        SPIHTB_CUDA_CHECK(cudaMemcpyAsync(ctx->host_out.data(), d_out, nbytes, cudaMemcpyDeviceToHost, ctx->stream));
+        SPIHTB_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    }
+    *out_bytes = ctx->host_out.data();
+    *out_nbits = res.nbits;
+    *out_max_n = res.max_n;
+    return SPIHTB_OK;
+}
+
+int spihtb_decode(spihtb_ctx *ctx, const uint8_t *host_data, uint64_t nbytes, int32_t n, int32_t c, int32_t h,
+                  int32_t w, int32_t ll_h, int32_t ll_w, int32_t *host_out)
+{
+    if (!ctx || (!host_data && nbytes) || !host_out) {
+        set_error("null pointer");
+        return SPIHTB_EINVAL;
+    }
+    if (n < 0 || n > 255) {
+        set_error("n must fit a u8, got %d", n);
+        return SPIHTB_EINVAL;
+    }
+    int rc = check_coder_geom(c, h, w, ll_h, ll_w);
+    if (rc) return rc;
+    SPIHTB_CUDA_CHECK(cudaSetDevice(ctx->device));
+    const size_t ncoef = (size_t)c * h * w;
+    const uint64_t stride = (nbytes + 15) / 8 * 8;
+    rc = ctx->ensure(ctx->io, ncoef * sizeof(int32_t) + 256);
+    if (rc) return rc;
+    rc = ctx->ensure(ctx->io2, stride + 64);
+    if (rc) return rc;
+    uint8_t *d_in = static_cast<uint8_t *>(ctx->io2.p);
+    uint64_t *d_nbytes = reinterpret_cast<uint64_t *>(d_in + stride);
+    int32_t *d_n = reinterpret_cast<int32_t *>(d_in + stride + 8);
+    SPIHTB_CUDA_CHECK(cudaMemsetAsync(d_in, 0, stride + 64, ctx->stream));
+    if (nbytes)
+        SPIHTB_CUDA_CHECK(cudaMemcpyAsync(d_in, host_data, nbytes, cudaMemcpyHostToDevice, ctx->stream));
+    struct { uint64_t nb; int32_t n; } hdr = {nbytes, n};
+    SPIHTB_CUDA_CHECK(cudaMemcpyAsync(d_nbytes, &hdr, 12, cudaMemcpyHostToDevice, ctx->stream));
+    DecArgs a;
+    a.in = d_in;
+    a.in_stride = stride;
+    a.nbytes = d_nbytes;
+    a.n = d_n;
+    a.B = 1; a.C = c; a.H = h; a.W = w; a.ll_h = ll_h; a.ll_w = ll_w;
+    a.out = static_cast<int32_t *>(ctx->io.p);
+    rc = launch_decode(ctx, a);
+    if (rc) return rc;
+    SPIHTB_CUDA_CHECK(cudaMemcpyAsync(host_out, ctx->io.p, ncoef * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    SPIHTB_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    return SPIHTB_OK;
+}
+
+int spihtb_forward(spihtb_ctx *ctx, const void *dev_pixels, int32_t pixel_dtype, int32_t B, int32_t C,
+                   const spihtb_geom *geom, int32_t color_model, const double *ch_scales, double q,
+                   int32_t *dev_coeffs)
+{
+    if (!ctx || !dev_pixels || !dev_coeffs) {
+        set_error("null pointer");
+        return SPIHTB_EINVAL;
+    }
+    XformArgs x;
+    int rc = fill_xform(&x, B, C, geom, color_model, ch_scales, q, pixel_dtype);
+    if (rc) return rc;
+    SPIHTB_CUDA_CHECK(cudaSetDevice(ctx->device));
+    return launch_forward(ctx, dev_pixels, x, dev_coeffs);
+}
+
+int spihtb_inverse(spihtb_ctx *ctx, const int32_t *dev_coeffs, int32_t B, int32_t C, const spihtb_geom *geom,
+                   int32_t color_model, const double *ch_scales, double q, void *dev_pixels_out,
+                   int32_t pixel_dtype)
+{
+    if (!ctx || !dev_pixels_out || !dev_coeffs) {
+        set_error("null pointer");
+        return SPIHTB_EINVAL;
+    }
+    XformArgs x;
+    int rc = fill_xform(&x, B, C, geom, color_model, ch_scales, q, pixel_dtype);
+    if (rc) return rc;
+    SPIHTB_CUDA_CHECK(cudaSetDevice(ctx->device));
+    return launch_inverse(ctx, dev_coeffs, x, dev_pixels_out);
+}
+
+int spihtb_encode_images(spihtb_ctx *ctx, const void *dev_pixels, int32_t pixel_dtype, int32_t B, int32_t C,
+                         const spihtb_geom *geom, int32_t color_model, const double *ch_scales, double q,
+                         uint64_t max_bits, const uint64_t *dev_max_bits, int32_t *dev_coeffs_scratch,
+                         uint8_t *dev_out, uint64_t out_stride, uint64_t *dev_nbits, int32_t *dev_max_n,
+                         int32_t *dev_status)
+{
+    if (!geom || !dev_coeffs_scratch) {
+        set_error("null pointer");
+        return SPIHTB_EINVAL;
+    }
+    int rc = check_coder_geom(C, geom->enc_h, geom->enc_w, geom->ll_h, geom->ll_w);
+    if (rc) return rc;
+    rc = spihtb_forward(ctx, dev_pixels, pixel_dtype, B, C, geom, color_model, ch_scales, q, dev_coeffs_scratch);
+    if (rc) return rc;
+    return spihtb_encode_coeffs(ctx, dev_coeffs_scratch, B, C, geom->enc_h, geom->enc_w, geom->ll_h, geom->ll_w,
+                                max_bits, dev_max_bits, dev_out, out_stride, dev_nbits, dev_max_n, dev_status);
+}
+
+int spihtb_decode_images(spihtb_ctx *ctx, const uint8_t *dev_in, uint64_t in_stride, const uint64_t *dev_nbytes,
+                         const int32_t *dev_n, int32_t B, int32_t C, const spihtb_geom *geom, int32_t color_model,
+                         const double *ch_scales, double q, int32_t *dev_coeffs_scratch, void *dev_pixels_out,
+                         int32_t pixel_dtype)
+{
+    if (!geom || !dev_coeffs_scratch) {
+        set_error("null pointer");
+        return SPIHTB_EINVAL;
+    }
+    int rc = spihtb_decode_coeffs(ctx, dev_in, in_stride, dev_nbytes, dev_n, B, C, geom->enc_h, geom->enc_w,
+                                  geom->ll_h, geom->ll_w, dev_coeffs_scratch);
+    if (rc) return rc;
+    return spihtb_inverse(ctx, dev_coeffs_scratch, B, C, geom, color_model, ch_scales, q, dev_pixels_out,
+                          pixel_dtype);
+}
+
+}  // extern "C"

@@ -1,0 +1,50 @@
+// Internal launch interfaces between the translation units of libspiht_b200.
+#pragma once
+#include "common.cuh"
+
+namespace spihtb {
+
+// ---- pyramid.cu
+int launch_pyramid(spihtb_ctx *ctx, const int32_t *coeffs, int B, int C, int H, int W, int ll_h, int ll_w,
+                   uint8_t *dp, uint8_t *lp, uint8_t *dpll, uint8_t *lpll, uint32_t *maxabs);
+
+// ---- spiht_enc.cu
+struct EncArgs {
+    const int32_t *coeffs;  // [B][C][H][W]
+    int B, C, H, W, ll_h, ll_w;
+    const uint8_t *dp, *lp, *dpll, *lpll;
+    const uint32_t *maxabs;        // [B]
+    uint64_t max_bits;             // 0 = unlimited
+    const uint64_t *dev_max_bits;  // optional [B]
+    uint8_t *out;
+    uint64_t out_stride;  // bytes, multiple of 8
+    uint64_t *nbits;      // [B]
+    int32_t *max_n;       // [B]
+    int32_t *status;      // optional [B]
+};
+int launch_encode(spihtb_ctx *ctx, const EncArgs &a);
+
+// ---- spiht_dec.cu
+struct DecArgs {
+    const uint8_t *in;
+    uint64_t in_stride;      // bytes, multiple of 8
+    const uint64_t *nbytes;  // [B]
+    const int32_t *n;        // [B]
+    int B, C, H, W, ll_h, ll_w;
+    int32_t *out;  // [B][C][H][W]
+};
+int launch_decode(spihtb_ctx *ctx, const DecArgs &a);
+
+// ---- dwt_fwd.cu / dwt_inv.cu
+struct XformArgs {
+    int B, C;
+    spihtb_geom g;
+    int color;
+    double scale[8];  // per-channel multipliers m_c (1.0 when none)
+    double q;
+    int pixel_dtype;
+};
+int launch_forward(spihtb_ctx *ctx, const void *pixels, const XformArgs &x, int32_t *coeffs);
+int launch_inverse(spihtb_ctx *ctx, const int32_t *coeffs, const XformArgs &x, void *pixels_out);
+
+}  // namespace spihtb

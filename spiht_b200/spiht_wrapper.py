@@ -1,0 +1,246 @@
+"""Drop-in for the reference's spiht/spiht_wrapper.py: same names, argument
+order, defaults and result fields; the colour transform, DWT, quantiser and
+SPIHT coder all run on the GPU through libspiht_b200.so.
+
+Added on top of the reference surface: `encode_images` / `decode_images`, the
+batched forms of `encode_image` / `decode_image` (one library call per batch of
+same-shaped images; mixed shapes are grouped).
+"""
+from dataclasses import asdict, dataclass
+from typing import Any, List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+
+from . import _lib
+from . import spiht as spiht_rs
+from .color_models import normalise as _norm_color
+
+
+def quantize(arr, q_scale=10.):
+    """spiht_wrapper.py:9-11"""
+    arr = arr * q_scale
+    return arr.astype(np.int32)
+
+
+def dequantize(arr, q_scale=10.):
+    """spiht_wrapper.py:13-14"""
+    return arr / q_scale
+
+
+ENCODER_DECODER_VERSION = "0.0.2"
+
+# max_bits=None in the reference (spiht_wrapper.py:174-176)
+_VERY_LARGE = 99999999999999999
+
+
+@dataclass
+class SpihtSettings:
+    """spiht_wrapper.py:20-63.  Parameters of the codec that are not particular
+    to one image: wavelet, quantisation scale, boundary mode, colour model and
+    optional per-channel quantisation scales."""
+    wavelet: str = 'bior2.2'
+    quantization_scale: float = 50.0
+    mode: str = 'reflect'
+    color_model: Optional[str] = None
+    per_channel_quant_scales: Optional[List[float]] = None
+
+
+@dataclass
+class EncodingResult:
+    """spiht_wrapper.py:65-89.
+    encoded_bytes: bytes returned by the spiht encoder
+    h, w, c: height, width, channels of the original image
+    max_n: the starting n parameter used in the spiht encoder
+    level: optional number of DWT levels
+    """
+    encoded_bytes: bytes
+    h: int
+    w: int
+    c: int
+    max_n: int
+    level: Optional[int]
+    _encoding_version: str = ENCODER_DECODER_VERSION
+
+    def to_dict(self):
+        return {f"encoding_result_{k}": v for k, v in asdict(self).items()}
+
+    @staticmethod
+    def from_dict(d):
+        d = {k.removeprefix('encoding_result_'): v for k, v in d.items() if k.startswith('encoding_result_')}
+        return EncodingResult(**d)
+
+
+def _geom(h, w, spiht_settings, level):
+    return _lib.plan(h, w, spiht_settings.wavelet, spiht_settings.mode, level)
+
+
+def get_slices_and_h_w(h: int, w: int, spiht_settings: SpihtSettings, level: Optional[int]):
+    """spiht_wrapper.py:92-139: the slices pywt.coeffs_to_array would use, and the
+    height and width of the coefficient array."""
+    g = _geom(h, w, spiht_settings, level)
+    start_h, start_w = g.ll_h, g.ll_w
+    slices: List[Any] = [(slice(None), slice(start_h), slice(start_w))]
+    for l in range(g.levels - 1, -1, -1):
+        bh, bw = g.band_h[l], g.band_w[l]
+        slices.append({
+            "ad": (slice(None), slice(0, bh), slice(start_w, start_w + bw)),
+            "da": (slice(None), slice(start_h, start_h + bh), slice(0, bw)),
+            "dd": (slice(None), slice(start_h, start_h + bh), slice(start_w, start_w + bw)),
+        })
+        start_h += bh
+        start_w += bw
+    return slices, start_h, start_w
+
+
+def _torch():
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError("spiht_b200 needs a CUDA device: the codec has no CPU fallback")
+    return torch
+
+
+def _to_device_pixels(image):
+    """numpy / torch image batch -> contiguous CUDA tensor, float32 kept, everything else float64"""
+    torch = _torch()
+    if isinstance(image, torch.Tensor):
+        t = image
+        if t.dtype not in (torch.float32, torch.float64):
+            t = t.to(torch.float64)
+        return t.cuda().contiguous()
+    a = np.asarray(image)
+    if a.dtype != np.float32:
+        a = a.astype(np.float64)
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def encode_image(image: np.ndarray, spiht_settings: SpihtSettings = SpihtSettings(), level: Optional[int] = None,
+                 max_bits: Optional[int] = None):
+    """spiht_wrapper.py:142-189.  Takes the DWT of the image, quantises the
+    coefficients and encodes them.
+
+    image: 3D array (C,H,W) of floating point pixel values (numpy, or a torch tensor)
+    Returns EncodingResult
+    """
+    if image.ndim != 3:
+        raise ValueError('image ndim must be 3: c,h,w')
+    return encode_images(image[None], spiht_settings, level, max_bits)[0]
+
+
+def encode_images(images, spiht_settings: SpihtSettings = SpihtSettings(), level: Optional[int] = None,
+                  max_bits: Optional[int] = None) -> List[EncodingResult]:
+    """Batched encode_image.  images: array/tensor (B,C,H,W), or a sequence of
+    (C,H,W) images (shapes may differ; equal shapes are encoded together)."""
+    from . import batch
+    torch = _torch()
+    if isinstance(images, (list, tuple)):
+        for im in images:
+            if im.ndim != 3:
+                raise ValueError('image ndim must be 3: c,h,w')
+        groups = {}
+        for idx, im in enumerate(images):
+            groups.setdefault((tuple(im.shape), str(im.dtype)), []).append(idx)
+        results: List[Optional[EncodingResult]] = [None] * len(images)
+        for _, idxs in groups.items():
+            ims = [images[i] for i in idxs]
+            stack = torch.stack(ims) if isinstance(ims[0], torch.Tensor) else np.stack(ims)
+            for i, r in zip(idxs, encode_images(stack, spiht_settings, level, max_bits)):
+                results[i] = r
+        return results  # type: ignore[return-value]
+    if images.ndim != 4:
+        raise ValueError('images ndim must be 4: b,c,h,w')
+    B, c, h, w = images.shape
+    _norm_color(spiht_settings.color_model)
+    g = _geom(h, w, spiht_settings, level)
+    pixels = _to_device_pixels(images)
+
+    if max_bits is None:
+        max_bits = _VERY_LARGE
+    budget = int(max_bits)
+    bound = 8 * int(_lib.lib().spihtb_stream_bound(c, g.enc_h, g.enc_w, g.ll_h, g.ll_w))
+    if budget == 0 or budget > bound:
+        # untruncated: run the transform first, size the rows from the largest coefficient
+        coeffs = batch.forward(pixels, g, spiht_settings)
+        planes = int(coeffs.abs().max().item()).bit_length() + 1
+        stride = (bound // 31 * min(planes + 1, 31) // 8 + 64) // 8 * 8
+        streams, nbits, max_n, status = batch.encode_coeffs(coeffs, g.ll_h, g.ll_w, budget, out_stride=stride)
+    else:
+        streams, nbits, max_n, status, _ = batch.encode_images(pixels, g, spiht_settings, budget)
+    nbits_h = nbits.cpu().numpy()
+    max_n_h = max_n.cpu().numpy()
+    if int(status.max().item()) != 0:
+        raise _lib.SpihtB200Error(_lib.ECAP, "bitstream row too small for an untruncated encode")
+    nbytes = (nbits_h + 7) // 8
+    rows = streams[:, :int(nbytes.max()) if B else 0].cpu().numpy()
+    return [EncodingResult(rows[b, :int(nbytes[b])].tobytes(), h, w, c, int(max_n_h[b]), level) for b in range(B)]
+
+
+def decode_image(encoding_result: EncodingResult, spiht_settings: SpihtSettings,
+                 return_metadata: bool = False) -> Union[np.ndarray, Tuple[np.ndarray, np.ndarray]]:
+    """spiht_wrapper.py:192-216.  Decodes the encoding_result to pixel values
+    (float64 array (C,H',W'); H' = H + 1 for odd H, as pywt.waverec2 returns)."""
+    if return_metadata:
+        raise NotImplementedError("decode_with_metadata is not implemented by spiht_b200 yet")
+    return decode_images([encoding_result], spiht_settings)[0]
+
+
+def decode_images(encoding_results: Sequence[EncodingResult], spiht_settings: SpihtSettings, as_numpy: bool = True):
+    """Batched decode_image.  Returns a list of float64 (C,H',W') arrays in input order."""
+    from . import batch
+    torch = _torch()
+    _norm_color(spiht_settings.color_model)
+    groups = {}
+    for idx, er in enumerate(encoding_results):
+        if er._encoding_version != ENCODER_DECODER_VERSION:
+            raise ValueError(er._encoding_version)
+        groups.setdefault((er.c, er.h, er.w, er.level), []).append(idx)
+    out: List[Any] = [None] * len(encoding_results)
+    for (c, h, w, level), idxs in groups.items():
+        g = _geom(h, w, spiht_settings, level)
+        ers = [encoding_results[i] for i in idxs]
+        lens = np.array([len(e.encoded_bytes) for e in ers], dtype=np.int64)
+        stride = (int(lens.max()) + 15) // 8 * 8
+        host = np.zeros((len(ers), stride), dtype=np.uint8)
+        for r, e in enumerate(ers):
+            host[r, :lens[r]] = np.frombuffer(e.encoded_bytes, dtype=np.uint8)
+        streams = torch.from_numpy(host).cuda()
+        nbytes = torch.from_numpy(lens).cuda()
+        max_n = torch.tensor([e.max_n for e in ers], dtype=torch.int32).cuda()
+        pix, _ = batch.decode_images(streams, nbytes, max_n, c, g, spiht_settings, dtype=torch.float64)
+        pix = pix.cpu().numpy() if as_numpy else pix
+        for r, i in enumerate(idxs):
+            out[i] = pix[r]
+    return out
+
+
+def decode_rec_array(encoding_result: EncodingResult, spiht_settings: SpihtSettings, return_metadata: bool = False):
+    """spiht_wrapper.py:218-257: bitstream -> int32 coefficient array (+ geometry)"""
+    encoded_bytes = encoding_result.encoded_bytes
+    h = encoding_result.h
+    w = encoding_result.w
+    c = encoding_result.c
+    max_n = encoding_result.max_n
+    level = encoding_result.level
+
+    if encoding_result._encoding_version != ENCODER_DECODER_VERSION:
+        raise ValueError(encoding_result._encoding_version)
+
+    slices, enc_h, enc_w = get_slices_and_h_w(h, w, spiht_settings, level)
+    ll_h, ll_w = slices[0][1].stop, slices[0][2].stop
+
+    if return_metadata:
+        raise NotImplementedError("decode_with_metadata is not implemented by spiht_b200 yet")
+    rec_arr = spiht_rs.decode(encoded_bytes, max_n, c, enc_h, enc_w, ll_h, ll_w)
+    return dict(rec_arr=rec_arr, slices=slices, spiht_metadata=None, h=h, w=w, level=level)
+
+
+def decode_from_rec_arr(rec_arr: np.ndarray, h: int, w: int, level, spiht_settings: SpihtSettings, slices=None):
+    """spiht_wrapper.py:259-281: int32 coefficient array -> image"""
+    from . import batch
+    torch = _torch()
+    _norm_color(spiht_settings.color_model)
+    g = _geom(h, w, spiht_settings, level)
+    rec_arr = np.asarray(rec_arr)
+    if rec_arr.shape[1:] != (g.enc_h, g.enc_w):
+        raise ValueError(f"rec_arr has shape {rec_arr.shape}, expected (c, {g.enc_h}, {g.enc_w})")
+    coeffs = torch.from_numpy(np.ascontiguousarray(rec_arr.astype(np.int32)))[None].cuda()
+    return batch.inverse(coeffs, g, spiht_settings, dtype=torch.float64)[0].cpu().numpy()

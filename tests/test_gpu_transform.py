@@ -1,0 +1,220 @@
+"""GPU parity of the float stages (colour, DWT, quantiser, inverse) against the
+float64 numpy oracle, and of the whole encode_image / decode_image path.
+
+Tolerances (stated by the north star as "a stated max-abs tolerance ... with
+resulting quantized-coefficient mismatches counted"):
+  * forward coefficients before truncation: |gpu - oracle| <= 1e-9 * max|coef|
+    (float64 on both sides; differences come from FMA contraction and, with
+    IPT, from pow() ulp differences);
+  * quantised int32 coefficients: mismatches are counted; each must be off by
+    exactly 1 and sit within 1e-6 of an integer boundary in the oracle's float
+    value; at most 1e-5 of the coefficients may mismatch (0 expected w/o IPT);
+  * inverse transform: |gpu - oracle| <= 1e-9 * max|pixel|.
+"""
+import numpy as np
+import pytest
+
+from conftest import synth_image
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch
+
+
+def _settings(**kw):
+    from spiht_b200 import SpihtSettings
+    return SpihtSettings(**kw)
+
+
+def _check_quantised(got, oracle_float, tag):
+    want = oracle_float.astype(np.int32)
+    bad = np.nonzero(got != want)
+    n_bad = len(bad[0])
+    if n_bad:
+        d = np.abs(got[bad].astype(np.int64) - want[bad])
+        f = oracle_float[bad]
+        near = np.minimum(np.abs(f - np.round(f)), 1.0)
+        assert d.max() <= 1, f"{tag}: quantised coefficient off by {d.max()}"
+        assert near.max() < 1e-6, f"{tag}: mismatch away from an integer boundary ({near.max()})"
+    assert n_bad <= max(1, int(1e-5 * got.size)), f"{tag}: {n_bad} of {got.size} quantised coefficients differ"
+    return n_bad
+
+
+CASES = [
+    ((3, 64, 96), "bior2.2", "reflect", None),
+    ((3, 256, 384), "bior2.2", "reflect", None),
+    ((1, 70, 70), "bior2.2", "reflect", None),       # odd LL band
+    ((3, 67, 131), "bior2.2", "reflect", 3),         # odd sizes
+    ((2, 128, 96), "bior4.4", "symmetric", None),
+    ((3, 200, 168), "bior4.4", "reflect", 2),
+    ((1, 320, 320), "bior6.8", "reflect", None),
+    ((3, 128, 256), "bior2.2", "periodization", None),
+    ((1, 130, 66), "bior4.4", "periodization", 2),
+    ((3, 96, 96), "bior6.8", "periodization", 1),
+]
+
+
+@pytest.mark.parametrize("shape,wavelet,mode,level", CASES)
+def test_forward_matches_oracle(torch_cuda, shape, wavelet, mode, level):
+    torch = torch_cuda
+    from oracle import wrapper_ref
+    from spiht_b200 import _lib, batch
+    c, h, w = shape
+    img = synth_image(c, h, w, 3)
+    st = _settings(wavelet=wavelet, mode=mode)
+    g = _lib.plan(h, w, wavelet, mode, level)
+    of, ll_h, ll_w = wrapper_ref.forward_coeffs(img, wavelet, mode, level, 50.0, return_float=True)
+    assert (ll_h, ll_w) == (g.ll_h, g.ll_w) and of.shape[1:] == (g.enc_h, g.enc_w)
+    got = batch.forward(torch.from_numpy(img[None]).cuda(), g, st)[0].cpu().numpy()
+    _check_quantised(got, of, f"{shape} {wavelet} {mode} L={level}")
+    # float32 pixels: the oracle sees the same float32 values upcast to float64
+    img32 = img.astype(np.float32)
+    of32, _, _ = wrapper_ref.forward_coeffs(img32.astype(np.float64), wavelet, mode, level, 50.0, return_float=True)
+    got32 = batch.forward(torch.from_numpy(img32[None]).cuda(), g, st)[0].cpu().numpy()
+    _check_quantised(got32, of32, f"f32 {shape} {wavelet} {mode} L={level}")
+
+
+def test_forward_per_channel_scales_and_batch(torch_cuda):
+    torch = torch_cuda
+    from oracle import wrapper_ref
+    from spiht_b200 import _lib, batch
+    imgs = np.stack([synth_image(3, 96, 128, s) for s in range(5)])
+    st = _settings(quantization_scale=1.0, per_channel_quant_scales=[50.0, 15.0, 15.0])
+    g = _lib.plan(96, 128)
+    got = batch.forward(torch.from_numpy(imgs).cuda(), g, st).cpu().numpy()
+    for b in range(5):
+        of, _, _ = wrapper_ref.forward_coeffs(imgs[b], quantization_scale=1.0,
+                                              per_channel_quant_scales=[50.0, 15.0, 15.0], return_float=True)
+        _check_quantised(got[b], of, f"image {b}")
+
+
+def test_forward_ipt(torch_cuda):
+    torch = torch_cuda
+    from oracle import wrapper_ref
+    from spiht_b200 import _lib, batch
+    img = synth_image(3, 128, 160, 5)
+    st = _settings(quantization_scale=1.0, color_model="IPT", per_channel_quant_scales=[50.0, 15.0, 15.0])
+    g = _lib.plan(128, 160)
+    of, _, _ = wrapper_ref.forward_coeffs(img, quantization_scale=1.0, color_model="IPT",
+                                          per_channel_quant_scales=[50.0, 15.0, 15.0], return_float=True)
+    got = batch.forward(torch.from_numpy(img[None]).cuda(), g, st)[0].cpu().numpy()
+    n_bad = _check_quantised(got, of, "IPT")
+    print("IPT quantised mismatches:", n_bad, "of", got.size)
+
+
+@pytest.mark.parametrize("shape,wavelet,mode,level", CASES)
+def test_inverse_matches_oracle(torch_cuda, shape, wavelet, mode, level):
+    torch = torch_cuda
+    from oracle import wrapper_ref
+    from spiht_b200 import _lib, batch
+    c, h, w = shape
+    g = _lib.plan(h, w, wavelet, mode, level)
+    rng = np.random.default_rng(4)
+    coeffs = rng.normal(0, 200, (c, g.enc_h, g.enc_w)).astype(np.int32)
+    want = wrapper_ref.inverse_coeffs(coeffs, h, w, wavelet, mode, level, 50.0)
+    st = _settings(wavelet=wavelet, mode=mode)
+    got = batch.inverse(torch.from_numpy(coeffs[None]).cuda(), g, st)[0].cpu().numpy()
+    assert got.shape == want.shape == (c, g.rec_h, g.rec_w)
+    tol = 1e-9 * max(1.0, np.abs(want).max())
+    assert np.abs(got - want).max() <= tol
+    got32 = batch.inverse(torch.from_numpy(coeffs[None]).cuda(), g, st, dtype=torch.float32)[0].cpu().numpy()
+    assert np.abs(got32 - want).max() <= 1e-6 * max(1.0, np.abs(want).max())
+
+
+def test_inverse_ipt(torch_cuda):
+    torch = torch_cuda
+    from oracle import wrapper_ref
+    from spiht_b200 import _lib, batch
+    img = synth_image(3, 64, 96, 8)
+    kw = dict(quantization_scale=1.0, color_model="IPT", per_channel_quant_scales=[100.0, 20.0, 20.0])
+    coeffs, _, _ = wrapper_ref.forward_coeffs(img, **kw)
+    want = wrapper_ref.inverse_coeffs(coeffs, 64, 96, **kw)
+    g = _lib.plan(64, 96)
+    got = batch.inverse(torch.from_numpy(coeffs[None]).cuda(), g, _settings(**kw))[0].cpu().numpy()
+    assert np.abs(got - want).max() <= 1e-9 * max(1.0, np.abs(want).max())
+
+
+def _psnr(a, b):
+    mse = np.mean((a - b) ** 2)
+    return 10 * np.log10(1.0 / mse)
+
+
+@pytest.mark.parametrize("kw,bpp", [
+    (dict(), 1.0),
+    (dict(), 0.1),
+    (dict(wavelet="bior4.4", mode="symmetric"), 0.5),
+    (dict(mode="periodization"), 0.5),
+    (dict(quantization_scale=1.0, color_model="IPT", per_channel_quant_scales=[50.0, 15.0, 15.0]), 0.5),
+])
+def test_encode_image_decode_image_parity(torch_cuda, kw, bpp):
+    """end to end: identical coefficient arrays give identical bytes; the decoded
+    image matches the oracle's decode of the same bytes; PSNR equal at equal bpp"""
+    import spiht_b200 as spiht
+    from oracle import wrapper_ref
+    img = synth_image(3, 128, 192, 21)
+    st = spiht.SpihtSettings(**kw)
+    mb = int(128 * 192 * bpp)
+    enc = spiht.encode_image(img, st, max_bits=mb)
+    ref = wrapper_ref.encode_image(img, max_bits=mb, **kw)
+    assert (enc.h, enc.w, enc.c, enc.level, enc._encoding_version) == (128, 192, 3, None, "0.0.2")
+    assert enc.max_n == ref["max_n"]
+    assert len(enc.encoded_bytes) == len(ref["encoded_bytes"])
+    if kw.get("color_model") is None:
+        assert enc.encoded_bytes == ref["encoded_bytes"]
+    rec = spiht.decode_image(enc, st)
+    rec_ref = wrapper_ref.decode_image(dict(encoded_bytes=enc.encoded_bytes, h=128, w=192, c=3, max_n=enc.max_n,
+                                            level=None), **kw)
+    assert rec.shape == rec_ref.shape
+    assert np.abs(rec - rec_ref).max() <= 1e-8
+    rec_full_ref = wrapper_ref.decode_image(ref, **kw)
+    assert abs(_psnr(rec, img) - _psnr(rec_full_ref, img)) < 0.05
+
+
+def test_wrapper_api_surface(torch_cuda):
+    import spiht_b200 as spiht
+    from spiht_b200 import spiht_wrapper as sw
+    img = synth_image(3, 64, 64, 2)
+    st = spiht.SpihtSettings()
+    with pytest.raises(ValueError):
+        spiht.encode_image(img[0], st)                       # spiht_wrapper.py:153-154
+    with pytest.raises(ValueError):
+        spiht.encode_image(img, spiht.SpihtSettings(color_model="CIE Lab"))
+    with pytest.raises(ValueError):
+        spiht.encode_image(img, spiht.SpihtSettings(wavelet="db9"))
+    enc = spiht.encode_image(img, st, level=2, max_bits=4096)
+    assert enc.level == 2 and len(enc.encoded_bytes) == 512
+    d = enc.to_dict()
+    assert set(d) == {"encoding_result_" + k for k in
+                      ("encoded_bytes", "h", "w", "c", "max_n", "level", "_encoding_version")}
+    enc2 = spiht.EncodingResult.from_dict(d)
+    assert enc2 == enc
+    bad = spiht.EncodingResult(enc.encoded_bytes, 64, 64, 3, enc.max_n, 2, "0.0.1")
+    with pytest.raises(ValueError):
+        spiht.decode_image(bad, st)                          # spiht_wrapper.py:226-227
+    r = sw.decode_rec_array(enc, st)
+    assert set(r) == {"rec_arr", "slices", "spiht_metadata", "h", "w", "level"}
+    img2 = sw.decode_from_rec_arr(r["rec_arr"], 64, 64, 2, st, slices=r["slices"])
+    assert np.abs(img2 - spiht.decode_image(enc, st)).max() < 1e-12
+    # untruncated: max_bits=None is lossless up to quantisation and the never-coded last row/col
+    enc_full = spiht.encode_image(img, st)
+    rec = spiht.decode_image(enc_full, st)
+    assert _psnr(rec, img) > 40
+
+
+def test_mixed_size_batch(torch_cuda):
+    import spiht_b200 as spiht
+    st = spiht.SpihtSettings()
+    imgs = [synth_image(3, 64, 64, 1), synth_image(3, 96, 64, 2), synth_image(3, 64, 64, 3),
+            synth_image(1, 128, 128, 4)]
+    encs = spiht.encode_images(imgs, st, max_bits=6000)
+    for im, e in zip(imgs, encs):
+        single = spiht.encode_image(im, st, max_bits=6000)
+        assert e == single
+    recs = spiht.decode_images(encs, st)
+    for im, r in zip(imgs, recs):
+        assert r.shape == im.shape

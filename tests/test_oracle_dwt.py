@@ -1,0 +1,80 @@
+"""CPU checks of the float64 DWT / IPT oracle (PyWavelets and colour-science are
+absent from this image: filter identities, perfect reconstruction and band
+geometry are what can be pinned)."""
+import numpy as np
+import pytest
+
+from oracle import dwt_ref as d, ipt_ref, wrapper_ref
+
+
+@pytest.mark.parametrize("name", ["bior2.2", "bior4.4", "bior6.8"])
+def test_filter_identities(name):
+    wv = d.Wavelet(name)
+    assert abs(wv.dec_lo.sum() - 2 ** 0.5) < 1e-12
+    assert abs(wv.rec_lo.sum() - 2 ** 0.5) < 1e-12
+    assert abs(wv.dec_hi.sum()) < 1e-11
+    assert abs(wv.rec_hi.sum()) < 1e-11
+
+
+@pytest.mark.parametrize("name", ["bior2.2", "bior4.4", "bior6.8"])
+@pytest.mark.parametrize("mode", d.MODES)
+def test_perfect_reconstruction_1d(name, mode):
+    rng = np.random.default_rng(0)
+    wv = d.Wavelet(name)
+    for n in (16, 17, 40, 41, 64, 100, 7):
+        x = rng.normal(size=(2, n))
+        lo, hi = d.dwt_axis(x, wv, mode, -1)
+        assert lo.shape[-1] == d.dwt_coeff_len(n, wv.dec_len, mode)
+        r = d.idwt_axis(lo, hi, wv, mode, -1)
+        assert np.abs(r[:, :n] - x).max() < 1e-10
+
+
+def test_geometry_of_the_configs():
+    """coefficient-array sizes of the BASELINE configs"""
+    assert d.get_slices_and_h_w(256, 384, "bior2.2", "reflect", None)[1:] == (277, 405)
+    assert d.wavedecn_shapes_2d(256, 384, "bior2.2")[:2] == (12, 16)
+    assert d.get_slices_and_h_w(1024, 1024, "bior2.2", "reflect", None)[1:] == (1053, 1053)
+    assert d.get_slices_and_h_w(2048, 2048, "bior2.2", "reflect", None)[1:] == (2081, 2081)
+    assert d.get_slices_and_h_w(8192, 8192, "bior6.8", "reflect", None)[1:] == (8321, 8321)
+    assert d.wavedecn_shapes_2d(8192, 8192, "bior6.8")[:2] == (48, 48)
+    assert d.get_slices_and_h_w(1024, 1024, "bior2.2", "periodization", None)[1:] == (1024, 1024)
+
+
+@pytest.mark.parametrize("mode", d.MODES)
+@pytest.mark.parametrize("name", ["bior2.2", "bior4.4"])
+def test_wavedec2_roundtrip_and_layout(name, mode):
+    rng = np.random.default_rng(1)
+    for (h, w) in [(64, 96), (67, 131)]:
+        img = rng.random((3, h, w))
+        co = d.wavedec2(img, name, mode)
+        arr = d.coeffs_to_array(co)
+        sl, eh, ew = d.get_slices_and_h_w(h, w, name, mode, None)
+        assert arr.shape[1:] == (eh, ew)
+        back = d.array_to_coeffs(arr, sl)
+        for a, b in zip(co[1:], back[1:]):
+            for x, y in zip(a, b):
+                assert np.array_equal(x, y)
+        rec = d.waverec2(back, name, mode)
+        assert np.abs(rec[:, :h, :w] - img).max() < 1e-10
+
+
+def test_ipt_roundtrip_close():
+    x = np.random.default_rng(2).random((3, 16, 16))
+    y = ipt_ref.convert(x, "RGB", "IPT")
+    z = ipt_ref.convert(y, "IPT", "RGB")
+    assert np.abs(z - x).max() < 2e-4      # the 4-digit sRGB matrices are not exact inverses
+    with pytest.raises(ValueError):
+        ipt_ref.convert(x, "RGB", "CIE Lab")
+
+
+def test_wrapper_ref_roundtrip():
+    from conftest import synth_image
+    img = synth_image(3, 64, 96, 0)
+    enc = wrapper_ref.encode_image(img, max_bits=64 * 96)
+    assert len(enc["encoded_bytes"]) == 64 * 96 // 8
+    rec = wrapper_ref.decode_image(enc)
+    assert rec.shape == img.shape
+    mse1 = np.mean((rec - img) ** 2)
+    rec_full = wrapper_ref.decode_image(wrapper_ref.encode_image(img))
+    mse_full = np.mean((rec_full - img) ** 2)
+    assert mse_full < 1e-3 and mse_full < mse1 < 0.05
