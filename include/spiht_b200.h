@@ -88,6 +88,15 @@ int spihtb_sync(spihtb_ctx *ctx);
 /* number of kernels this context has launched so far (bench.py `gpu_launches`) */
 int64_t spihtb_launch_count(spihtb_ctx *ctx);
 
+/* ---- stage timers (CUDA events on the context's stream; used by bench.py for the roofline) ----
+ * Stages: 0 forward DWT level 1, 1 forward remaining levels (+ colour, gap fill), 2 pyramid base pass,
+ * 3 pyramid upper rings + LL roots, 4 SPIHT encode kernel, 5 SPIHT decode (zero fill + kernel),
+ * 6 inverse DWT coarse levels, 7 inverse DWT finest level (+ colour). */
+#define SPIHTB_NSTAGES 8
+int spihtb_profile_enable(spihtb_ctx *ctx, int enable);
+/* total milliseconds and number of recorded intervals per stage since the last reset; synchronises */
+int spihtb_profile_read(spihtb_ctx *ctx, double *ms_out, int64_t *count_out, int reset);
+
 /* ---- geometry (host only; replaces spiht_wrapper.py:92-139, pywt.wavedecn_shapes,
  *      and pywt's level=None -> dwtn_max_level) ----------------------------- */
 /* level < 0 means "max level" (Python level=None). */

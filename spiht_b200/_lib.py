@@ -48,6 +48,7 @@ EXPORTS = (
     "spihtb_sync", "spihtb_launch_count", "spihtb_plan", "spihtb_encode", "spihtb_decode",
     "spihtb_encode_coeffs", "spihtb_decode_coeffs", "spihtb_forward", "spihtb_inverse",
     "spihtb_encode_images", "spihtb_decode_images", "spihtb_stream_bound",
+    "spihtb_profile_enable", "spihtb_profile_read",
 )
 
 
@@ -89,10 +90,10 @@ def lib():
         L.spihtb_decode_images.argtypes = [vp, vp, u64, vp, vp, i32, i32, P(Geom), i32, P(dbl), dbl, vp, vp, i32]
         L.spihtb_stream_bound.argtypes = [i32, i32, i32, i32, i32]
         L.spihtb_stream_bound.restype = u64
+        L.spihtb_profile_enable.argtypes = [vp, ctypes.c_int]
+        L.spihtb_profile_read.argtypes = [vp, P(dbl), P(ctypes.c_int64), ctypes.c_int]
         for name in EXPORTS:
-            f = getattr(L, name)
-            if f.restype is ctypes.c_int and name not in ("spihtb_version",):
-                pass
+            getattr(L, name)   # every declared symbol must resolve
         _lib = L
         return _lib
 
@@ -134,6 +135,20 @@ class Context:
 
     def launch_count(self):
         return int(lib().spihtb_launch_count(self._h))
+
+    STAGES = ("dwt_fwd_level1", "dwt_fwd_rest", "pyramid_base", "pyramid_rest", "spiht_encode", "spiht_decode",
+              "dwt_inv_coarse", "dwt_inv_level1")
+
+    def profile(self, enable=True):
+        check(lib().spihtb_profile_enable(self._h, int(bool(enable))))
+
+    def profile_read(self, reset=True):
+        """{stage: (total_ms, intervals)} since the last reset (synchronises)"""
+        n = len(self.STAGES)
+        ms = (ctypes.c_double * n)()
+        cnt = (ctypes.c_int64 * n)()
+        check(lib().spihtb_profile_read(self._h, ms, cnt, int(bool(reset))))
+        return {name: (ms[i], int(cnt[i])) for i, name in enumerate(self.STAGES)}
 
     def close(self):
         if self._h:

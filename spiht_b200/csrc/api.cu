@@ -147,7 +147,73 @@ int spihtb_ctx::ensure(DevBuf &b, size_t bytes)
     return SPIHTB_OK;
 }
 
+void spihtb_ctx::harvest(int s, bool all)
+{
+    StageProf &p = prof[s];
+    // intervals [harvested, recorded) are pending; keep at most PROF_RING - 1 outstanding
+    while (p.harvested < p.recorded && (all || p.recorded - p.harvested >= PROF_RING)) {
+        const int slot = (int)(p.harvested % PROF_RING);
+        float ms = 0.f;
+        if (cudaEventSynchronize(p.b[slot]) == cudaSuccess && cudaEventElapsedTime(&ms, p.a[slot], p.b[slot]) == cudaSuccess)
+            p.acc_ms += ms;
+        p.harvested++;
+    }
+}
+
+void spihtb_ctx::stage_begin(int s)
+{
+    if (!profiling) return;
+    StageProf &p = prof[s];
+    if (!p.made) {
+        for (int i = 0; i < PROF_RING; ++i) {
+            cudaEventCreate(&p.a[i]);
+            cudaEventCreate(&p.b[i]);
+        }
+        p.made = true;
+    }
+    harvest(s, false);
+    cudaEventRecord(p.a[p.recorded % PROF_RING], stream);
+}
+
+void spihtb_ctx::stage_end(int s)
+{
+    if (!profiling) return;
+    StageProf &p = prof[s];
+    cudaEventRecord(p.b[p.recorded % PROF_RING], stream);
+    p.recorded++;
+}
+
 extern "C" {
+
+int spihtb_profile_enable(spihtb_ctx *ctx, int enable)
+{
+    if (!ctx) {
+        set_error("ctx is null");
+        return SPIHTB_EINVAL;
+    }
+    ctx->profiling = enable != 0;
+    return SPIHTB_OK;
+}
+
+int spihtb_profile_read(spihtb_ctx *ctx, double *ms_out, int64_t *count_out, int reset)
+{
+    if (!ctx || !ms_out || !count_out) {
+        set_error("null pointer");
+        return SPIHTB_EINVAL;
+    }
+    SPIHTB_CUDA_CHECK(cudaSetDevice(ctx->device));
+    for (int s = 0; s < SPIHTB_NSTAGES; ++s) {
+        if (ctx->prof[s].made) ctx->harvest(s, true);
+        ms_out[s] = ctx->prof[s].acc_ms;
+        count_out[s] = ctx->prof[s].harvested;
+        if (reset) {
+            ctx->prof[s].acc_ms = 0.0;
+            ctx->prof[s].recorded = 0;
+            ctx->prof[s].harvested = 0;
+        }
+    }
+    return SPIHTB_OK;
+}
 
 int spihtb_version(void) { return SPIHTB_VERSION; }
 const char *spihtb_last_error(void) { return g_err; }
@@ -189,6 +255,12 @@ int spihtb_destroy(spihtb_ctx *ctx)
     DevBuf *bufs[] = {&ctx->pyr, &ctx->lists, &ctx->misc, &ctx->tmpa, &ctx->tmpb, &ctx->io, &ctx->io2};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
+    for (int s = 0; s < SPIHTB_NSTAGES; ++s)
+        if (ctx->prof[s].made)
+            for (int i = 0; i < PROF_RING; ++i) {
+                cudaEventDestroy(ctx->prof[s].a[i]);
+                cudaEventDestroy(ctx->prof[s].b[i]);
+            }
     delete ctx;
     return SPIHTB_OK;
 }

@@ -30,6 +30,16 @@ struct DevBuf {
 
 }  // namespace spihtb
 
+namespace spihtb {
+constexpr int PROF_RING = 64;
+struct StageProf {
+    cudaEvent_t a[PROF_RING], b[PROF_RING];
+    bool made = false;
+    int64_t recorded = 0, harvested = 0;
+    double acc_ms = 0.0;
+};
+}  // namespace spihtb
+
 struct spihtb_ctx {
     int device = 0;
     int sm_count = 148;
@@ -43,7 +53,12 @@ struct spihtb_ctx {
     spihtb::DevBuf io;       // staging for the host-pointer entry points
     spihtb::DevBuf io2;
     std::vector<uint8_t> host_out;  // spihtb_encode result
+    bool profiling = false;
+    spihtb::StageProf prof[SPIHTB_NSTAGES];
     int ensure(spihtb::DevBuf &b, size_t bytes);
+    void stage_begin(int s);
+    void stage_end(int s);
+    void harvest(int s, bool all);
 };
 
 namespace spihtb {

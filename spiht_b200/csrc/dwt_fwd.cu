@@ -265,8 +265,11 @@ int launch_forward(spihtb_ctx *ctx, const void *pixels, const XformArgs &x, int3
         k.tiles_y = (k.bh + FW_TH - 1) / FW_TH;
         for (int c = 0; c < 8; ++c) k.scale[c] = x.scale[c];
         k.q = x.q;
+        if (l == 0) ctx->stage_begin(0);
+        if (l == 1) ctx->stage_begin(1);
         rc = src_is_f64 ? launch_level_w<double>(ctx, g.wavelet, k, nz) : launch_level_w<float>(ctx, g.wavelet, k, nz);
         if (rc) return rc;
+        if (l == 0) ctx->stage_end(0);
         src = k.dst_ll;
         src_is_f64 = true;
     }
@@ -285,10 +288,12 @@ int launch_forward(spihtb_ctx *ctx, const void *pixels, const XformArgs &x, int3
             gk.sw[l] = g.off_w[l];
             any |= (gk.sh[l] > gk.bh[l]) || (gk.sw[l] > gk.bw[l]);
         }
+        if (L == 1) ctx->stage_begin(1);
         if (any) {
             gap_fill_kernel<<<dim3(8, std::min(nz, 65535)), 256, 0, ctx->stream>>>(gk);
             ctx->launches++;
         }
+        ctx->stage_end(1);
     }
     SPIHTB_CUDA_CHECK(cudaGetLastError());
     return SPIHTB_OK;

@@ -265,8 +265,13 @@ int launch_inverse(spihtb_ctx *ctx, const int32_t *coeffs, const XformArgs &x, v
 
     const double *src = nullptr;
     int a_h = 0, a_w = 0;
+    if (L > 1) ctx->stage_begin(6);
     for (int l = L - 1; l >= 0; --l) {
         InvK k;
+        if (l == 0) {
+            if (L > 1) ctx->stage_end(6);
+            ctx->stage_begin(7);
+        }
         k.src_a = src;
         k.a_h = a_h;
         k.a_w = a_w;
@@ -322,6 +327,7 @@ int launch_inverse(spihtb_ctx *ctx, const int32_t *coeffs, const XformArgs &x, v
                                                                    static_cast<double *>(pixels_out), img, x.B, mi);
         ctx->launches++;
     }
+    ctx->stage_end(7);
     SPIHTB_CUDA_CHECK(cudaGetLastError());
     return SPIHTB_OK;
 }

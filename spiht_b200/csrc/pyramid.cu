@@ -141,9 +141,12 @@ int launch_pyramid(spihtb_ctx *ctx, const int32_t *coeffs, int B, int C, int H, 
             set_error("pyramid grid too large");
             return SPIHTB_ESHAPE;
         }
+        ctx->stage_begin(2);
         pyr_base_kernel<<<(unsigned)nb, dim3(32, 8), 0, st>>>(coeffs, H, W, NH, NW, gx, gy, C, dp, lp, maxabs);
         ctx->launches++;
+        ctx->stage_end(2);
     }
+    ctx->stage_begin(3);
     for (int t = 2;; ++t) {
         const long long s = 1LL << (t - 1);
         const int RH = (int)((NH + s - 1) / s), RW = (int)((NW + s - 1) / s);
@@ -160,6 +163,7 @@ int launch_pyramid(spihtb_ctx *ctx, const int32_t *coeffs, int B, int C, int H, 
         pyr_ll_kernel<<<nb, 256, 0, st>>>(coeffs, H, W, NH, NW, ll_h, ll_w, nz, dp, dpll, lpll);
         ctx->launches++;
     }
+    ctx->stage_end(3);
     SPIHTB_CUDA_CHECK(cudaGetLastError());
     return SPIHTB_OK;
 }

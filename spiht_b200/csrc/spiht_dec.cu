@@ -16,6 +16,14 @@
 // does, so pad bits and duplicated coordinates behave identically.  Decoding
 // stops at the first bit position >= 8 * nbytes (pop_bit!, :314-325): an
 // action is applied only if every bit it needs lies below that.
+//
+// Odd LL sizes: the reference's LL-root offspring rule (:50-62) then gives some
+// cells two parents, so whole subtrees sit in the lists twice and two list
+// entries write the same cell.  Those writes must land in list order (pad bits
+// or foreign streams can make the two entries disagree), so writes to cells of
+// duplicated subtrees are queued in list order (ordered compaction through the
+// CTA scan) and applied by one thread after each parallel step.  Even LL sizes
+// (all BASELINE configs) never take that path.
 #include <algorithm>
 
 #include "common.cuh"
@@ -27,6 +35,7 @@ constexpr int DEC_NT = 256;
 constexpr int DEC_CH = 8192;  // list entries per chain round
 constexpr int DEC_EV = 1024;  // event buffer
 constexpr int DEC_SLACK = 8 * DEC_NT + 64;
+constexpr int DEC_DQ = 4 * DEC_NT;  // ordered write queue (odd LL sizes only)
 
 struct DecK {
     const uint32_t *in;
@@ -61,6 +70,20 @@ struct BitRow {
     }
     __device__ __forceinline__ uint32_t bit(uint64_t p) const { return (word(p >> 5) >> (p & 31)) & 1u; }
 };
+
+// Is (y,x) inside a subtree that the reference's lists hold twice?  Cells with
+// two LL-root parents: row ll_h (odd ll_h) x cols [ll_w, 2 ll_w) and col ll_w
+// (odd ll_w) x rows [ll_h, 2 ll_h); their descendants follow the dyadic rule.
+__device__ __forceinline__ bool in_dup_subtree(uint32_t y, uint32_t x, uint32_t ll_h, uint32_t ll_w)
+{
+    for (int t = 0; t < 32; ++t) {
+        const uint32_t yy = y >> t, xx = x >> t;
+        if (yy < ll_h && xx < ll_w) return false;
+        if ((ll_h & 1u) && yy == ll_h && xx >= ll_w && xx < 2 * ll_w) return true;
+        if ((ll_w & 1u) && xx == ll_w && yy >= ll_h && yy < 2 * ll_h) return true;
+    }
+    return false;
+}
 
 struct ChainState {
     uint64_t p;      // next bit position
@@ -122,6 +145,32 @@ __device__ void run_chain(const BitRow &br, bool lis_mode, const uint32_t *tmask
     st.ended = p >= br.nbits ? 1u : 0u;
 }
 
+// set_bit (encoder_decoder.rs:14-29): set / clear bit n of the magnitude, keep the sign
+__device__ __forceinline__ void refine_cell(int32_t *cell, int n, uint32_t bit)
+{
+    const int32_t x = *cell;
+    const uint32_t m = 1u << n;
+    uint32_t mag = absu(x);
+    mag = bit ? (mag | m) : (mag & ~m);
+    *cell = x >= 0 ? (int32_t)mag : -(int32_t)mag;
+}
+
+// One thread: apply queued writes in list order.
+__device__ void apply_queue(const uint2 *dq, uint32_t cnt, const KeyFmt &kf, int32_t *rec, uint32_t H, uint32_t W,
+                            int n)
+{
+    for (uint32_t q = 0; q < cnt; ++q) {
+        const uint2 op = dq[q];
+        uint32_t k, i, j;
+        key_unpack(kf, op.x, k, i, j);
+        int32_t *cell = rec + ((size_t)k * H + i) * W + j;
+        if (op.x >> 31)
+            refine_cell(cell, n, op.y);
+        else
+            *cell = (int32_t)op.y;
+    }
+}
+
 __global__ void __launch_bounds__(DEC_NT) spiht_decode_kernel(const DecK p)
 {
     __shared__ uint32_t s_tmask[DEC_CH / 32];
@@ -130,6 +179,7 @@ __global__ void __launch_bounds__(DEC_NT) spiht_decode_kernel(const DecK p)
     __shared__ uint64_t s_wtot[DEC_NT / 32];
     __shared__ ChainState s_st;
     __shared__ int s_img;
+    __shared__ uint2 s_dq[DEC_DQ];  // {cell key | refine flag << 31, value or bit}
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const KeyFmt kf = p.kf;
@@ -139,6 +189,7 @@ __global__ void __launch_bounds__(DEC_NT) spiht_decode_kernel(const DecK p)
     uint32_t *R = p.lis + (size_t)blockIdx.x * 3 * p.lis_cap;
     uint32_t *G0 = R + p.lis_cap;
     uint32_t *G1 = G0 + p.lis_cap;
+    const bool has_dups = ((ll_h | ll_w) & 1u) != 0;
 
     for (;;) {
         if (tid == 0) s_img = (int)atomicAdd(p.counter, 1u);
@@ -205,15 +256,31 @@ __global__ void __launch_bounds__(DEC_NT) spiht_decode_kernel(const DecK p)
                         const bool end_now = s_st.ended != 0;
                         pos = s_st.p;
                         // events: newly significant pixels, in list order
-                        for (uint32_t r = tid; r < nev; r += DEC_NT) {
-                            const uint2 ev = s_ev[r];
-                            const uint64_t ps = p_base + ev.y + 1;  // sign bit
-                            if (ps < br.nbits) {
-                                const uint32_t key = lip[ebase + ev.x];
-                                uint32_t k, i, j;
-                                key_unpack(kf, key, k, i, j);
-                                rec[((size_t)k * H + i) * W + j] = br.bit(ps) ? basev : -basev;
-                                lsp[lsp_len + r] = key;
+                        for (uint32_t rb = 0; rb < nev; rb += DEC_NT) {
+                            const uint32_t r = rb + tid;
+                            bool defer = false;
+                            uint32_t key = 0;
+                            int32_t val = 0;
+                            if (r < nev) {
+                                const uint2 ev = s_ev[r];
+                                const uint64_t ps = p_base + ev.y + 1;  // sign bit
+                                if (ps < br.nbits) {
+                                    key = lip[ebase + ev.x];
+                                    uint32_t k, i, j;
+                                    key_unpack(kf, key, k, i, j);
+                                    val = br.bit(ps) ? basev : -basev;
+                                    defer = has_dups && in_dup_subtree(i, j, ll_h, ll_w);
+                                    if (!defer) rec[((size_t)k * H + i) * W + j] = val;
+                                    lsp[lsp_len + r] = key;
+                                }
+                            }
+                            if (has_dups) {
+                                uint64_t tot;
+                                const uint64_t ex = block_exscan<DEC_NT>(defer ? 1ull : 0ull, s_wtot, tot);
+                                if (defer) s_dq[(uint32_t)ex] = make_uint2(key, (uint32_t)val);
+                                __syncthreads();
+                                if (tid == 0) apply_queue(s_dq, (uint32_t)tot, kf, rec, H, W, n);
+                                __syncthreads();
                             }
                         }
                         lsp_len += nev;
@@ -284,6 +351,7 @@ __global__ void __launch_bounds__(DEC_NT) spiht_decode_kernel(const DecK p)
                                 const bool valid = r < nev;
                                 uint32_t key = 0, k = 0, i = 0, j = 0, ci = 0, cj = 0;
                                 uint32_t nlsp = 0, nlip = 0, nnext = 0, sigmask = 0, sgnmask = 0, nread = 0;
+                                uint32_t ndef = 0, defmask = 0;
                                 bool isA = false, has = false;
                                 if (valid) {
                                     const uint2 ev = s_ev[r];
@@ -317,24 +385,37 @@ __global__ void __launch_bounds__(DEC_NT) spiht_decode_kernel(const DecK p)
                                             }
                                         }
                                         if (!cut && has_desc_past_offspring(i, j, H, W)) nnext = 1;
+                                        if (has_dups && nlsp) {
+                                            for (uint32_t c4 = 0; c4 < nread; ++c4)
+                                                if ((sigmask & (1u << c4)) &&
+                                                    in_dup_subtree(ci + (c4 >> 1), cj + (c4 & 1), ll_h, ll_w)) {
+                                                    defmask |= 1u << c4;
+                                                    ++ndef;
+                                                }
+                                        }
                                     } else {
                                         nnext = has ? 4 : 0;
                                     }
                                 }
-                                const uint64_t pack = (uint64_t)nlsp | ((uint64_t)nlip << 16) | ((uint64_t)nnext << 32);
+                                const uint64_t pack = (uint64_t)nlsp | ((uint64_t)nlip << 16) | ((uint64_t)nnext << 32) |
+                                                      ((uint64_t)ndef << 48);
                                 uint64_t tot;
                                 const uint64_t ex = block_exscan<DEC_NT>(pack, s_wtot, tot);
                                 if (valid) {
                                     uint32_t os = lsp_len + (uint32_t)(ex & 0xffff);
                                     uint32_t oi = lip_len + (uint32_t)((ex >> 16) & 0xffff);
-                                    const uint32_t on = nxt_len + (uint32_t)(ex >> 32);
+                                    const uint32_t on = nxt_len + (uint32_t)((ex >> 32) & 0xffff);
+                                    uint32_t od = (uint32_t)(ex >> 48);
                                     if (isA) {
                                         for (uint32_t c4 = 0; c4 < nread; ++c4) {
                                             const uint32_t y = ci + (c4 >> 1), x = cj + (c4 & 1);
                                             const uint32_t ck = key_pack(kf, k, y, x);
                                             if (sigmask & (1u << c4)) {
-                                                rec[((size_t)k * H + y) * W + x] =
-                                                    (sgnmask & (1u << c4)) ? basev : -basev;
+                                                const int32_t val = (sgnmask & (1u << c4)) ? basev : -basev;
+                                                if (defmask & (1u << c4))
+                                                    s_dq[od++] = make_uint2(ck, (uint32_t)val);
+                                                else
+                                                    rec[((size_t)k * H + y) * W + x] = val;
                                                 lsp[os++] = ck;
                                             } else {
                                                 lip[oi++] = ck;
@@ -349,7 +430,12 @@ __global__ void __launch_bounds__(DEC_NT) spiht_decode_kernel(const DecK p)
                                 }
                                 lsp_len += (uint32_t)(tot & 0xffff);
                                 lip_len += (uint32_t)((tot >> 16) & 0xffff);
-                                nxt_len += (uint32_t)(tot >> 32);
+                                nxt_len += (uint32_t)((tot >> 32) & 0xffff);
+                                if (has_dups) {
+                                    __syncthreads();
+                                    if (tid == 0) apply_queue(s_dq, (uint32_t)(tot >> 48), kf, rec, H, W, n);
+                                    __syncthreads();
+                                }
                             }
                             // retained sets [eprev, ecur)
                             for (uint32_t cb = eprev; cb < ecur; cb += DEC_NT) {
@@ -379,18 +465,35 @@ __global__ void __launch_bounds__(DEC_NT) spiht_decode_kernel(const DecK p)
             if (ended) break;
 
             // ================= refinement (encoder_decoder.rs:439-444)
-            for (uint32_t e = tid; e < lsp_len0; e += DEC_NT) {
-                const uint64_t q = pos + e;
-                if (q < br.nbits) {
-                    const uint32_t key = lsp[e];
-                    uint32_t k, i, j;
-                    key_unpack(kf, key, k, i, j);
-                    int32_t *cell = rec + ((size_t)k * H + i) * W + j;
-                    const int32_t x = *cell;
-                    const uint32_t m = 1u << n;
-                    uint32_t mag = absu(x);
-                    mag = br.bit(q) ? (mag | m) : (mag & ~m);
-                    *cell = x >= 0 ? (int32_t)mag : -(int32_t)mag;
+            if (!has_dups) {
+                for (uint32_t e = tid; e < lsp_len0; e += DEC_NT) {
+                    const uint64_t q = pos + e;
+                    if (q < br.nbits) {
+                        uint32_t k, i, j;
+                        key_unpack(kf, lsp[e], k, i, j);
+                        refine_cell(rec + ((size_t)k * H + i) * W + j, n, br.bit(q));
+                    }
+                }
+            } else {
+                for (uint32_t eb = 0; eb < lsp_len0; eb += DEC_NT) {
+                    const uint32_t e = eb + tid;
+                    const uint64_t q = pos + e;
+                    bool defer = false;
+                    uint32_t key = 0, bit = 0;
+                    if (e < lsp_len0 && q < br.nbits) {
+                        key = lsp[e];
+                        bit = br.bit(q);
+                        uint32_t k, i, j;
+                        key_unpack(kf, key, k, i, j);
+                        defer = in_dup_subtree(i, j, ll_h, ll_w);
+                        if (!defer) refine_cell(rec + ((size_t)k * H + i) * W + j, n, bit);
+                    }
+                    uint64_t tot;
+                    const uint64_t ex = block_exscan<DEC_NT>(defer ? 1ull : 0ull, s_wtot, tot);
+                    if (defer) s_dq[(uint32_t)ex] = make_uint2(key | 0x80000000u, bit);
+                    __syncthreads();
+                    if (tid == 0) apply_queue(s_dq, (uint32_t)tot, kf, rec, H, W, n);
+                    __syncthreads();
                 }
             }
             pos += lsp_len0;
@@ -444,10 +547,12 @@ int launch_decode(spihtb_ctx *ctx, const DecArgs &a)
     k.lsp = k.lip + (size_t)slots * pix_cap;
     k.counter = static_cast<unsigned int *>(ctx->misc.p);
 
+    ctx->stage_begin(5);
     SPIHTB_CUDA_CHECK(cudaMemsetAsync(a.out, 0, sizeof(int32_t) * (size_t)a.B * a.C * a.H * a.W, ctx->stream));
     SPIHTB_CUDA_CHECK(cudaMemsetAsync(k.counter, 0, sizeof(unsigned int), ctx->stream));
     spiht_decode_kernel<<<slots, DEC_NT, 0, ctx->stream>>>(k);
     ctx->launches++;
+    ctx->stage_end(5);
     SPIHTB_CUDA_CHECK(cudaGetLastError());
     return SPIHTB_OK;
 }

@@ -359,8 +359,10 @@ int launch_encode(spihtb_ctx *ctx, const EncArgs &a)
     k.lsp = reinterpret_cast<uint32_t *>(base + (size_t)slots * (lis_cap * 3 * sizeof(uint2) + pix_cap * 4));
     k.counter = static_cast<unsigned int *>(ctx->misc.p);
     SPIHTB_CUDA_CHECK(cudaMemsetAsync(k.counter, 0, sizeof(unsigned int), ctx->stream));
+    ctx->stage_begin(4);
     spiht_encode_kernel<<<slots, ENC_NT, 0, ctx->stream>>>(k);
     ctx->launches++;
+    ctx->stage_end(4);
     SPIHTB_CUDA_CHECK(cudaGetLastError());
     return SPIHTB_OK;
 }

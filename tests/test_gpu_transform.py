@@ -203,7 +203,7 @@ def test_wrapper_api_surface(torch_cuda):
     # untruncated: max_bits=None is lossless up to quantisation and the never-coded last row/col
     enc_full = spiht.encode_image(img, st)
     rec = spiht.decode_image(enc_full, st)
-    assert _psnr(rec, img) > 40
+    assert _psnr(rec, img) > 36     # truncating quantiser at q=50: error variance (1/50)^2/3 -> ~38.8 dB
 
 
 def test_mixed_size_batch(torch_cuda):
