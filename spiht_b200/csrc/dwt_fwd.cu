@@ -3,10 +3,10 @@
 // Replaces spiht_wrapper.py:158-172 (colour.convert, pywt.wavedec2,
 // pywt.coeffs_to_array, channel_mults, quantize).
 //
-// One kernel per level.  A CTA produces a 32x32 tile of each of the four bands
-// of one (image, channel) plane: it stages the (64+F-2)^2 input window in
-// shared memory with the boundary rule applied on load, filters along axis -2
-// then along axis -1 (PyWavelets' order) in float64, and writes
+// One kernel per level.  A warp streams a strip of one (image, channel) plane
+// (see dwt_fwd_task): filters along axis -2 in registers as it walks down the
+// rows, then along axis -1 through warp shuffles (PyWavelets' order, float64),
+// and writes
 //   - the three detail bands, scaled and truncated to int32, straight to their
 //     final place in the coefficient array, and
 //   - the approximation band to a float64 scratch plane for the next level
@@ -21,7 +21,7 @@
 
 namespace spihtb {
 
-constexpr int FW_TH = 32, FW_TW = 32, FW_NT = 256;
+constexpr int FW_WARPS = 4;  // warps (= independent tasks) per CTA
 
 struct FwdK {
     const void *src;        // [nz][src_h][src_w] planes of Tin
@@ -31,7 +31,9 @@ struct FwdK {
     int32_t *coeffs;        // [nz][Hc][Wc]
     int Hc, Wc, sh, sw;     // detail block offsets of this level
     int mode, C, last;
-    int tiles_x, tiles_y;
+    int tiles_x, tiles_y;   // strips across, row chunks down
+    int RH;                 // output rows per chunk
+    long long ntasks;       // nz * tiles_y * tiles_x
     double scale[8];
     double q;
 };
@@ -39,85 +41,197 @@ struct FwdK {
 // spiht_wrapper.py:9-11,167-172: ((m_c * x) * q).astype(int32), truncation toward zero
 __device__ __forceinline__ int32_t quantise(double x, double m, double q) { return __double2int_rz((m * x) * q); }
 
-template <typename Tin, int WID>
-__global__ void __launch_bounds__(FW_NT) dwt_fwd_level_kernel(const FwdK p)
+template <typename T>
+struct Pair;
+template <>
+struct Pair<float> {
+    using type = float2;
+};
+template <>
+struct Pair<double> {
+    using type = double2;
+};
+
+// One warp = one task: a strip of NOUT = 32 - (F/2 - 1) output columns by RH output
+// rows of one (image, channel) plane.  Lane l owns the input column pair
+// (E, O) = (x[2m], x[2m+1]), m = k0 - (F/2-1) + l, and walks down the rows:
+//   axis -2: a register window of F rows of its two columns gives the row-filtered
+//            (lo, hi) pair of both columns -- no exchange needed;
+//   axis -1: out[k] = sum_u f[2u] O[k-u] + f[2u+1] E[k-u] takes the neighbours'
+//            values by warp shuffle (lanes l-1 .. l-(F/2-1)); lanes >= F/2-1 own an
+//            output column.
+// No shared memory and no barrier: warps are independent, every input sample is
+// read from HBM once per strip (the F-2 halo columns hit L1/L2), loads are
+// prefetched PD row pairs ahead, each lane writes its four band values
+// (approximation as float64 scratch for the next level, details quantised).
+template <typename Tin, int WID, bool INSIDE>
+__device__ __forceinline__ void dwt_fwd_task(const FwdK &p, int tx, int ty, int z)
 {
     constexpr int F = Wav<WID>::F;
-    constexpr int IH = 2 * FW_TH + F - 2, IW = 2 * FW_TW + F - 2, IW2 = IW / 2;
-    extern __shared__ __align__(16) unsigned char smem[];
-    Tin *s_in = reinterpret_cast<Tin *>(smem);  // [IH][IW]
-    double *s_v = reinterpret_cast<double *>(smem + ((IH * IW * sizeof(Tin) + 15) / 16) * 16);  // [2][TH][2][IW2]
+    constexpr int HF = F / 2;
+    constexpr int NOUT = 32 - (HF - 1);
+    constexpr int PD = (HF % 3 == 0) ? 3 : HF;  // prefetch distance in row pairs; divides HF
+    using Tin2 = typename Pair<Tin>::type;
+    const int lane = threadIdx.x & 31;
+    const int src_h = p.src_h, src_w = p.src_w, mode = p.mode;
+    const int sft = mode == SPIHTB_MODE_PERIODIZATION ? (HF - 1) : 0;  // even for every supported wavelet
+    const int k0 = tx * NOUT, r0 = ty * p.RH;
+    const int nrows = min(p.RH, p.bh - r0);
+    const int k = k0 - (HF - 1) + lane;  // this lane's pair index = its output column
+    const int gcE = 2 * k + sft;
+    const int gr0 = 2 * r0 - (F - 2) + sft;
 
-    const int tid = threadIdx.x;
-    uint32_t bid = blockIdx.x;
-    const int tx = bid % p.tiles_x;
-    bid /= p.tiles_x;
-    const int ty = bid % p.tiles_y;
-    const int z = bid / p.tiles_y;
+    const Tin *plane = static_cast<const Tin *>(p.src) + (size_t)z * src_h * src_w;
+    // whole strip inside the plane and rows pair-aligned: one vector load per row
+    const int gc_first = 2 * (k0 - (HF - 1)) + sft;
+    const bool vec = gc_first >= 0 && gc_first + 63 < src_w && (src_w & 1) == 0 &&
+                     (reinterpret_cast<uintptr_t>(plane) & (2 * sizeof(Tin) - 1)) == 0;
+    const int colE = vec ? gcE : ext_index(gcE, src_w, mode);
+    const int colO = vec ? gcE + 1 : ext_index(gcE + 1, src_w, mode);
 
-    const int r0 = ty * FW_TH, c0 = tx * FW_TW;
-    const int shift = p.mode == SPIHTB_MODE_PERIODIZATION ? (F / 2 - 1) : 0;
-    const int gr0 = 2 * r0 - (F - 2) + shift, gc0 = 2 * c0 - (F - 2) + shift;
-
-    const Tin *src = static_cast<const Tin *>(p.src) + (size_t)z * p.src_h * p.src_w;
-    for (int idx = tid; idx < IH * IW; idx += FW_NT) {
-        const int li = idx / IW, lj = idx - li * IW;
-        const int gi = ext_index(gr0 + li, p.src_h, p.mode);
-        const int gj = ext_index(gc0 + lj, p.src_w, p.mode);
-        s_in[idx] = src[(size_t)gi * p.src_w + gj];
-    }
-    __syncthreads();
-
-    // axis -2: rows.  local input row of tap j for output row r: 2r + F-1 - j
-    for (int idx = tid; idx < FW_TH * IW; idx += FW_NT) {
-        const int r = idx / IW, x = idx - r * IW;
-        double lo = 0.0, hi = 0.0;
-#pragma unroll
-        for (int j = 0; j < F; ++j) {
-            const double v = (double)s_in[(2 * r + F - 1 - j) * IW + x];
-            if (Wav<WID>::dec_lo(j) != 0.0) lo = fma(Wav<WID>::dec_lo(j), v, lo);
-            if (wav_dec_hi<WID>(j) != 0.0) hi = fma(wav_dec_hi<WID>(j), v, hi);
+    auto load_row = [&](int li, Tin &e, Tin &o) {
+        const int gi = INSIDE ? gr0 + li : ext_index(gr0 + li, src_h, mode);
+        const Tin *row = plane + (size_t)gi * src_w;
+        if (vec) {
+            const Tin2 v = __ldg(reinterpret_cast<const Tin2 *>(row + colE));
+            e = v.x;
+            o = v.y;
+        } else {
+            e = __ldg(row + colE);
+            o = __ldg(row + colO);
         }
-        const int o = (r * 2 + (x & 1)) * IW2 + (x >> 1);
-        s_v[o] = lo;
-        s_v[FW_TH * IW + o] = hi;
-    }
-    __syncthreads();
+    };
 
-    // axis -1: columns, then write
+    // local row li of the chunk lives in window slot li % F; output row i needs rows 2i .. 2i+F-1
+    double wE[F], wO[F];
+#pragma unroll
+    for (int t = 0; t < F - 2; ++t) {
+        Tin e, o;
+        load_row(t, e, o);
+        wE[t] = (double)e;
+        wO[t] = (double)o;
+    }
+    Tin qE[PD][2], qO[PD][2];
+#pragma unroll
+    for (int s = 0; s < PD; ++s) {
+        qE[s][0] = qE[s][1] = qO[s][0] = qO[s][1] = (Tin)0;
+        if (s < nrows) {
+            load_row(F - 2 + 2 * s, qE[s][0], qO[s][0]);
+            load_row(F - 1 + 2 * s, qE[s][1], qO[s][1]);
+        }
+    }
+
     const int zc = z % p.C;
     const double m = p.scale[zc], q = p.q;
-    int32_t *cz = p.coeffs + (size_t)z * p.Hc * p.Wc;
-    for (int idx = tid; idx < FW_TH * FW_TW; idx += FW_NT) {
-        const int r = idx / FW_TW, c = idx - r * FW_TW;
-        double aa = 0.0, ad = 0.0, da = 0.0, dd = 0.0;
+    const bool out_active = lane >= HF - 1 && k < p.bw;
+    const int Wc = p.Wc;
+    int32_t *cz = p.coeffs + (size_t)z * p.Hc * Wc;
+    int32_t *p_aa = cz + (size_t)r0 * Wc + k;           // LL corner (last level only)
+    int32_t *p_ad = p_aa + p.sw;                        // rows lo, cols hi: top right
+    int32_t *p_da = cz + (size_t)(p.sh + r0) * Wc + k;  // rows hi, cols lo: bottom left
+    int32_t *p_dd = p_da + p.sw;
+    const bool ll_scratch = !p.last;
+    double *p_ll = ll_scratch ? p.dst_ll + ((size_t)z * p.bh + r0) * p.bw + k : nullptr;
+    const int bw = p.bw;
+
+    for (int rb = 0; rb < nrows; rb += HF) {
 #pragma unroll
-        for (int j = 0; j < F; ++j) {
-            constexpr int dummy = 0;
-            (void)dummy;
-            const int col = F - 1 - j;  // + 2c
-            const int o = (r * 2 + (col & 1)) * IW2 + c + (col >> 1);
-            const double vlo = s_v[o], vhi = s_v[FW_TH * IW + o];
-            if (Wav<WID>::dec_lo(j) != 0.0) {
-                aa = fma(Wav<WID>::dec_lo(j), vlo, aa);
-                da = fma(Wav<WID>::dec_lo(j), vhi, da);
+        for (int u = 0; u < HF; ++u) {
+            const int i = rb + u;
+            if (i < nrows) {
+                const int slot = u % PD;
+                wE[(2 * u + F - 2) % F] = (double)qE[slot][0];
+                wO[(2 * u + F - 2) % F] = (double)qO[slot][0];
+                wE[(2 * u + F - 1) % F] = (double)qE[slot][1];
+                wO[(2 * u + F - 1) % F] = (double)qO[slot][1];
+                if (i + PD < nrows) {
+                    load_row(2 * (i + PD) + F - 2, qE[slot][0], qO[slot][0]);
+                    load_row(2 * (i + PD) + F - 1, qE[slot][1], qO[slot][1]);
+                }
+                // axis -2: tap j multiplies local row 2i + F-1 - j
+                double loE = 0.0, loO = 0.0, hiE = 0.0, hiO = 0.0;
+#pragma unroll
+                for (int j = 0; j < F; ++j) {
+                    const double ve = wE[(2 * u + F - 1 - j) % F], vo = wO[(2 * u + F - 1 - j) % F];
+                    if (Wav<WID>::dec_lo(j) != 0.0) {
+                        loE = fma(Wav<WID>::dec_lo(j), ve, loE);
+                        loO = fma(Wav<WID>::dec_lo(j), vo, loO);
+                    }
+                    if (wav_dec_hi<WID>(j) != 0.0) {
+                        hiE = fma(wav_dec_hi<WID>(j), ve, hiE);
+                        hiO = fma(wav_dec_hi<WID>(j), vo, hiO);
+                    }
+                }
+                // axis -1: tap 2u' multiplies O[k-u'], tap 2u'+1 multiplies E[k-u']
+                double aa = 0.0, ad = 0.0, da = 0.0, dd = 0.0;
+#pragma unroll
+                for (int v = 0; v < HF; ++v) {
+                    constexpr unsigned FULL = 0xffffffffu;
+                    const bool needO = Wav<WID>::dec_lo(2 * v) != 0.0 || wav_dec_hi<WID>(2 * v) != 0.0;
+                    const bool needE = Wav<WID>::dec_lo(2 * v + 1) != 0.0 || wav_dec_hi<WID>(2 * v + 1) != 0.0;
+                    if (needO) {
+                        const double lo_o = v ? __shfl_up_sync(FULL, loO, v) : loO;
+                        const double hi_o = v ? __shfl_up_sync(FULL, hiO, v) : hiO;
+                        if (Wav<WID>::dec_lo(2 * v) != 0.0) {
+                            aa = fma(Wav<WID>::dec_lo(2 * v), lo_o, aa);
+                            da = fma(Wav<WID>::dec_lo(2 * v), hi_o, da);
+                        }
+                        if (wav_dec_hi<WID>(2 * v) != 0.0) {
+                            ad = fma(wav_dec_hi<WID>(2 * v), lo_o, ad);
+                            dd = fma(wav_dec_hi<WID>(2 * v), hi_o, dd);
+                        }
+                    }
+                    if (needE) {
+                        const double lo_e = v ? __shfl_up_sync(FULL, loE, v) : loE;
+                        const double hi_e = v ? __shfl_up_sync(FULL, hiE, v) : hiE;
+                        if (Wav<WID>::dec_lo(2 * v + 1) != 0.0) {
+                            aa = fma(Wav<WID>::dec_lo(2 * v + 1), lo_e, aa);
+                            da = fma(Wav<WID>::dec_lo(2 * v + 1), hi_e, da);
+                        }
+                        if (wav_dec_hi<WID>(2 * v + 1) != 0.0) {
+                            ad = fma(wav_dec_hi<WID>(2 * v + 1), lo_e, ad);
+                            dd = fma(wav_dec_hi<WID>(2 * v + 1), hi_e, dd);
+                        }
+                    }
+                }
+                if (out_active) {
+                    *p_ad = quantise(ad, m, q);
+                    *p_da = quantise(da, m, q);
+                    *p_dd = quantise(dd, m, q);
+                    if (ll_scratch)
+                        *p_ll = aa;
+                    else
+                        *p_aa = quantise(aa, m, q);
+                }
+                p_aa += Wc;
+                p_ad += Wc;
+                p_da += Wc;
+                p_dd += Wc;
+                if (ll_scratch) p_ll += bw;
             }
-            if (wav_dec_hi<WID>(j) != 0.0) {
-                ad = fma(wav_dec_hi<WID>(j), vlo, ad);
-                dd = fma(wav_dec_hi<WID>(j), vhi, dd);
-            }
-        }
-        const int gr = r0 + r, gc = c0 + c;
-        if (gr < p.bh && gc < p.bw) {
-            cz[(size_t)gr * p.Wc + p.sw + gc] = quantise(ad, m, q);
-            cz[(size_t)(p.sh + gr) * p.Wc + gc] = quantise(da, m, q);
-            cz[(size_t)(p.sh + gr) * p.Wc + p.sw + gc] = quantise(dd, m, q);
-            if (p.last)
-                cz[(size_t)gr * p.Wc + gc] = quantise(aa, m, q);
-            else
-                p.dst_ll[((size_t)z * p.bh + gr) * p.bw + gc] = aa;
         }
     }
+}
+
+template <typename Tin, int WID>
+__global__ void __launch_bounds__(FW_WARPS * 32) dwt_fwd_level_kernel(const FwdK p)
+{
+    constexpr int F = Wav<WID>::F;
+    long long task = (long long)blockIdx.x * FW_WARPS + (threadIdx.x >> 5);
+    if (task >= p.ntasks) return;
+    const int tx = (int)(task % p.tiles_x);
+    task /= p.tiles_x;
+    const int ty = (int)(task % p.tiles_y);
+    const int z = (int)(task / p.tiles_y);
+    const int r0 = ty * p.RH;
+    const int nrows = min(p.RH, p.bh - r0);
+    const int sft = p.mode == SPIHTB_MODE_PERIODIZATION ? (F / 2 - 1) : 0;
+    const int gr0 = 2 * r0 - (F - 2) + sft;
+    // rows of the chunk's window all inside the plane (warp-uniform)
+    if (gr0 >= 0 && gr0 + 2 * nrows + F - 2 <= p.src_h)
+        dwt_fwd_task<Tin, WID, true>(p, tx, ty, z);
+    else
+        dwt_fwd_task<Tin, WID, false>(p, tx, ty, z);
 }
 
 // zero the gaps coeffs_to_array leaves between a level's off-diagonal blocks
@@ -177,23 +291,22 @@ __global__ void __launch_bounds__(256) rgb_to_ipt_kernel(const Tin *__restrict__
 }
 
 template <typename Tin, int WID>
-static int launch_level(spihtb_ctx *ctx, const FwdK &k, int nz)
+static int launch_level(spihtb_ctx *ctx, FwdK k, int nz)
 {
     constexpr int F = Wav<WID>::F;
-    constexpr int IH = 2 * FW_TH + F - 2, IW = 2 * FW_TW + F - 2;
-    const size_t smem = ((IH * IW * sizeof(Tin) + 15) / 16) * 16 + 2 * FW_TH * IW * sizeof(double);
-    auto kern = dwt_fwd_level_kernel<Tin, WID>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        SPIHTB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
-    const long long nb = (long long)k.tiles_x * k.tiles_y * nz;
+    constexpr int NOUT = 32 - (F / 2 - 1);
+    constexpr int RHMAX = 64;
+    k.tiles_x = (k.bw + NOUT - 1) / NOUT;
+    // balanced row chunks (no nearly empty tail chunk)
+    k.tiles_y = (k.bh + RHMAX - 1) / RHMAX;
+    k.RH = (k.bh + k.tiles_y - 1) / k.tiles_y;
+    k.ntasks = (long long)k.tiles_x * k.tiles_y * nz;
+    const long long nb = (k.ntasks + FW_WARPS - 1) / FW_WARPS;
     if (nb > 0x7fffffffLL) {
         set_error("forward DWT grid too large");
         return SPIHTB_ESHAPE;
     }
-    kern<<<(unsigned)nb, FW_NT, smem, ctx->stream>>>(k);
+    dwt_fwd_level_kernel<Tin, WID><<<(unsigned)nb, FW_WARPS * 32, 0, ctx->stream>>>(k);
     ctx->launches++;
     return SPIHTB_OK;
 }
@@ -261,8 +374,6 @@ int launch_forward(spihtb_ctx *ctx, const void *pixels, const XformArgs &x, int3
         k.sw = g.off_w[l];
         k.mode = g.mode;
         k.C = x.C;
-        k.tiles_x = (k.bw + FW_TW - 1) / FW_TW;
-        k.tiles_y = (k.bh + FW_TH - 1) / FW_TH;
         for (int c = 0; c < 8; ++c) k.scale[c] = x.scale[c];
         k.q = x.q;
         if (l == 0) ctx->stage_begin(0);

@@ -15,51 +15,47 @@
 namespace spihtb {
 
 // ---- base pass: reads every coefficient once (HBM-bound) ------------------
-// blockDim (32, 8); a warp owns one row pair and PYR_COLS columns.
-constexpr int PYR_UNROLL = 8;
-constexpr int PYR_COLS = 32 * PYR_UNROLL;
+// blockDim (32, 8); a warp owns one row pair.  A lane reads the two adjacent
+// columns of its cell in both rows (the 2x2 block of one tree node), so a cell
+// needs no exchange and a warp writes 32 consecutive plane bytes.
+constexpr int PYR_UNROLL = 4;
 
 __global__ void __launch_bounds__(256) pyr_base_kernel(const int32_t *__restrict__ coeffs, int H, int W, int NH, int NW,
-                                                       int gx, int gy, int C, uint8_t *__restrict__ dp,
-                                                       uint8_t *__restrict__ lp, uint32_t *__restrict__ maxabs)
+                                                       int gy, int C, uint8_t *__restrict__ dp,
+                                                       uint32_t *__restrict__ maxabs)
 {
     __shared__ uint32_t s_max[8];
     const int lane = threadIdx.x, wy = threadIdx.y;
-    uint32_t bid = blockIdx.x;
-    const int bx = bid % gx;
-    bid /= gx;
-    const int by = bid % gy;
-    const int z = bid / gy;  // image * C + channel
+    const int by = blockIdx.x % gy;
+    const int z = blockIdx.x / gy;  // image * C + channel
 
     const int ip = by * 8 + wy;  // row pair
-    const int r0 = 2 * ip, r1 = r0 + 1;
-    const int32_t *a = coeffs + (size_t)z * H * W;
-    uint32_t m[PYR_UNROLL];
+    const int r0 = 2 * ip;
     uint32_t wmax = 0;
     if (r0 < H) {
-        const int32_t *p0 = a + (size_t)r0 * W;
-        const int32_t *p1 = a + (size_t)r1 * W;
-        const bool has1 = r1 < H;
+        const int32_t *p0 = coeffs + (size_t)z * H * W + (size_t)r0 * W;
+        const bool has1 = r0 + 1 < H;
+        const int32_t *p1 = has1 ? p0 + W : p0;
+        uint8_t *drow = dp + ((size_t)z * NH + (ip < NH ? ip : 0)) * NW;
+        const int ncell = (W + 1) >> 1;  // cells incl. a half cell in the last odd column
+        for (int jb = 0; jb < ncell; jb += 32 * PYR_UNROLL) {
+            uint32_t m[PYR_UNROLL];
 #pragma unroll
-        for (int u = 0; u < PYR_UNROLL; ++u) {
-            int col = bx * PYR_COLS + u * 32 + lane;
-            uint32_t v0 = 0, v1 = 0;
-            if (col < W) {
-                v0 = absu(__ldg(p0 + col));
-                if (has1) v1 = absu(__ldg(p1 + col));
+            for (int u = 0; u < PYR_UNROLL; ++u) {
+                const int j = jb + u * 32 + lane;
+                const int c = 2 * j;
+                uint32_t v = 0;
+                if (c < W) {
+                    v = max(absu(__ldg(p0 + c)), absu(__ldg(p1 + c)));
+                    if (c + 1 < W) v = max(v, max(absu(__ldg(p0 + c + 1)), absu(__ldg(p1 + c + 1))));
+                }
+                m[u] = v;
             }
-            m[u] = max(v0, v1);
-        }
 #pragma unroll
-        for (int u = 0; u < PYR_UNROLL; ++u) {
-            uint32_t pm = max(m[u], __shfl_xor_sync(0xffffffffu, m[u], 1));
-            wmax = max(wmax, pm);
-            int col = bx * PYR_COLS + u * 32 + lane;
-            int jn = col >> 1;
-            if (!(lane & 1) && ip < NH && jn < NW) {
-                size_t o = ((size_t)z * NH + ip) * NW + jn;
-                dp[o] = (uint8_t)plane1(pm);
-                lp[o] = 0;
+            for (int u = 0; u < PYR_UNROLL; ++u) {
+                const int j = jb + u * 32 + lane;
+                wmax = max(wmax, m[u]);
+                if (ip < NH && j < NW) drow[j] = (uint8_t)plane1(m[u]);
             }
         }
     }
@@ -133,16 +129,16 @@ int launch_pyramid(spihtb_ctx *ctx, const int32_t *coeffs, int B, int C, int H, 
     cudaStream_t st = ctx->stream;
     const int NH = H / 2, NW = W / 2, nz = B * C;
     SPIHTB_CUDA_CHECK(cudaMemsetAsync(maxabs, 0, sizeof(uint32_t) * B, st));
+    SPIHTB_CUDA_CHECK(cudaMemsetAsync(lp, 0, (size_t)nz * NH * NW, st));  // ring-1 nodes have no L-set
     {
-        const int gx = (W + PYR_COLS - 1) / PYR_COLS;
         const int gy = ((H + 1) / 2 + 7) / 8;
-        const long long nb = (long long)gx * gy * nz;
+        const long long nb = (long long)gy * nz;
         if (nb > 0x7fffffffLL) {
             set_error("pyramid grid too large");
             return SPIHTB_ESHAPE;
         }
         ctx->stage_begin(2);
-        pyr_base_kernel<<<(unsigned)nb, dim3(32, 8), 0, st>>>(coeffs, H, W, NH, NW, gx, gy, C, dp, lp, maxabs);
+        pyr_base_kernel<<<(unsigned)nb, dim3(32, 8), 0, st>>>(coeffs, H, W, NH, NW, gy, C, dp, maxabs);
         ctx->launches++;
         ctx->stage_end(2);
     }
