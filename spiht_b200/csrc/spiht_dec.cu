@@ -1,17 +1,28 @@
 // SPIHT decoder (replaces src/encoder_decoder.rs:307-454), one CTA per stream.
 //
 // The decoder's control flow depends on the bits it reads, so record
-// boundaries cannot be found by a scan alone.  Each list pass is split in two:
-//   chain   : one thread walks the pass's bit region, skipping runs of zero
-//             bits 64 at a time (a zero is "entry stays"), and records an
-//             event (entry index, bit position) at every set bit that starts a
-//             record -- a newly significant pixel, a fired A set (whose 4..8
-//             child bits it skips) or a fired B set.  The chain touches only
-//             the bitstream (read-only cache) and two shared-memory bitmasks.
-//   apply   : all threads process the events in parallel (child bits, value
-//             writes, list appends through a CTA-wide scan) and compact the
-//             retained entries in place.
-// The refinement pass is a plain parallel map (entry e reads bit p0 + e).
+// boundaries are not known up front.  Each list pass is parsed as follows.
+//
+//   LIP pass (records "0" | "1 sign"): fully parallel.  Any 0 bit is followed
+//   by a record start, so inside the pass "bit p starts a record" <=> the run of
+//   1 bits ending at p-1 has even length.  Every thread takes a 32-bit window,
+//   the run parity entering each window comes from a scan over 2-state
+//   transition functions, and popcounts of the start masks give every record
+//   its list index.
+//
+//   LIS pass (records "0" | B:"1" | A:"1 c c c c", c = "0" | "1 sign"): only a
+//   fired A set is longer than one bit.  One thread walks the pass, but it only
+//   stops at fired A sets: it ANDs the bitstream with the list's set-type mask
+//   (shifted by the bits consumed so far) and jumps from one fired A set to the
+//   next with a find-first-set, recording the length of its child bits.  All
+//   other work -- reading every entry's own bit at (entry index + prefix sum of
+//   the child lengths), the child bits, value writes, list appends through a
+//   CTA-wide scan, stable compaction of the retained entries -- is a parallel
+//   map over the entries.  The FIFO order of the reference is reproduced
+//   generation by generation as in the encoder.
+//
+//   Refinement pass: a parallel map (entry e reads bit p0 + e).
+//
 // Values are written straight into the coefficient array, as the reference
 // does, so pad bits and duplicated coordinates behave identically.  Decoding
 // stops at the first bit position >= 8 * nbytes (pop_bit!, :314-325): an
@@ -31,11 +42,11 @@
 
 namespace spihtb {
 
-constexpr int DEC_NT = 256;
-constexpr int DEC_CH = 8192;  // list entries per chain round
-constexpr int DEC_EV = 1024;  // event buffer
+constexpr int DEC_NT = 512;
+constexpr int DEC_NW = DEC_NT / 32;
+constexpr int DEC_CH = 8192;           // LIS entries per chain round
 constexpr int DEC_SLACK = 8 * DEC_NT + 64;
-constexpr int DEC_DQ = 4 * DEC_NT;  // ordered write queue (odd LL sizes only)
+constexpr int DEC_DQ = 4 * DEC_NT;     // ordered write queue (odd LL sizes only)
 
 struct DecK {
     const uint32_t *in;
@@ -45,7 +56,7 @@ struct DecK {
     int B, C, H, W, ll_h, ll_w;
     KeyFmt kf;
     int32_t *out;
-    uint32_t *lip, *lsp, *lis;  // lis: 3 buffers per slot
+    uint32_t *lip, *lsp, *lis;  // lip: 2 buffers per slot; lis: 3 buffers per slot
     size_t pix_cap, lis_cap;
     unsigned int *counter;
 };
@@ -85,66 +96,6 @@ __device__ __forceinline__ bool in_dup_subtree(uint32_t y, uint32_t x, uint32_t 
     return false;
 }
 
-struct ChainState {
-    uint64_t p;      // next bit position
-    uint32_t e;      // next entry (relative to the round)
-    uint32_t nev;    // events recorded in this sub-round
-    uint32_t ended;  // the stream is exhausted
-};
-
-// Thread 0 only.  Entries [st.e, cnt) of the round; stops when the event
-// buffer is full.  lis_mode: record kind taken from tmask (1 = A, 0 = B);
-// otherwise LIP records ("0" | "1 sign").
-__device__ void run_chain(const BitRow &br, bool lis_mode, const uint32_t *tmask, uint32_t *fmask, uint2 *ev,
-                          uint32_t cnt, uint64_t p_base, ChainState &st)
-{
-    uint64_t p = st.p;
-    uint32_t e = st.e, nev = 0;
-    while (e < cnt && nev < DEC_EV) {
-        if (p >= br.nbits) break;
-        const uint64_t w = br.get64(p);
-        uint64_t lim = cnt - e;
-        if (lim > 64) lim = 64;
-        const uint64_t rem = br.nbits - p;
-        if (rem < lim) lim = rem;  // bits past the end are not data
-        const uint64_t wl = lim < 64 ? (w & ((1ull << lim) - 1ull)) : w;
-        if (wl == 0) {
-            e += (uint32_t)lim;
-            p += lim;
-            continue;
-        }
-        const int z = __ffsll((long long)wl) - 1;
-        e += z;
-        p += z;
-        fmask[e >> 5] |= 1u << (e & 31);
-        uint32_t len;
-        if (!lis_mode) {
-            len = 1;
-        } else if ((tmask[e >> 5] >> (e & 31)) & 1u) {
-            uint32_t cb = (z + 9 <= 64) ? (uint32_t)(w >> (z + 1)) : br.get32(p + 1);
-            len = 4;
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                if (cb & 1u) {
-                    cb >>= 2;
-                    ++len;
-                } else {
-                    cb >>= 1;
-                }
-            }
-        } else {
-            len = 0;
-        }
-        ev[nev++] = make_uint2(e, (uint32_t)(p - p_base));
-        p += 1 + len;
-        e += 1;
-    }
-    st.p = p;
-    st.e = e;
-    st.nev = nev;
-    st.ended = p >= br.nbits ? 1u : 0u;
-}
-
 // set_bit (encoder_decoder.rs:14-29): set / clear bit n of the magnitude, keep the sign
 __device__ __forceinline__ void refine_cell(int32_t *cell, int n, uint32_t bit)
 {
@@ -171,25 +122,65 @@ __device__ void apply_queue(const uint2 *dq, uint32_t cnt, const KeyFmt &kf, int
     }
 }
 
-__global__ void __launch_bounds__(DEC_NT) spiht_decode_kernel(const DecK p)
+// ---- LIP parse: 2-state automaton over the bits of a pass -------------------
+// state s = 1: the next bit starts a record; s = 0: the next bit is a sign bit.
+// next(s, b) = !(s & b).  A transition function over a bit window is stored as
+// 2 bits: bit x = state after the window when entered in state x.
+__device__ __forceinline__ uint32_t lip_fn_compose(uint32_t first, uint32_t then)
 {
-    __shared__ uint32_t s_tmask[DEC_CH / 32];
-    __shared__ uint32_t s_fmask[DEC_CH / 32];
-    __shared__ uint2 s_ev[DEC_EV];
-    __shared__ uint64_t s_wtot[DEC_NT / 32];
-    __shared__ ChainState s_st;
+    return ((then >> (first & 1u)) & 1u) | (((then >> ((first >> 1) & 1u)) & 1u) << 1);
+}
+
+// Exclusive scan of transition functions over the CTA, applied to `s_in`
+// (the state entering thread 0's window).  Returns the state entering this
+// thread's window and, in `s_out`, the state after the last window.
+__device__ __forceinline__ uint32_t lip_state_scan(uint32_t fn, uint32_t s_in, uint32_t *warp_fn, uint32_t &s_out)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t inc = fn;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc = lip_fn_compose(t, inc);
+    }
+    __syncthreads();  // previous users of warp_fn are done
+    if (lane == 31) warp_fn[wid] = inc;
+    __syncthreads();
+    uint32_t s = s_in, s_mine = s_in;
+#pragma unroll
+    for (int q = 0; q < DEC_NW; ++q) {
+        if (q == wid) s_mine = s;
+        s = (warp_fn[q] >> s) & 1u;
+    }
+    s_out = s;
+    // state entering this lane = exclusive prefix within the warp applied to the warp's entry state
+    const uint32_t prev = __shfl_up_sync(0xffffffffu, inc, 1);
+    return lane == 0 ? s_mine : ((prev >> s_mine) & 1u);
+}
+
+__global__ void __launch_bounds__(DEC_NT, 2) spiht_decode_kernel(const DecK p)
+{
+    __shared__ uint32_t s_tmask[DEC_CH / 32 + 4];  // A sets with offspring (a fired record carries child bits)
+    __shared__ __align__(16) uint8_t s_x[DEC_CH];               // child-bit length of fired A sets, 0 elsewhere
+    __shared__ uint32_t s_grp[DEC_CH / 32];        // exclusive prefix of s_x per 32 entries
+    __shared__ uint64_t s_wtot[DEC_NW];
+    __shared__ uint32_t s_wfn[DEC_NW];
+    __shared__ uint64_t s_chain_p;
     __shared__ int s_img;
     __shared__ uint2 s_dq[DEC_DQ];  // {cell key | refine flag << 31, value or bit}
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const KeyFmt kf = p.kf;
     const uint32_t H = p.H, W = p.W, ll_h = p.ll_h, ll_w = p.ll_w, C = p.C;
-    uint32_t *lip = p.lip + (size_t)blockIdx.x * p.pix_cap;
+    uint32_t *lipA = p.lip + (size_t)blockIdx.x * 2 * p.pix_cap;
+    uint32_t *lipB = lipA + p.pix_cap;
     uint32_t *lsp = p.lsp + (size_t)blockIdx.x * p.pix_cap;
     uint32_t *R = p.lis + (size_t)blockIdx.x * 3 * p.lis_cap;
     uint32_t *G0 = R + p.lis_cap;
     uint32_t *G1 = G0 + p.lis_cap;
     const bool has_dups = ((ll_h | ll_w) & 1u) != 0;
+    // bits per thread in a LIP round; the ordered write queue bounds it when cells can be duplicated
+    const int BPT = has_dups ? 4 : 32;
 
     for (;;) {
         if (tid == 0) s_img = (int)atomicAdd(p.counter, 1u);
@@ -203,11 +194,13 @@ __global__ void __launch_bounds__(DEC_NT) spiht_decode_kernel(const DecK p)
         br.nwords = p.in_stride_words;
         br.nbits = p.nbytes[b] * 8ull;
         if (br.nbits > br.nwords * 32ull) br.nbits = br.nwords * 32ull;
+        const uint64_t limit = br.nbits;
         int32_t *rec = p.out + (size_t)b * C * H * W;
         int n = p.n[b];
         n = n < 0 ? 0 : (n > 31 ? 31 : n);
 
         // ---- list initialisation (encoder_decoder.rs:329-348)
+        uint32_t *lip = lipA, *lip_alt = lipB;
         const uint32_t T0 = ll_h * ll_w * C;
         uint32_t lip_len = T0, lsp_len = 0, r_len = 0;
         for (uint32_t base = 0; base < T0; base += DEC_NT) {
@@ -230,82 +223,145 @@ __global__ void __launch_bounds__(DEC_NT) spiht_decode_kernel(const DecK p)
         __syncthreads();
 
         uint64_t pos = 0;  // uniform: next unread bit
-        bool ended = br.nbits == 0;
-        for (; !ended; --n) {
+        for (; pos < limit; --n) {
             const int32_t basev = n == 0 ? 1 : (int32_t)((1u << (n - 1)) + (1u << n));
             const uint32_t lsp_len0 = lsp_len;
 
             // ================= LIP pass (encoder_decoder.rs:355-377)
             {
-                uint32_t keep = 0;
-                for (uint32_t ebase = 0; ebase < lip_len && !ended; ebase += DEC_CH) {
-                    const uint32_t cnt = min((uint32_t)DEC_CH, lip_len - ebase);
-                    for (uint32_t i = tid; i < (cnt + 31) / 32; i += DEC_NT) s_fmask[i] = 0;
-                    if (tid == 0) {
-                        s_st.p = pos;
-                        s_st.e = 0;
-                        s_st.ended = 0;
+                uint32_t done_e = 0, keep = 0;
+                while (done_e < lip_len && pos < limit) {
+                    // this thread's window: BPT bits at wp; bits at or past `limit` are not data
+                    const uint64_t wp = pos + (uint64_t)tid * BPT;
+                    uint32_t nv = wp < limit ? (uint32_t)min((uint64_t)BPT, limit - wp) : 0u;
+                    const uint32_t vmask = nv >= 32 ? 0xffffffffu : ((1u << nv) - 1u);
+                    const uint32_t wbits = (nv ? br.get32(wp) : 0u) & vmask;
+                    // transition function of the window (all BPT bits; invalid ones read as 0)
+                    uint32_t fn;
+                    {
+                        const uint32_t full = BPT >= 32 ? 0xffffffffu : ((1u << BPT) - 1u);
+                        if ((wbits & full) == full) {
+                            fn = (BPT & 1) ? 0x1u : 0x2u;  // all ones: the state flips BPT times
+                        } else {
+                            // after the highest 0 bit the state is 1; then it flips once per trailing 1
+                            const uint32_t inv = ~wbits & full;
+                            const int top0 = 31 - __clz((int)inv);
+                            const uint32_t ones = (uint32_t)(BPT - 1 - top0);
+                            const uint32_t s = (ones & 1u) ? 0u : 1u;
+                            fn = s | (s << 1);
+                        }
                     }
-                    __syncthreads();
-                    uint32_t eprev = 0;
-                    for (;;) {
-                        const uint64_t p_base = pos;
-                        if (tid == 0) run_chain(br, false, nullptr, s_fmask, s_ev, cnt, p_base, s_st);
-                        __syncthreads();
-                        const uint32_t nev = s_st.nev, ecur = s_st.e;
-                        const bool end_now = s_st.ended != 0;
-                        pos = s_st.p;
-                        // events: newly significant pixels, in list order
-                        for (uint32_t rb = 0; rb < nev; rb += DEC_NT) {
-                            const uint32_t r = rb + tid;
-                            bool defer = false;
-                            uint32_t key = 0;
-                            int32_t val = 0;
-                            if (r < nev) {
-                                const uint2 ev = s_ev[r];
-                                const uint64_t ps = p_base + ev.y + 1;  // sign bit
-                                if (ps < br.nbits) {
-                                    key = lip[ebase + ev.x];
-                                    uint32_t k, i, j;
-                                    key_unpack(kf, key, k, i, j);
-                                    val = br.bit(ps) ? basev : -basev;
-                                    defer = has_dups && in_dup_subtree(i, j, ll_h, ll_w);
-                                    if (!defer) rec[((size_t)k * H + i) * W + j] = val;
-                                    lsp[lsp_len + r] = key;
+                    uint32_t s_last;
+                    uint32_t s = lip_state_scan(fn, 1u, s_wfn, s_last);
+                    // start mask of the window
+                    uint32_t smask = 0;
+                    for (int i = 0; i < BPT; ++i) {
+                        smask |= s << i;
+                        s = ((wbits >> i) & s & 1u) ^ 1u;
+                    }
+                    smask &= vmask;
+                    const uint32_t nrec = __popc(smask);
+                    uint64_t tot;
+                    const uint32_t e0 = (uint32_t)block_exscan<DEC_NT>((uint64_t)nrec, s_wtot, tot);
+                    const uint32_t rem = lip_len - done_e;
+                    const uint32_t take = min((uint32_t)tot, rem);
+                    // records of this window that belong to the pass: the first `mine`
+                    const uint32_t mine = e0 >= take ? 0u : min(nrec, take - e0);
+                    uint32_t use = smask;
+                    for (uint32_t q = nrec; q > mine; --q) use &= ~(0x80000000u >> __clz((int)use));
+                    // newly significant: start bit set and the sign bit below the limit
+                    const uint32_t sigm = use & wbits;
+                    uint32_t okm = sigm;
+                    if (nv && nv <= 32 && wp + nv >= limit) {
+                        // the window holds the last valid bit: a record starting there has no sign bit
+                        okm &= ~(1u << (nv - 1));
+                    }
+                    const uint32_t nsig = __popc(okm), nkeep = __popc(use & ~wbits);
+                    // sign bits: bit i+1 of the window, the last one from the next word
+                    const uint32_t nextbits = (uint32_t)(br.get64(wp) >> 1);
+                    uint32_t ndef = 0, defm = 0;
+                    if (has_dups) {
+                        uint32_t mm = okm;
+                        uint32_t idx = e0;
+                        uint32_t um = use;
+                        while (um) {
+                            const int bpos = __ffs((int)um) - 1;
+                            um &= um - 1;
+                            if ((mm >> bpos) & 1u) {
+                                const uint32_t key = lip[done_e + idx];
+                                uint32_t k, i, j;
+                                key_unpack(kf, key, k, i, j);
+                                if (in_dup_subtree(i, j, ll_h, ll_w)) {
+                                    defm |= 1u << bpos;
+                                    ++ndef;
                                 }
                             }
-                            if (has_dups) {
-                                uint64_t tot;
-                                const uint64_t ex = block_exscan<DEC_NT>(defer ? 1ull : 0ull, s_wtot, tot);
-                                if (defer) s_dq[(uint32_t)ex] = make_uint2(key, (uint32_t)val);
-                                __syncthreads();
-                                if (tid == 0) apply_queue(s_dq, (uint32_t)tot, kf, rec, H, W, n);
-                                __syncthreads();
+                            ++idx;
+                        }
+                    }
+                    const uint64_t pack = (uint64_t)nsig | ((uint64_t)nkeep << 20) | ((uint64_t)ndef << 40);
+                    uint64_t tot2;
+                    const uint64_t ex = block_exscan<DEC_NT>(pack, s_wtot, tot2);
+                    {
+                        uint32_t os = lsp_len + (uint32_t)(ex & 0xfffff);
+                        uint32_t ok = keep + (uint32_t)((ex >> 20) & 0xfffff);
+                        uint32_t od = (uint32_t)(ex >> 40);
+                        uint32_t idx = done_e + e0;
+                        uint32_t um = use;
+                        while (um) {
+                            const int bpos = __ffs((int)um) - 1;
+                            um &= um - 1;
+                            const uint32_t key = lip[idx++];
+                            if ((wbits >> bpos) & 1u) {
+                                if ((okm >> bpos) & 1u) {
+                                    uint32_t k, i, j;
+                                    key_unpack(kf, key, k, i, j);
+                                    const int32_t val = ((nextbits >> bpos) & 1u) ? basev : -basev;
+                                    if ((defm >> bpos) & 1u)
+                                        s_dq[od++] = make_uint2(key, (uint32_t)val);
+                                    else
+                                        rec[((size_t)k * H + i) * W + j] = val;
+                                    lsp[os++] = key;
+                                }
+                            } else {
+                                lip_alt[ok++] = key;
                             }
                         }
-                        lsp_len += nev;
-                        // retained entries [eprev, ecur): in-place stable compaction
-                        for (uint32_t cb = eprev; cb < ecur; cb += DEC_NT) {
-                            const uint32_t e = cb + tid;
-                            const bool valid = e < ecur;
-                            const bool keepit = valid && !((s_fmask[e >> 5] >> (e & 31)) & 1u);
-                            const uint32_t key = keepit ? lip[ebase + e] : 0u;
-                            uint64_t tot;
-                            const uint64_t ex = block_exscan<DEC_NT>(keepit ? 1ull : 0ull, s_wtot, tot);
-                            if (keepit) lip[keep + (uint32_t)ex] = key;
-                            keep += (uint32_t)tot;
-                        }
-                        eprev = ecur;
+                    }
+                    if (has_dups) {
                         __syncthreads();
-                        if (end_now) ended = true;
-                        if (ended || ecur >= cnt) break;
+                        if (tid == 0) apply_queue(s_dq, (uint32_t)(tot2 >> 40), kf, rec, H, W, n);
+                        __syncthreads();
+                    }
+                    lsp_len += (uint32_t)(tot2 & 0xfffff);
+                    keep += (uint32_t)((tot2 >> 20) & 0xfffff);
+                    done_e += take;
+                    // next unread bit: the start of record `take` if the window holds it, else the
+                    // bit after the window (plus the sign bit the window's last record still owes)
+                    if ((uint32_t)tot > take) {
+                        // position of start number `take`: in the thread with e0 <= take < e0 + nrec
+                        if (e0 <= take && take < e0 + nrec) {
+                            uint32_t um = smask;
+                            for (uint32_t q = e0; q < take; ++q) um &= um - 1;
+                            s_chain_p = wp + (uint64_t)(__ffs((int)um) - 1);
+                        }
+                        __syncthreads();
+                        pos = s_chain_p;
+                        __syncthreads();
+                    } else {
+                        pos = pos + (uint64_t)DEC_NT * BPT + (s_last ? 0u : 1u);
                     }
                 }
-                if (ended) break;
+                if (done_e < lip_len) break;  // the stream ended inside the pass
+                uint32_t *t = lip;
+                lip = lip_alt;
+                lip_alt = t;
                 lip_len = keep;
             }
+            if (pos >= limit) break;
 
             // ================= LIS pass (encoder_decoder.rs:379-436), generation by generation
+            bool ended = false;
             {
                 uint32_t *cur = R, *nxt = G0;
                 uint32_t cur_len = r_len, rkeep = 0;
@@ -314,9 +370,8 @@ __global__ void __launch_bounds__(DEC_NT) spiht_decode_kernel(const DecK p)
                     uint32_t nxt_len = 0;
                     for (uint32_t ebase = 0; ebase < cur_len && !ended; ebase += DEC_CH) {
                         const uint32_t cnt = min((uint32_t)DEC_CH, cur_len - ebase);
-                        // set-type mask of this round's entries
-                        // (bit set = A set that has offspring, i.e. a fired record carries child bits)
-                        for (uint32_t w = wid; w < (cnt + 31) / 32; w += DEC_NT / 32) {
+                        // set-type mask of this round's entries; clear the child-length bytes
+                        for (uint32_t w = wid; w < (cnt + 31) / 32 + 3; w += DEC_NW) {
                             const uint32_t e = w * 32 + lane;
                             const uint32_t key = e < cnt ? cur[ebase + e] : 0u;
                             bool a_with_children = false;
@@ -326,133 +381,174 @@ __global__ void __launch_bounds__(DEC_NT) spiht_decode_kernel(const DecK p)
                                 a_with_children = offspring_corner(i, j, H, W, ll_h, ll_w, ci, cj);
                             }
                             const uint32_t m = __ballot_sync(0xffffffffu, a_with_children);
-                            if (lane == 0) {
-                                s_tmask[w] = m;
-                                s_fmask[w] = 0;
-                            }
-                        }
-                        if (tid == 0) {
-                            s_st.p = pos;
-                            s_st.e = 0;
-                            s_st.ended = 0;
+                            if (lane == 0) s_tmask[w] = m;
+                            if (e < DEC_CH) s_x[e] = 0;
                         }
                         __syncthreads();
-                        uint32_t eprev = 0;
-                        for (;;) {
-                            const uint64_t p_base = pos;
-                            if (tid == 0) run_chain(br, true, s_tmask, s_fmask, s_ev, cnt, p_base, s_st);
-                            __syncthreads();
-                            const uint32_t nev = s_st.nev, ecur = s_st.e;
-                            const bool end_now = s_st.ended != 0;
-                            pos = s_st.p;
-                            // events: fired sets, in list order
-                            for (uint32_t rb = 0; rb < nev; rb += DEC_NT) {
-                                const uint32_t r = rb + tid;
-                                const bool valid = r < nev;
-                                uint32_t key = 0, k = 0, i = 0, j = 0, ci = 0, cj = 0;
-                                uint32_t nlsp = 0, nlip = 0, nnext = 0, sigmask = 0, sgnmask = 0, nread = 0;
-                                uint32_t ndef = 0, defmask = 0;
-                                bool isA = false, has = false;
-                                if (valid) {
-                                    const uint2 ev = s_ev[r];
-                                    key = cur[ebase + ev.x];
-                                    isA = (key >> 31) != 0;
-                                    key_unpack(kf, key, k, i, j);
-                                    has = offspring_corner(i, j, H, W, ll_h, ll_w, ci, cj);
-                                    if (isA) {
-                                        uint64_t q = p_base + ev.y + 1;
-                                        uint32_t cbits = br.get32(q);
-                                        bool cut = false;
-                                        if (has) {
+                        // ---- chain: one thread jumps from fired A set to fired A set
+                        if (tid == 0) {
+                            uint64_t cp = pos;
+                            uint32_t e = 0;
+                            while (e < cnt && cp < limit) {
+                                const uint64_t sb = br.get64(cp);
+                                const uint32_t tw = e >> 5;
+                                const int tsh = (int)(e & 31);
+                                const uint32_t t0 = s_tmask[tw], t1 = s_tmask[tw + 1], t2 = s_tmask[tw + 2];
+                                const uint64_t tb = (uint64_t)__funnelshift_r(t0, t1, tsh) |
+                                                    ((uint64_t)__funnelshift_r(t1, t2, tsh) << 32);
+                                uint64_t lim = cnt - e;
+                                if (lim > 64) lim = 64;
+                                const uint64_t rem = limit - cp;
+                                if (rem < lim) lim = rem;
+                                uint64_t m = sb & tb;
+                                if (lim < 64) m &= (1ull << lim) - 1ull;
+                                if (m == 0) {
+                                    e += (uint32_t)lim;
+                                    cp += lim;
+                                    continue;
+                                }
+                                const int z = __ffsll((long long)m) - 1;
+                                e += z;
+                                cp += z;
+                                uint32_t cb = (z + 9 <= 64) ? (uint32_t)(sb >> (z + 1)) : br.get32(cp + 1);
+                                uint32_t len = 4;
 #pragma unroll
-                                            for (int c4 = 0; c4 < 4; ++c4) {
-                                                if (cut) break;
-                                                if (q >= br.nbits) { cut = true; break; }
-                                                const uint32_t sg = cbits & 1u;
+                                for (int r = 0; r < 4; ++r) {
+                                    if (cb & 1u) {
+                                        cb >>= 2;
+                                        ++len;
+                                    } else {
+                                        cb >>= 1;
+                                    }
+                                }
+                                s_x[e] = (uint8_t)len;
+                                cp += 1 + len;
+                                e += 1;
+                            }
+                            s_chain_p = cp + (cnt - e);  // entries past the end of the stream: one bit each
+                        }
+                        __syncthreads();
+                        const uint64_t p_base = pos;
+                        pos = s_chain_p;
+                        // ---- prefix of the child lengths per 32 entries
+                        {
+                            uint32_t v = 0;
+                            if ((uint32_t)tid < (cnt + 31) / 32) {
+                                const uint32_t *xw = reinterpret_cast<const uint32_t *>(s_x) + tid * 8;
+#pragma unroll
+                                for (int q = 0; q < 8; ++q) v += __dp4a(xw[q], 0x01010101u, 0u);
+                            }
+                            static_assert(DEC_CH / 32 <= DEC_NT, "one thread per 32-entry group");
+                            uint64_t tot;
+                            const uint64_t ex = block_exscan<DEC_NT>((uint64_t)v, s_wtot, tot);
+                            if (tid < DEC_CH / 32) s_grp[tid] = (uint32_t)ex;
+                        }
+                        __syncthreads();
+                        // ---- every entry: its own bit, then the fired sets' records
+                        for (uint32_t eb = 0; eb < cnt; eb += DEC_NT) {
+                            const uint32_t e = eb + tid;
+                            const bool valid = e < cnt;
+                            // bit position: entries before e take one bit each plus the child bits of fired A sets
+                            const uint32_t xe = valid ? s_x[e] : 0u;
+                            uint32_t inc = xe;
+#pragma unroll
+                            for (int d = 1; d < 32; d <<= 1) {
+                                const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+                                if (lane >= d) inc += t;
+                            }
+                            const uint64_t pe = p_base + e + (valid ? s_grp[e >> 5] : 0u) + (inc - xe);
+                            const bool avail = valid && pe < limit;
+                            const uint32_t key = valid ? cur[ebase + e] : 0u;
+                            const bool fired = avail && br.bit(pe);
+                            uint32_t k = 0, i = 0, j = 0, ci = 0, cj = 0;
+                            uint32_t nlsp = 0, nlip = 0, nnext = 0, sigmask = 0, sgnmask = 0, nread = 0;
+                            uint32_t ndef = 0, defmask = 0;
+                            const bool isA = (key >> 31) != 0;
+                            if (fired) {
+                                key_unpack(kf, key, k, i, j);
+                                const bool has = offspring_corner(i, j, H, W, ll_h, ll_w, ci, cj);
+                                if (isA) {
+                                    uint64_t q = pe + 1;
+                                    uint32_t cbits = br.get32(q);
+                                    bool cut = false;
+                                    if (has) {
+#pragma unroll
+                                        for (int c4 = 0; c4 < 4; ++c4) {
+                                            if (cut) break;
+                                            if (q >= limit) { cut = true; break; }
+                                            const uint32_t sg = cbits & 1u;
+                                            cbits >>= 1;
+                                            ++q;
+                                            if (sg) {
+                                                if (q >= limit) { cut = true; break; }
+                                                sigmask |= 1u << c4;
+                                                sgnmask |= (cbits & 1u) << c4;
                                                 cbits >>= 1;
                                                 ++q;
-                                                if (sg) {
-                                                    if (q >= br.nbits) { cut = true; break; }
-                                                    sigmask |= 1u << c4;
-                                                    sgnmask |= (cbits & 1u) << c4;
-                                                    cbits >>= 1;
-                                                    ++q;
-                                                    ++nlsp;
-                                                } else {
-                                                    ++nlip;
-                                                }
-                                                ++nread;
-                                            }
-                                        }
-                                        if (!cut && has_desc_past_offspring(i, j, H, W)) nnext = 1;
-                                        if (has_dups && nlsp) {
-                                            for (uint32_t c4 = 0; c4 < nread; ++c4)
-                                                if ((sigmask & (1u << c4)) &&
-                                                    in_dup_subtree(ci + (c4 >> 1), cj + (c4 & 1), ll_h, ll_w)) {
-                                                    defmask |= 1u << c4;
-                                                    ++ndef;
-                                                }
-                                        }
-                                    } else {
-                                        nnext = has ? 4 : 0;
-                                    }
-                                }
-                                const uint64_t pack = (uint64_t)nlsp | ((uint64_t)nlip << 16) | ((uint64_t)nnext << 32) |
-                                                      ((uint64_t)ndef << 48);
-                                uint64_t tot;
-                                const uint64_t ex = block_exscan<DEC_NT>(pack, s_wtot, tot);
-                                if (valid) {
-                                    uint32_t os = lsp_len + (uint32_t)(ex & 0xffff);
-                                    uint32_t oi = lip_len + (uint32_t)((ex >> 16) & 0xffff);
-                                    const uint32_t on = nxt_len + (uint32_t)((ex >> 32) & 0xffff);
-                                    uint32_t od = (uint32_t)(ex >> 48);
-                                    if (isA) {
-                                        for (uint32_t c4 = 0; c4 < nread; ++c4) {
-                                            const uint32_t y = ci + (c4 >> 1), x = cj + (c4 & 1);
-                                            const uint32_t ck = key_pack(kf, k, y, x);
-                                            if (sigmask & (1u << c4)) {
-                                                const int32_t val = (sgnmask & (1u << c4)) ? basev : -basev;
-                                                if (defmask & (1u << c4))
-                                                    s_dq[od++] = make_uint2(ck, (uint32_t)val);
-                                                else
-                                                    rec[((size_t)k * H + y) * W + x] = val;
-                                                lsp[os++] = ck;
+                                                ++nlsp;
                                             } else {
-                                                lip[oi++] = ck;
+                                                ++nlip;
                                             }
+                                            ++nread;
                                         }
-                                        if (nnext) nxt[on] = key & 0x7fffffffu;
-                                    } else if (nnext) {
-#pragma unroll
-                                        for (int c4 = 0; c4 < 4; ++c4)
-                                            nxt[on + c4] = 0x80000000u | key_pack(kf, k, ci + (c4 >> 1), cj + (c4 & 1));
                                     }
-                                }
-                                lsp_len += (uint32_t)(tot & 0xffff);
-                                lip_len += (uint32_t)((tot >> 16) & 0xffff);
-                                nxt_len += (uint32_t)((tot >> 32) & 0xffff);
-                                if (has_dups) {
-                                    __syncthreads();
-                                    if (tid == 0) apply_queue(s_dq, (uint32_t)(tot >> 48), kf, rec, H, W, n);
-                                    __syncthreads();
+                                    if (!cut && has_desc_past_offspring(i, j, H, W)) nnext = 1;
+                                    if (has_dups && nlsp) {
+                                        for (uint32_t c4 = 0; c4 < nread; ++c4)
+                                            if ((sigmask & (1u << c4)) &&
+                                                in_dup_subtree(ci + (c4 >> 1), cj + (c4 & 1), ll_h, ll_w)) {
+                                                defmask |= 1u << c4;
+                                                ++ndef;
+                                            }
+                                    }
+                                } else {
+                                    nnext = has ? 4 : 0;
                                 }
                             }
-                            // retained sets [eprev, ecur)
-                            for (uint32_t cb = eprev; cb < ecur; cb += DEC_NT) {
-                                const uint32_t e = cb + tid;
-                                const bool valid = e < ecur;
-                                const bool keepit = valid && !((s_fmask[e >> 5] >> (e & 31)) & 1u);
-                                const uint32_t key = keepit ? cur[ebase + e] : 0u;
-                                uint64_t tot;
-                                const uint64_t ex = block_exscan<DEC_NT>(keepit ? 1ull : 0ull, s_wtot, tot);
-                                if (keepit) R[rkeep + (uint32_t)ex] = key;
-                                rkeep += (uint32_t)tot;
+                            const uint64_t pack = (uint64_t)nlsp | ((uint64_t)nlip << 12) | ((uint64_t)nnext << 24) |
+                                                  ((uint64_t)ndef << 36) | ((uint64_t)(avail && !fired) << 48);
+                            uint64_t tot;
+                            const uint64_t ex = block_exscan<DEC_NT>(pack, s_wtot, tot);
+                            if (avail && !fired) R[rkeep + (uint32_t)(ex >> 48)] = key;
+                            if (fired) {
+                                uint32_t os = lsp_len + (uint32_t)(ex & 0xfff);
+                                uint32_t oi = lip_len + (uint32_t)((ex >> 12) & 0xfff);
+                                const uint32_t on = nxt_len + (uint32_t)((ex >> 24) & 0xfff);
+                                uint32_t od = (uint32_t)((ex >> 36) & 0xfff);
+                                if (isA) {
+                                    for (uint32_t c4 = 0; c4 < nread; ++c4) {
+                                        const uint32_t y = ci + (c4 >> 1), x = cj + (c4 & 1);
+                                        const uint32_t ck = key_pack(kf, k, y, x);
+                                        if (sigmask & (1u << c4)) {
+                                            const int32_t val = (sgnmask & (1u << c4)) ? basev : -basev;
+                                            if (defmask & (1u << c4))
+                                                s_dq[od++] = make_uint2(ck, (uint32_t)val);
+                                            else
+                                                rec[((size_t)k * H + y) * W + x] = val;
+                                            lsp[os++] = ck;
+                                        } else {
+                                            lip[oi++] = ck;
+                                        }
+                                    }
+                                    if (nnext) nxt[on] = key & 0x7fffffffu;
+                                } else if (nnext) {
+#pragma unroll
+                                    for (int c4 = 0; c4 < 4; ++c4)
+                                        nxt[on + c4] = 0x80000000u | key_pack(kf, k, ci + (c4 >> 1), cj + (c4 & 1));
+                                }
                             }
-                            eprev = ecur;
-                            __syncthreads();
-                            if (end_now) ended = true;
-                            if (ended || ecur >= cnt) break;
+                            lsp_len += (uint32_t)(tot & 0xfff);
+                            lip_len += (uint32_t)((tot >> 12) & 0xfff);
+                            nxt_len += (uint32_t)((tot >> 24) & 0xfff);
+                            rkeep += (uint32_t)(tot >> 48);
+                            if (has_dups) {
+                                __syncthreads();
+                                if (tid == 0) apply_queue(s_dq, (uint32_t)((tot >> 36) & 0xfff), kf, rec, H, W, n);
+                                __syncthreads();
+                            }
                         }
+                        __syncthreads();  // s_x / s_tmask / s_grp are rewritten by the next round
+                        if (pos >= limit) ended = true;
                     }
                     uint32_t *old = cur;
                     cur = nxt;
@@ -468,7 +564,7 @@ __global__ void __launch_bounds__(DEC_NT) spiht_decode_kernel(const DecK p)
             if (!has_dups) {
                 for (uint32_t e = tid; e < lsp_len0; e += DEC_NT) {
                     const uint64_t q = pos + e;
-                    if (q < br.nbits) {
+                    if (q < limit) {
                         uint32_t k, i, j;
                         key_unpack(kf, lsp[e], k, i, j);
                         refine_cell(rec + ((size_t)k * H + i) * W + j, n, br.bit(q));
@@ -480,7 +576,7 @@ __global__ void __launch_bounds__(DEC_NT) spiht_decode_kernel(const DecK p)
                     const uint64_t q = pos + e;
                     bool defer = false;
                     uint32_t key = 0, bit = 0;
-                    if (e < lsp_len0 && q < br.nbits) {
+                    if (e < lsp_len0 && q < limit) {
                         key = lsp[e];
                         bit = br.bit(q);
                         uint32_t k, i, j;
@@ -497,7 +593,6 @@ __global__ void __launch_bounds__(DEC_NT) spiht_decode_kernel(const DecK p)
                 }
             }
             pos += lsp_len0;
-            if (pos >= br.nbits) ended = true;
             __syncthreads();
             if (n == 0) break;
         }
@@ -536,7 +631,7 @@ int launch_decode(spihtb_ctx *ctx, const DecArgs &a)
     const uint64_t lis_cap = std::min<uint64_t>(lis_shape, T0 + budget) + DEC_SLACK;
     k.pix_cap = pix_cap;
     k.lis_cap = lis_cap;
-    const size_t per_slot = (pix_cap * 2 + lis_cap * 3) * sizeof(uint32_t);
+    const size_t per_slot = (pix_cap * 3 + lis_cap * 3) * sizeof(uint32_t);
     int rc = ctx->ensure(ctx->lists, per_slot * slots + 256);
     if (rc) return rc;
     rc = ctx->ensure(ctx->misc, 256);
@@ -544,7 +639,7 @@ int launch_decode(spihtb_ctx *ctx, const DecArgs &a)
     uint32_t *base = static_cast<uint32_t *>(ctx->lists.p);
     k.lis = base;
     k.lip = base + (size_t)slots * lis_cap * 3;
-    k.lsp = k.lip + (size_t)slots * pix_cap;
+    k.lsp = k.lip + (size_t)slots * pix_cap * 2;
     k.counter = static_cast<unsigned int *>(ctx->misc.p);
 
     ctx->stage_begin(5);
