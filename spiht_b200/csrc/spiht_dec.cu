@@ -61,6 +61,35 @@ struct DecK {
     unsigned int *counter;
 };
 
+// per-phase cycle counters of image 0's CTA (tools/dec_phases.py); compiled in, costs a few clock reads per pass
+__device__ unsigned long long g_dec_prof[16];
+#define DEC_PROF_T0() const long long _t0 = clock64()
+#define DEC_PROF_ADD(slot)                                                        \
+    do {                                                                          \
+        if (tid == 0 && b == 0) g_dec_prof[slot] += (unsigned long long)(clock64() - _t0); \
+    } while (0)
+#define DEC_PROF_CNT(slot, v)                                  \
+    do {                                                       \
+        if (tid == 0 && b == 0) g_dec_prof[slot] += (v);       \
+    } while (0)
+
+__device__ __forceinline__ uint32_t lds_u8(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_u8(uint32_t addr, uint32_t v)
+{
+    asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
 struct BitRow {
     const uint32_t *row;
     uint64_t nwords;
@@ -166,6 +195,7 @@ __global__ void __launch_bounds__(DEC_NT, 2) spiht_decode_kernel(const DecK p)
     __shared__ uint64_t s_wtot[DEC_NW];
     __shared__ uint32_t s_wfn[DEC_NW];
     __shared__ uint64_t s_chain_p;
+    __shared__ uint8_t s_len[256];  // child-bit length of a fired A record from its next 8 bits
     __shared__ int s_img;
     __shared__ uint2 s_dq[DEC_DQ];  // {cell key | refine flag << 31, value or bit}
 
@@ -179,6 +209,19 @@ __global__ void __launch_bounds__(DEC_NT, 2) spiht_decode_kernel(const DecK p)
     uint32_t *G0 = R + p.lis_cap;
     uint32_t *G1 = G0 + p.lis_cap;
     const bool has_dups = ((ll_h | ll_w) & 1u) != 0;
+    if (tid < 256) {  // index: the 8 bits after the fire bit, first bit in bit 7
+        uint32_t cb = (uint32_t)tid << 24, len = 4;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            if (cb >> 31) {
+                cb <<= 2;
+                ++len;
+            } else {
+                cb <<= 1;
+            }
+        }
+        s_len[tid] = (uint8_t)len;
+    }
     // bits per thread in a LIP round; the ordered write queue bounds it when cells can be duplicated
     const int BPT = has_dups ? 4 : 32;
 
@@ -223,6 +266,7 @@ __global__ void __launch_bounds__(DEC_NT, 2) spiht_decode_kernel(const DecK p)
         __syncthreads();
 
         uint64_t pos = 0;  // uniform: next unread bit
+        const long long _timg = clock64();
         for (; pos < limit; --n) {
             const int32_t basev = n == 0 ? 1 : (int32_t)((1u << (n - 1)) + (1u << n));
             const uint32_t lsp_len0 = lsp_len;
@@ -231,6 +275,7 @@ __global__ void __launch_bounds__(DEC_NT, 2) spiht_decode_kernel(const DecK p)
             {
                 uint32_t done_e = 0, keep = 0;
                 while (done_e < lip_len && pos < limit) {
+                    DEC_PROF_T0();
                     // this thread's window: BPT bits at wp; bits at or past `limit` are not data
                     const uint64_t wp = pos + (uint64_t)tid * BPT;
                     uint32_t nv = wp < limit ? (uint32_t)min((uint64_t)BPT, limit - wp) : 0u;
@@ -351,6 +396,8 @@ __global__ void __launch_bounds__(DEC_NT, 2) spiht_decode_kernel(const DecK p)
                     } else {
                         pos = pos + (uint64_t)DEC_NT * BPT + (s_last ? 0u : 1u);
                     }
+                    DEC_PROF_ADD(0);
+                    DEC_PROF_CNT(8, 1);
                 }
                 if (done_e < lip_len) break;  // the stream ended inside the pass
                 uint32_t *t = lip;
@@ -370,6 +417,7 @@ __global__ void __launch_bounds__(DEC_NT, 2) spiht_decode_kernel(const DecK p)
                     uint32_t nxt_len = 0;
                     for (uint32_t ebase = 0; ebase < cur_len && !ended; ebase += DEC_CH) {
                         const uint32_t cnt = min((uint32_t)DEC_CH, cur_len - ebase);
+                        DEC_PROF_T0();
                         // set-type mask of this round's entries; clear the child-length bytes
                         for (uint32_t w = wid; w < (cnt + 31) / 32 + 3; w += DEC_NW) {
                             const uint32_t e = w * 32 + lane;
@@ -381,51 +429,91 @@ __global__ void __launch_bounds__(DEC_NT, 2) spiht_decode_kernel(const DecK p)
                                 a_with_children = offspring_corner(i, j, H, W, ll_h, ll_w, ci, cj);
                             }
                             const uint32_t m = __ballot_sync(0xffffffffu, a_with_children);
-                            if (lane == 0) s_tmask[w] = m;
+                            if (lane == 0) s_tmask[w] = __brev(m);  // MSB-first for the chain
                             if (e < DEC_CH) s_x[e] = 0;
                         }
                         __syncthreads();
+                        DEC_PROF_ADD(1);
                         // ---- chain: one thread jumps from fired A set to fired A set
                         if (tid == 0) {
-                            uint64_t cp = pos;
-                            uint32_t e = 0;
-                            while (e < cnt && cp < limit) {
-                                const uint64_t sb = br.get64(cp);
-                                const uint32_t tw = e >> 5;
-                                const int tsh = (int)(e & 31);
-                                const uint32_t t0 = s_tmask[tw], t1 = s_tmask[tw + 1], t2 = s_tmask[tw + 2];
-                                const uint64_t tb = (uint64_t)__funnelshift_r(t0, t1, tsh) |
-                                                    ((uint64_t)__funnelshift_r(t1, t2, tsh) << 32);
-                                uint64_t lim = cnt - e;
-                                if (lim > 64) lim = 64;
-                                const uint64_t rem = limit - cp;
-                                if (rem < lim) lim = rem;
-                                uint64_t m = sb & tb;
-                                if (lim < 64) m &= (1ull << lim) - 1ull;
-                                if (m == 0) {
-                                    e += (uint32_t)lim;
-                                    cp += lim;
-                                    continue;
+                            const long long _tc = clock64();
+                            uint32_t n_it = 0, n_ev = 0;
+                            // Everything is kept MSB-first (words bit-reversed on load) so that the next
+                            // fired A set is one count-leading-zeros away.  r0..r2: stream words, sS =
+                            // consumed bits of r0, r3/r4 prefetched; t0, t1: set-type words, sT likewise.
+                            // Shared memory is addressed with 32-bit shared-space addresses.
+                            const uint64_t avail = limit - pos;
+                            const uint32_t pmax = avail > 0xfffffff0ull ? 0xfffffff0u : (uint32_t)avail;
+                            const uint32_t *wp = br.row + (pos >> 5);
+                            const uint32_t *const wend = br.row + br.nwords;
+                            auto next_word = [&]() -> uint32_t {
+                                const uint32_t v = wp < wend ? __ldg(wp) : 0u;
+                                ++wp;
+                                return __brev(v);
+                            };
+                            uint32_t sS = (uint32_t)(pos & 31), sT = 0;
+                            uint32_t r0 = next_word(), r1 = next_word(), r2 = next_word(), r3 = next_word(),
+                                     r4 = next_word();
+                            uint32_t a_lut = (uint32_t)__cvta_generic_to_shared(s_len);
+                            uint32_t a_x = (uint32_t)__cvta_generic_to_shared(s_x);
+                            uint32_t a_t = (uint32_t)__cvta_generic_to_shared(s_tmask);
+                            // keep the addresses in registers (the compiler would otherwise rebuild them
+                            // from a special register inside the loop)
+                            asm volatile("" : "+r"(a_lut), "+r"(a_x), "+r"(a_t));
+                            uint32_t t0 = lds_u32(a_t), t1 = lds_u32(a_t + 4), t2 = lds_u32(a_t + 8);
+                            a_t += 12;
+                            uint32_t e = 0, pr = 0;  // entries / bits consumed in this round
+                            while (e < cnt && pr < pmax) {
+                                const uint32_t w0 = __funnelshift_l(r1, r0, sS), w1 = __funnelshift_l(r2, r1, sS);
+                                const uint32_t tt = __funnelshift_l(t1, t0, sT);
+                                const uint32_t nl = min(32u, cnt - e);
+                                const uint32_t lz = (uint32_t)__clz((int)(w0 & tt));  // 32: no fired A set ahead
+                                const bool ev = lz < 32;
+                                const uint32_t sh = ev ? lz + 1 : nl;
+                                uint32_t len = 0;
+                                if (ev) {
+                                    len = lds_u8(a_lut + (__funnelshift_lc(w1, w0, sh) >> 24));
+                                    sts_u8(a_x + e + lz, len);
                                 }
-                                const int z = __ffsll((long long)m) - 1;
-                                e += z;
-                                cp += z;
-                                uint32_t cb = (z + 9 <= 64) ? (uint32_t)(sb >> (z + 1)) : br.get32(cp + 1);
-                                uint32_t len = 4;
-#pragma unroll
-                                for (int r = 0; r < 4; ++r) {
-                                    if (cb & 1u) {
-                                        cb >>= 2;
-                                        ++len;
-                                    } else {
-                                        cb >>= 1;
+                                n_it += 1;
+                                n_ev += ev ? 1u : 0u;
+                                e += sh;
+                                sT += sh;
+                                const uint32_t adv = sh + len;
+                                pr += adv;
+                                sS += adv;
+                                if (sT >= 32) {
+                                    sT -= 32;
+                                    t0 = t1;
+                                    t1 = t2;
+                                    t2 = lds_u32(a_t);
+                                    a_t += 4;
+                                }
+                                if (sS >= 32) {
+                                    sS -= 32;
+                                    r0 = r1;
+                                    r1 = r2;
+                                    r2 = r3;
+                                    r3 = r4;
+                                    r4 = next_word();
+                                    if (sS >= 32) {
+                                        sS -= 32;
+                                        r0 = r1;
+                                        r1 = r2;
+                                        r2 = r3;
+                                        r3 = r4;
+                                        r4 = next_word();
                                     }
                                 }
-                                s_x[e] = (uint8_t)len;
-                                cp += 1 + len;
-                                e += 1;
                             }
+                            const uint64_t cp = pos + pr;
                             s_chain_p = cp + (cnt - e);  // entries past the end of the stream: one bit each
+                            if (b == 0) {
+                                g_dec_prof[2] += (unsigned long long)(clock64() - _tc);
+                                g_dec_prof[9] += n_it;
+                                g_dec_prof[10] += n_ev;
+                                g_dec_prof[11] += 1;
+                            }
                         }
                         __syncthreads();
                         const uint64_t p_base = pos;
@@ -444,6 +532,7 @@ __global__ void __launch_bounds__(DEC_NT, 2) spiht_decode_kernel(const DecK p)
                             if (tid < DEC_CH / 32) s_grp[tid] = (uint32_t)ex;
                         }
                         __syncthreads();
+                        const long long _tb = clock64();
                         // ---- every entry: its own bit, then the fired sets' records
                         for (uint32_t eb = 0; eb < cnt; eb += DEC_NT) {
                             const uint32_t e = eb + tid;
@@ -548,6 +637,10 @@ __global__ void __launch_bounds__(DEC_NT, 2) spiht_decode_kernel(const DecK p)
                             }
                         }
                         __syncthreads();  // s_x / s_tmask / s_grp are rewritten by the next round
+                        if (tid == 0 && b == 0) {
+                            g_dec_prof[3] += (unsigned long long)(clock64() - _tb);
+                            g_dec_prof[12] += (cnt + DEC_NT - 1) / DEC_NT;
+                        }
                         if (pos >= limit) ended = true;
                     }
                     uint32_t *old = cur;
@@ -561,6 +654,7 @@ __global__ void __launch_bounds__(DEC_NT, 2) spiht_decode_kernel(const DecK p)
             if (ended) break;
 
             // ================= refinement (encoder_decoder.rs:439-444)
+            DEC_PROF_T0();
             if (!has_dups) {
                 for (uint32_t e = tid; e < lsp_len0; e += DEC_NT) {
                     const uint64_t q = pos + e;
@@ -594,10 +688,21 @@ __global__ void __launch_bounds__(DEC_NT, 2) spiht_decode_kernel(const DecK p)
             }
             pos += lsp_len0;
             __syncthreads();
+            DEC_PROF_ADD(4);
             if (n == 0) break;
         }
         __syncthreads();
+        if (tid == 0 && b == 0) g_dec_prof[5] += (unsigned long long)(clock64() - _timg);
     }
+}
+
+// debug: read and clear the phase counters (tools/dec_phases.py)
+extern "C" int spihtb_debug_dec_prof(unsigned long long *out16)
+{
+    unsigned long long z[16] = {0};
+    if (cudaMemcpyFromSymbol(out16, g_dec_prof, sizeof(z)) != cudaSuccess) return SPIHTB_ECUDA;
+    if (cudaMemcpyToSymbol(g_dec_prof, z, sizeof(z)) != cudaSuccess) return SPIHTB_ECUDA;
+    return SPIHTB_OK;
 }
 
 int launch_decode(spihtb_ctx *ctx, const DecArgs &a)

@@ -1,0 +1,29 @@
+"""Debug: per-phase cycle counts of the decoder for image 0 of a batch (spihtb_debug_dec_prof)."""
+import argparse, ctypes, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import spiht_b200 as spiht
+from spiht_b200 import _lib, batch
+from spiht_b200.utils import synthetic_images
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--batch", type=int, default=256)
+ap.add_argument("--size", type=int, default=1024)
+ap.add_argument("--bpp", type=float, default=0.5)
+a = ap.parse_args()
+st = spiht.SpihtSettings()
+g = _lib.plan(a.size, a.size, "bior2.2", "reflect")
+px = synthetic_images(a.batch, 3, a.size, a.size, seed=2000)
+mb = int(a.size * a.size * a.bpp)
+s, nbits, max_n, status, coeffs = batch.encode_images(px, g, st, mb)
+nbytes = (nbits + 7) // 8
+out = (ctypes.c_ulonglong * 16)()
+lib = _lib.lib()
+for it in range(3):
+    batch.decode_images(s, nbytes, max_n, 3, g, st, dtype=torch.float32)
+    torch.cuda.synchronize()
+    lib.spihtb_debug_dec_prof(out)
+    v = list(out)
+    names = ["lip_rounds", "lis_tmask", "chain", "lis_batches", "refine", "image_total"]
+    print({n: v[i] for i, n in enumerate(names)},
+          {"lip_rounds_n": v[8], "chain_iters": v[9], "chain_events": v[10], "lis_rounds": v[11], "lis_batches_n": v[12]})
