@@ -13,6 +13,8 @@
 //     (or, at the last level, quantised into the LL corner).
 // analysis (non-periodization): out[k] = sum_j f[j] x_ext[2k + 1 - j]
 // periodization:                out[k] = sum_j f[j] x_per[(2k + F/2 - j) mod Np]
+#include <string.h>
+
 #include <algorithm>
 
 #include "common.cuh"
@@ -38,200 +40,311 @@ struct FwdK {
     double q;
 };
 
+// out-of-line boundary rule: keeps the division sequences out of the streaming loop's code
+__device__ __noinline__ int ext_index_slow(int g, int n, int mode) { return ext_index(g, n, mode); }
+
 // spiht_wrapper.py:9-11,167-172: ((m_c * x) * q).astype(int32), truncation toward zero
 __device__ __forceinline__ int32_t quantise(double x, double m, double q) { return __double2int_rz((m * x) * q); }
+// m == 1.0: (1.0 * x) * q == x * q exactly
+__device__ __forceinline__ int32_t quantise1(double x, double q) { return __double2int_rz(x * q); }
 
-template <typename T>
-struct Pair;
-template <>
-struct Pair<float> {
-    using type = float2;
-};
-template <>
-struct Pair<double> {
-    using type = double2;
+// ---- asynchronous global -> shared copies (LDGSTS): the input prefetch queue lives in shared memory,
+// costs no registers and no scoreboard slot, and can run many row pairs ahead of the arithmetic
+template <int BYTES>
+__device__ __forceinline__ void cp_async(uint32_t saddr, const void *gptr)
+{
+    static_assert(BYTES == 4 || BYTES == 8 || BYTES == 16, "cp.async copies 4, 8 or 16 bytes");
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(saddr), "l"(gptr), "n"(BYTES) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait()
+{
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+// NC elements of Tin from this lane's shared-memory slot
+template <typename Tin, int NC>
+__device__ __forceinline__ void lds_frag(uint32_t saddr, Tin (&v)[NC])
+{
+    constexpr int BYTES = NC * (int)sizeof(Tin);
+    if constexpr (BYTES == 8) {
+        uint2 r;
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(saddr));
+        memcpy(v, &r, 8);
+    } else {
+        static_assert(BYTES % 16 == 0, "row fragment must be 8 bytes or a multiple of 16");
+#pragma unroll
+        for (int q = 0; q < BYTES / 16; ++q) {
+            uint4 r;
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                         : "r"(saddr + 16 * q));
+            memcpy(reinterpret_cast<char *>(v) + 16 * q, &r, 16);
+        }
+    }
+}
+
+template <int WID>
+struct FwdCfg {
+    static constexpr int F = Wav<WID>::F;
+    static constexpr int HF = F / 2;
+    static constexpr int NP = F == 6 ? 2 : 1;  // column pairs per lane (register budget: F rows x 2 NP columns)
+    static constexpr int NC = 2 * NP;
+    static constexpr int NOUT = 32 * NP - (HF - 1);
+    // prefetch ring depth in row pairs: a multiple of HF (static slot offsets in the unrolled loop)
+    static constexpr int DEPTH = HF == 3 ? 6 : HF;
 };
 
-// One warp = one task: a strip of NOUT = 32 - (F/2 - 1) output columns by RH output
-// rows of one (image, channel) plane.  Lane l owns the input column pair
-// (E, O) = (x[2m], x[2m+1]), m = k0 - (F/2-1) + l, and walks down the rows:
-//   axis -2: a register window of F rows of its two columns gives the row-filtered
-//            (lo, hi) pair of both columns -- no exchange needed;
-//   axis -1: out[k] = sum_u f[2u] O[k-u] + f[2u+1] E[k-u] takes the neighbours'
-//            values by warp shuffle (lanes l-1 .. l-(F/2-1)); lanes >= F/2-1 own an
-//            output column.
+// One warp = one task: a strip of NOUT = 32 NP - (F/2 - 1) output columns by RH output
+// rows of one (image, channel) plane.  Lane l owns the NP input column pairs
+// (E, O) = (x[2m], x[2m+1]), m = k0 - (F/2-1) + NP l + t, and walks down the rows:
+//   axis -2: a register window of F rows of its 2 NP columns gives the row-filtered
+//            (lo, hi) values of every column -- no exchange needed;
+//   axis -1: out[k] = sum_v f[2v] O[k-v] + f[2v+1] E[k-v] takes the pairs to its left
+//            from its own registers or, by warp shuffle, from the lanes before it;
+//            the first (F/2-1)/NP lanes only feed their neighbours.
 // No shared memory and no barrier: warps are independent, every input sample is
-// read from HBM once per strip (the F-2 halo columns hit L1/L2), loads are
-// prefetched PD row pairs ahead, each lane writes its four band values
-// (approximation as float64 scratch for the next level, details quantised).
-template <typename Tin, int WID, bool INSIDE>
-__device__ __forceinline__ void dwt_fwd_task(const FwdK &p, int tx, int ty, int z)
+// read from HBM once per strip (the F-2 halo columns hit L1/L2).  Input rows are
+// prefetched DEPTH row pairs ahead with cp.async into a per-warp shared-memory ring
+// (every lane copies and later reads back only its own fragment, so no barrier is
+// needed); each lane writes its band values (approximation as float64 scratch for
+// the next level, details quantised).  A lane whose columns lie inside the plane
+// (and whose rows are vector-aligned) copies its fragment as one vector; the halo
+// lanes of the edge strips go through the boundary map one element at a time.
+template <typename Tin, int WID, int NP>
+__device__ __forceinline__ void dwt_fwd_task(const FwdK &p, int tx, int ty, int z, uint32_t ring, bool aligned)
 {
     constexpr int F = Wav<WID>::F;
     constexpr int HF = F / 2;
-    constexpr int NOUT = 32 - (HF - 1);
-    constexpr int PD = (HF % 3 == 0) ? 3 : HF;  // prefetch distance in row pairs; divides HF
-    using Tin2 = typename Pair<Tin>::type;
+    constexpr int NC = 2 * NP;
+    static_assert((HF - 1) % NP == 0, "halo must be a whole number of lanes");
+    constexpr int HL = (HF - 1) / NP;           // lanes that only feed their neighbours
+    constexpr int NOUT = 32 * NP - (HF - 1);
+    constexpr int DEPTH = FwdCfg<WID>::DEPTH;
+    constexpr int FRAG = NC * (int)sizeof(Tin);  // bytes of one lane's row fragment
+    constexpr int SLOT = 2 * 32 * FRAG;          // one row pair of the warp
+    constexpr unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const int src_h = p.src_h, src_w = p.src_w, mode = p.mode;
     const int sft = mode == SPIHTB_MODE_PERIODIZATION ? (HF - 1) : 0;  // even for every supported wavelet
     const int k0 = tx * NOUT, r0 = ty * p.RH;
     const int nrows = min(p.RH, p.bh - r0);
-    const int k = k0 - (HF - 1) + lane;  // this lane's pair index = its output column
-    const int gcE = 2 * k + sft;
-    const int gr0 = 2 * r0 - (F - 2) + sft;
+    const int kf = k0 - (HF - 1) + NP * lane;  // this lane's first pair index = its first output column
+    const int gc = 2 * kf + sft;               // its first input column
+    const int gr0 = 2 * r0 - (F - 2) + sft;    // first input row of the chunk's window
 
     const Tin *plane = static_cast<const Tin *>(p.src) + (size_t)z * src_h * src_w;
-    // whole strip inside the plane and rows pair-aligned: one vector load per row
-    const int gc_first = 2 * (k0 - (HF - 1)) + sft;
-    const bool vec = gc_first >= 0 && gc_first + 63 < src_w && (src_w & 1) == 0 &&
-                     (reinterpret_cast<uintptr_t>(plane) & (2 * sizeof(Tin) - 1)) == 0;
-    const int colE = vec ? gcE : ext_index(gcE, src_w, mode);
-    const int colO = vec ? gcE + 1 : ext_index(gcE + 1, src_w, mode);
+    const bool lane_vec = aligned && gc >= 0 && gc + NC <= src_w;
+    int col[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) col[c] = lane_vec ? gc + c : ext_index(gc + c, src_w, mode);
 
-    auto load_row = [&](int li, Tin &e, Tin &o) {
-        const int gi = INSIDE ? gr0 + li : ext_index(gr0 + li, src_h, mode);
-        const Tin *row = plane + (size_t)gi * src_w;
-        if (vec) {
-            const Tin2 v = __ldg(reinterpret_cast<const Tin2 *>(row + colE));
-            e = v.x;
-            o = v.y;
-        } else {
-            e = __ldg(row + colE);
-            o = __ldg(row + colO);
+    // rows gr, gr+1 (warp-uniform; any integer) -> ring slot `slot` (row 0 at +0, row 1 at +32 FRAG)
+    const Tin *runp = plane + (ptrdiff_t)gr0 * src_w;  // row gr of the plane while gr is inside it
+    int gr = gr0;
+    const uint32_t my = ring + lane * FRAG;
+    auto fetch_pair = [&](uint32_t slot_off) {
+        const Tin *pa = runp, *pb = runp + src_w;
+        if (gr < 0 || gr + 1 >= src_h) {  // rare (warp-uniform): boundary rows go through the extension map
+            pa = plane + (size_t)ext_index_slow(gr, src_h, mode) * src_w;
+            pb = plane + (size_t)ext_index_slow(gr + 1, src_h, mode) * src_w;
         }
+        const uint32_t sa = my + slot_off, sb = sa + 32 * FRAG;
+        if (lane_vec) {
+            constexpr int VB = FRAG >= 16 ? 16 : 8;
+#pragma unroll
+            for (int o = 0; o < FRAG; o += VB) {
+                cp_async<VB>(sa + o, reinterpret_cast<const char *>(pa + gc) + o);
+                cp_async<VB>(sb + o, reinterpret_cast<const char *>(pb + gc) + o);
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                cp_async<(int)sizeof(Tin)>(sa + c * (int)sizeof(Tin), pa + col[c]);
+                cp_async<(int)sizeof(Tin)>(sb + c * (int)sizeof(Tin), pb + col[c]);
+            }
+        }
+        cp_async_commit();
+        gr += 2;
+        runp += 2 * (ptrdiff_t)src_w;
+    };
+    // the oldest outstanding row pair (DEPTH are in flight) has landed: read it back
+    auto take_pair = [&](uint32_t slot_off, Tin (&a)[NC], Tin (&b)[NC]) {
+        cp_async_wait<DEPTH - 1>();
+        const uint32_t sa = my + slot_off;
+        lds_frag<Tin, NC>(sa, a);
+        lds_frag<Tin, NC>(sa + 32 * FRAG, b);
     };
 
+    // row pair j of the chunk (local rows 2j, 2j+1) goes through ring slot j % DEPTH; pairs 0 .. HF-2
+    // fill the window, pair HF-1+i completes output row i.  DEPTH pairs are always in flight.
+    static_assert(DEPTH >= HF - 1, "ring depth");
+#pragma unroll
+    for (int j = 0; j < DEPTH; ++j) fetch_pair(j * SLOT);
     // local row li of the chunk lives in window slot li % F; output row i needs rows 2i .. 2i+F-1
-    double wE[F], wO[F];
+    double w[F][NC];
 #pragma unroll
-    for (int t = 0; t < F - 2; ++t) {
-        Tin e, o;
-        load_row(t, e, o);
-        wE[t] = (double)e;
-        wO[t] = (double)o;
-    }
-    Tin qE[PD][2], qO[PD][2];
+    for (int j = 0; j < HF - 1; ++j) {
+        Tin a[NC], b[NC];
+        take_pair(j * SLOT, a, b);
 #pragma unroll
-    for (int s = 0; s < PD; ++s) {
-        qE[s][0] = qE[s][1] = qO[s][0] = qO[s][1] = (Tin)0;
-        if (s < nrows) {
-            load_row(F - 2 + 2 * s, qE[s][0], qO[s][0]);
-            load_row(F - 1 + 2 * s, qE[s][1], qO[s][1]);
+        for (int c = 0; c < NC; ++c) {
+            w[2 * j][c] = (double)a[c];
+            w[2 * j + 1][c] = (double)b[c];
         }
+        fetch_pair(j * SLOT);  // pair j + DEPTH
     }
+    uint32_t slot_off = ((HF - 1) % DEPTH) * SLOT;  // ring slot of the next pair to take
 
     const int zc = z % p.C;
-    const double m = p.scale[zc], q = p.q;
-    const bool out_active = lane >= HF - 1 && k < p.bw;
+    const double m = p.scale[zc], qs = p.q;
+    const bool unit_m = m == 1.0;
+    bool col_ok[NP];
+#pragma unroll
+    for (int t = 0; t < NP; ++t) col_ok[t] = lane >= HL && kf + t < p.bw;
     const int Wc = p.Wc;
     int32_t *cz = p.coeffs + (size_t)z * p.Hc * Wc;
-    int32_t *p_aa = cz + (size_t)r0 * Wc + k;           // LL corner (last level only)
-    int32_t *p_ad = p_aa + p.sw;                        // rows lo, cols hi: top right
-    int32_t *p_da = cz + (size_t)(p.sh + r0) * Wc + k;  // rows hi, cols lo: bottom left
+    int32_t *p_aa = cz + (ptrdiff_t)r0 * Wc + kf;           // LL corner (last level only)
+    int32_t *p_ad = p_aa + p.sw;                            // rows lo, cols hi: top right
+    int32_t *p_da = cz + (ptrdiff_t)(p.sh + r0) * Wc + kf;  // rows hi, cols lo: bottom left
     int32_t *p_dd = p_da + p.sw;
     const bool ll_scratch = !p.last;
-    double *p_ll = ll_scratch ? p.dst_ll + ((size_t)z * p.bh + r0) * p.bw + k : nullptr;
+    double *p_ll = ll_scratch ? p.dst_ll + ((size_t)z * p.bh + r0) * p.bw + kf : nullptr;
     const int bw = p.bw;
 
-    for (int rb = 0; rb < nrows; rb += HF) {
+    // the loop body is unrolled over HF rows so that the window slots are static
+    const int niter = (nrows + HF - 1) / HF;
+    for (int it = 0; it < niter; ++it) {
 #pragma unroll
         for (int u = 0; u < HF; ++u) {
-            const int i = rb + u;
-            if (i < nrows) {
-                const int slot = u % PD;
-                wE[(2 * u + F - 2) % F] = (double)qE[slot][0];
-                wO[(2 * u + F - 2) % F] = (double)qO[slot][0];
-                wE[(2 * u + F - 1) % F] = (double)qE[slot][1];
-                wO[(2 * u + F - 1) % F] = (double)qO[slot][1];
-                if (i + PD < nrows) {
-                    load_row(2 * (i + PD) + F - 2, qE[slot][0], qO[slot][0]);
-                    load_row(2 * (i + PD) + F - 1, qE[slot][1], qO[slot][1]);
-                }
-                // axis -2: tap j multiplies local row 2i + F-1 - j
-                double loE = 0.0, loO = 0.0, hiE = 0.0, hiO = 0.0;
+            const int i = it * HF + u;  // rows past nrows (fewer than HF) are computed and dropped
+            {
+                Tin a[NC], b[NC];
+                take_pair(slot_off, a, b);
 #pragma unroll
-                for (int j = 0; j < F; ++j) {
-                    const double ve = wE[(2 * u + F - 1 - j) % F], vo = wO[(2 * u + F - 1 - j) % F];
-                    if (Wav<WID>::dec_lo(j) != 0.0) {
-                        loE = fma(Wav<WID>::dec_lo(j), ve, loE);
-                        loO = fma(Wav<WID>::dec_lo(j), vo, loO);
-                    }
-                    if (wav_dec_hi<WID>(j) != 0.0) {
-                        hiE = fma(wav_dec_hi<WID>(j), ve, hiE);
-                        hiO = fma(wav_dec_hi<WID>(j), vo, hiO);
+                for (int c = 0; c < NC; ++c) {
+                    w[(2 * u + F - 2) % F][c] = (double)a[c];
+                    w[(2 * u + F - 1) % F][c] = (double)b[c];
+                }
+            }
+            fetch_pair(slot_off);
+            slot_off = slot_off + SLOT == DEPTH * SLOT ? 0u : slot_off + SLOT;
+            // axis -2: tap j multiplies local row 2i + F-1 - j
+            double lo[NC], hi[NC];
+#pragma unroll
+            for (int c = 0; c < NC; ++c) lo[c] = hi[c] = 0.0;
+#pragma unroll
+            for (int j = 0; j < F; ++j) {
+#pragma unroll
+                for (int c = 0; c < NC; ++c) {
+                    const double v = w[(2 * u + F - 1 - j) % F][c];
+                    if (Wav<WID>::dec_lo(j) != 0.0) lo[c] = fma(Wav<WID>::dec_lo(j), v, lo[c]);
+                    if (wav_dec_hi<WID>(j) != 0.0) hi[c] = fma(wav_dec_hi<WID>(j), v, hi[c]);
+                }
+            }
+            // pairs at offsets -(HF-1) .. NP-1 from this lane's first pair: own registers or the lanes before
+            double xlo[HF - 1 + NP][2], xhi[HF - 1 + NP][2];
+#pragma unroll
+            for (int j = 0; j < HF - 1 + NP; ++j) {
+                const int s = j - (HF - 1);
+                if (s >= 0) {
+                    xlo[j][0] = lo[2 * s];
+                    xlo[j][1] = lo[2 * s + 1];
+                    xhi[j][0] = hi[2 * s];
+                    xhi[j][1] = hi[2 * s + 1];
+                } else {
+                    const int d = (-s + NP - 1) / NP, idx = s + d * NP;
+#pragma unroll
+                    for (int eo = 0; eo < 2; ++eo) {
+                        // tap 2v multiplies O (eo = 1), tap 2v+1 multiplies E (eo = 0); skip all-zero taps
+                        bool used = false;
+#pragma unroll
+                        for (int t = 0; t < NP; ++t) {
+                            const int v = t - s;
+                            if (v >= 0 && v < HF) {
+                                const int tap = eo ? 2 * v : 2 * v + 1;
+                                used = used || Wav<WID>::dec_lo(tap) != 0.0 || wav_dec_hi<WID>(tap) != 0.0;
+                            }
+                        }
+                        xlo[j][eo] = used ? __shfl_up_sync(FULL, lo[2 * idx + eo], d) : 0.0;
+                        xhi[j][eo] = used ? __shfl_up_sync(FULL, hi[2 * idx + eo], d) : 0.0;
                     }
                 }
-                // axis -1: tap 2u' multiplies O[k-u'], tap 2u'+1 multiplies E[k-u']
+            }
+            const bool row_ok = i < nrows;
+#pragma unroll
+            for (int t = 0; t < NP; ++t) {
+                // axis -1: tap 2v multiplies O[k-v], tap 2v+1 multiplies E[k-v]
                 double aa = 0.0, ad = 0.0, da = 0.0, dd = 0.0;
 #pragma unroll
                 for (int v = 0; v < HF; ++v) {
-                    constexpr unsigned FULL = 0xffffffffu;
-                    const bool needO = Wav<WID>::dec_lo(2 * v) != 0.0 || wav_dec_hi<WID>(2 * v) != 0.0;
-                    const bool needE = Wav<WID>::dec_lo(2 * v + 1) != 0.0 || wav_dec_hi<WID>(2 * v + 1) != 0.0;
-                    if (needO) {
-                        const double lo_o = v ? __shfl_up_sync(FULL, loO, v) : loO;
-                        const double hi_o = v ? __shfl_up_sync(FULL, hiO, v) : hiO;
-                        if (Wav<WID>::dec_lo(2 * v) != 0.0) {
-                            aa = fma(Wav<WID>::dec_lo(2 * v), lo_o, aa);
-                            da = fma(Wav<WID>::dec_lo(2 * v), hi_o, da);
-                        }
-                        if (wav_dec_hi<WID>(2 * v) != 0.0) {
-                            ad = fma(wav_dec_hi<WID>(2 * v), lo_o, ad);
-                            dd = fma(wav_dec_hi<WID>(2 * v), hi_o, dd);
-                        }
+                    const int j = t - v + (HF - 1);
+                    if (Wav<WID>::dec_lo(2 * v) != 0.0) {
+                        aa = fma(Wav<WID>::dec_lo(2 * v), xlo[j][1], aa);
+                        da = fma(Wav<WID>::dec_lo(2 * v), xhi[j][1], da);
                     }
-                    if (needE) {
-                        const double lo_e = v ? __shfl_up_sync(FULL, loE, v) : loE;
-                        const double hi_e = v ? __shfl_up_sync(FULL, hiE, v) : hiE;
-                        if (Wav<WID>::dec_lo(2 * v + 1) != 0.0) {
-                            aa = fma(Wav<WID>::dec_lo(2 * v + 1), lo_e, aa);
-                            da = fma(Wav<WID>::dec_lo(2 * v + 1), hi_e, da);
-                        }
-                        if (wav_dec_hi<WID>(2 * v + 1) != 0.0) {
-                            ad = fma(wav_dec_hi<WID>(2 * v + 1), lo_e, ad);
-                            dd = fma(wav_dec_hi<WID>(2 * v + 1), hi_e, dd);
-                        }
+                    if (wav_dec_hi<WID>(2 * v) != 0.0) {
+                        ad = fma(wav_dec_hi<WID>(2 * v), xlo[j][1], ad);
+                        dd = fma(wav_dec_hi<WID>(2 * v), xhi[j][1], dd);
+                    }
+                    if (Wav<WID>::dec_lo(2 * v + 1) != 0.0) {
+                        aa = fma(Wav<WID>::dec_lo(2 * v + 1), xlo[j][0], aa);
+                        da = fma(Wav<WID>::dec_lo(2 * v + 1), xhi[j][0], da);
+                    }
+                    if (wav_dec_hi<WID>(2 * v + 1) != 0.0) {
+                        ad = fma(wav_dec_hi<WID>(2 * v + 1), xlo[j][0], ad);
+                        dd = fma(wav_dec_hi<WID>(2 * v + 1), xhi[j][0], dd);
                     }
                 }
-                if (out_active) {
-                    *p_ad = quantise(ad, m, q);
-                    *p_da = quantise(da, m, q);
-                    *p_dd = quantise(dd, m, q);
+                if (!unit_m) {  // warp-uniform
+                    ad *= m;
+                    da *= m;
+                    dd *= m;
+                    if (!ll_scratch) aa *= m;
+                }
+                if (row_ok && col_ok[t]) {
+                    p_ad[t] = quantise1(ad, qs);
+                    p_da[t] = quantise1(da, qs);
+                    p_dd[t] = quantise1(dd, qs);
                     if (ll_scratch)
-                        *p_ll = aa;
+                        p_ll[t] = aa;
                     else
-                        *p_aa = quantise(aa, m, q);
+                        p_aa[t] = quantise1(aa, qs);
                 }
-                p_aa += Wc;
-                p_ad += Wc;
-                p_da += Wc;
-                p_dd += Wc;
-                if (ll_scratch) p_ll += bw;
             }
+            p_aa += Wc;
+            p_ad += Wc;
+            p_da += Wc;
+            p_dd += Wc;
+            if (ll_scratch) p_ll += bw;
         }
     }
 }
 
-template <typename Tin, int WID>
+template <typename Tin, int WID, int NP>
 __global__ void __launch_bounds__(FW_WARPS * 32) dwt_fwd_level_kernel(const FwdK p)
 {
     constexpr int F = Wav<WID>::F;
+    constexpr int NOUT = 32 * NP - (F / 2 - 1);
+    constexpr int DEPTH = FwdCfg<WID>::DEPTH;
+    constexpr int WARP_RING = DEPTH * 2 * 32 * 2 * NP * (int)sizeof(Tin);
+    __shared__ __align__(16) unsigned char s_ring[FW_WARPS * WARP_RING];
+    const uint32_t ring = (uint32_t)__cvta_generic_to_shared(s_ring) + (threadIdx.x >> 5) * WARP_RING;
     long long task = (long long)blockIdx.x * FW_WARPS + (threadIdx.x >> 5);
     if (task >= p.ntasks) return;
     const int tx = (int)(task % p.tiles_x);
     task /= p.tiles_x;
     const int ty = (int)(task % p.tiles_y);
     const int z = (int)(task / p.tiles_y);
-    const int r0 = ty * p.RH;
-    const int nrows = min(p.RH, p.bh - r0);
+    // every row fragment of the strip vector-aligned (warp-uniform)
     const int sft = p.mode == SPIHTB_MODE_PERIODIZATION ? (F / 2 - 1) : 0;
-    const int gr0 = 2 * r0 - (F - 2) + sft;
-    // rows of the chunk's window all inside the plane (warp-uniform)
-    if (gr0 >= 0 && gr0 + 2 * nrows + F - 2 <= p.src_h)
-        dwt_fwd_task<Tin, WID, true>(p, tx, ty, z);
-    else
-        dwt_fwd_task<Tin, WID, false>(p, tx, ty, z);
+    const int gc_first = 2 * (tx * NOUT - (F / 2 - 1)) + sft;
+    constexpr int VB = 2 * NP * (int)sizeof(Tin) >= 16 ? 16 : 8;  // vector bytes
+    const long long base = (long long)reinterpret_cast<uintptr_t>(p.src) +
+                           (long long)z * p.src_h * p.src_w * (long long)sizeof(Tin);
+    const bool aligned = ((size_t)p.src_w * sizeof(Tin)) % VB == 0 &&
+                         (base + (long long)gc_first * (long long)sizeof(Tin)) % VB == 0;
+    dwt_fwd_task<Tin, WID, NP>(p, tx, ty, z, ring, aligned);
 }
 
 // zero the gaps coeffs_to_array leaves between a level's off-diagonal blocks
@@ -293,8 +406,8 @@ __global__ void __launch_bounds__(256) rgb_to_ipt_kernel(const Tin *__restrict__
 template <typename Tin, int WID>
 static int launch_level(spihtb_ctx *ctx, FwdK k, int nz)
 {
-    constexpr int F = Wav<WID>::F;
-    constexpr int NOUT = 32 - (F / 2 - 1);
+    constexpr int NP = FwdCfg<WID>::NP;
+    constexpr int NOUT = FwdCfg<WID>::NOUT;
     constexpr int RHMAX = 64;
     k.tiles_x = (k.bw + NOUT - 1) / NOUT;
     // balanced row chunks (no nearly empty tail chunk)
@@ -306,7 +419,7 @@ static int launch_level(spihtb_ctx *ctx, FwdK k, int nz)
         set_error("forward DWT grid too large");
         return SPIHTB_ESHAPE;
     }
-    dwt_fwd_level_kernel<Tin, WID><<<(unsigned)nb, FW_WARPS * 32, 0, ctx->stream>>>(k);
+    dwt_fwd_level_kernel<Tin, WID, NP><<<(unsigned)nb, FW_WARPS * 32, 0, ctx->stream>>>(k);
     ctx->launches++;
     return SPIHTB_OK;
 }
