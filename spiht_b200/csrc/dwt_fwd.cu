@@ -84,6 +84,30 @@ __device__ __forceinline__ void lds_frag(uint32_t saddr, Tin (&v)[NC])
     }
 }
 
+// A lane holds two adjacent int32 outputs (v0 at p[0], v1 at p[1]; ok0/ok1: inside the band).  When p is
+// 8-byte aligned (warp-uniform: lanes are 8 bytes apart) the pair goes out as one store; otherwise every
+// lane takes its left neighbour's v1 and stores (v1', v0) at p - 1, and the row's two end columns go out
+// alone.  `row_ok` is warp-uniform.
+__device__ __forceinline__ void store_pair(int32_t *p, int32_t v0, int32_t v1, bool row_ok, bool ok0, bool ok1,
+                                           bool ok_prev, bool ok_next)
+{
+    if ((reinterpret_cast<uintptr_t>(p) & 7) == 0) {
+        if (row_ok && ok0 && ok1)
+            *reinterpret_cast<int2 *>(p) = make_int2(v0, v1);
+        else if (row_ok && ok0)
+            p[0] = v0;
+    } else {
+        const int32_t up = __shfl_up_sync(0xffffffffu, v1, 1);
+        if (row_ok && ok0) {
+            if (ok_prev)
+                *reinterpret_cast<int2 *>(p - 1) = make_int2(up, v0);
+            else
+                p[0] = v0;
+        }
+        if (row_ok && ok1 && !ok_next) p[1] = v1;
+    }
+}
+
 template <int WID>
 struct FwdCfg {
     static constexpr int F = Wav<WID>::F;
@@ -111,7 +135,7 @@ struct FwdCfg {
 // the next level, details quantised).  A lane whose columns lie inside the plane
 // (and whose rows are vector-aligned) copies its fragment as one vector; the halo
 // lanes of the edge strips go through the boundary map one element at a time.
-template <typename Tin, int WID, int NP>
+template <typename Tin, int WID, int NP, bool UNIT_M, bool LAST>
 __device__ __forceinline__ void dwt_fwd_task(const FwdK &p, int tx, int ty, int z, uint32_t ring, bool aligned)
 {
     constexpr int F = Wav<WID>::F;
@@ -142,7 +166,8 @@ __device__ __forceinline__ void dwt_fwd_task(const FwdK &p, int tx, int ty, int 
     // rows gr, gr+1 (warp-uniform; any integer) -> ring slot `slot` (row 0 at +0, row 1 at +32 FRAG)
     const Tin *runp = plane + (ptrdiff_t)gr0 * src_w;  // row gr of the plane while gr is inside it
     int gr = gr0;
-    const uint32_t my = ring + lane * FRAG;
+    uint32_t my = ring + lane * FRAG;
+    asm volatile("" : "+r"(my));  // keep the shared address in a register (not rebuilt from special registers)
     auto fetch_pair = [&](uint32_t slot_off) {
         const Tin *pa = runp, *pb = runp + src_w;
         if (gr < 0 || gr + 1 >= src_h) {  // rare (warp-uniform): boundary rows go through the extension map
@@ -197,18 +222,20 @@ __device__ __forceinline__ void dwt_fwd_task(const FwdK &p, int tx, int ty, int 
     uint32_t slot_off = ((HF - 1) % DEPTH) * SLOT;  // ring slot of the next pair to take
 
     const int zc = z % p.C;
-    const double m = p.scale[zc], qs = p.q;
-    const bool unit_m = m == 1.0;
+    const double m = UNIT_M ? 1.0 : p.scale[zc], qs = p.q;
     bool col_ok[NP];
 #pragma unroll
     for (int t = 0; t < NP; ++t) col_ok[t] = lane >= HL && kf + t < p.bw;
+    // does the lane before / after this one store its last / first column?  (NP == 2 pair stores)
+    const bool ok_prev = lane >= 1 && lane - 1 >= HL && kf - 1 < p.bw;
+    const bool ok_next = lane < 31 && lane + 1 >= HL && kf + NP < p.bw;
     const int Wc = p.Wc;
     int32_t *cz = p.coeffs + (size_t)z * p.Hc * Wc;
     int32_t *p_aa = cz + (ptrdiff_t)r0 * Wc + kf;           // LL corner (last level only)
     int32_t *p_ad = p_aa + p.sw;                            // rows lo, cols hi: top right
     int32_t *p_da = cz + (ptrdiff_t)(p.sh + r0) * Wc + kf;  // rows hi, cols lo: bottom left
     int32_t *p_dd = p_da + p.sw;
-    const bool ll_scratch = !p.last;
+    constexpr bool ll_scratch = !LAST;
     double *p_ll = ll_scratch ? p.dst_ll + ((size_t)z * p.bh + r0) * p.bw + kf : nullptr;
     const int bw = p.bw;
 
@@ -272,10 +299,12 @@ __device__ __forceinline__ void dwt_fwd_task(const FwdK &p, int tx, int ty, int 
                 }
             }
             const bool row_ok = i < nrows;
+            int32_t q_ad[NP], q_da[NP], q_dd[NP], q_aa[NP];
+            double f_aa[NP];
 #pragma unroll
             for (int t = 0; t < NP; ++t) {
                 // axis -1: tap 2v multiplies O[k-v], tap 2v+1 multiplies E[k-v]
-                double aa = 0.0, ad = 0.0, da = 0.0, dd = 0.0;
+                double aa = 0.0, ad = 0.0, da = 0.0, dd = 0.0;  // this lane's output column kf + t
 #pragma unroll
                 for (int v = 0; v < HF; ++v) {
                     const int j = t - v + (HF - 1);
@@ -296,20 +325,45 @@ __device__ __forceinline__ void dwt_fwd_task(const FwdK &p, int tx, int ty, int 
                         dd = fma(wav_dec_hi<WID>(2 * v + 1), xhi[j][0], dd);
                     }
                 }
-                if (!unit_m) {  // warp-uniform
+                if (!UNIT_M) {  // (1.0 * x) * q == x * q exactly
                     ad *= m;
                     da *= m;
                     dd *= m;
                     if (!ll_scratch) aa *= m;
                 }
-                if (row_ok && col_ok[t]) {
-                    p_ad[t] = quantise1(ad, qs);
-                    p_da[t] = quantise1(da, qs);
-                    p_dd[t] = quantise1(dd, qs);
-                    if (ll_scratch)
-                        p_ll[t] = aa;
-                    else
-                        p_aa[t] = quantise1(aa, qs);
+                q_ad[t] = quantise1(ad, qs);
+                q_da[t] = quantise1(da, qs);
+                q_dd[t] = quantise1(dd, qs);
+                q_aa[t] = ll_scratch ? 0 : quantise1(aa, qs);
+                f_aa[t] = aa;
+            }
+            if constexpr (NP == 2) {
+                // both columns of a lane go out as one 8-byte store (whole 32-byte sectors per warp)
+                store_pair(p_ad, q_ad[0], q_ad[1], row_ok, col_ok[0], col_ok[1], ok_prev, ok_next);
+                store_pair(p_da, q_da[0], q_da[1], row_ok, col_ok[0], col_ok[1], ok_prev, ok_next);
+                store_pair(p_dd, q_dd[0], q_dd[1], row_ok, col_ok[0], col_ok[1], ok_prev, ok_next);
+                if (ll_scratch) {
+                    if (row_ok && col_ok[0] && col_ok[1] && (reinterpret_cast<uintptr_t>(p_ll) & 15) == 0) {
+                        *reinterpret_cast<double2 *>(p_ll) = make_double2(f_aa[0], f_aa[1]);
+                    } else {
+                        if (row_ok && col_ok[0]) p_ll[0] = f_aa[0];
+                        if (row_ok && col_ok[1]) p_ll[1] = f_aa[1];
+                    }
+                } else {
+                    store_pair(p_aa, q_aa[0], q_aa[1], row_ok, col_ok[0], col_ok[1], ok_prev, ok_next);
+                }
+            } else {
+#pragma unroll
+                for (int t = 0; t < NP; ++t) {
+                    if (row_ok && col_ok[t]) {
+                        p_ad[t] = q_ad[t];
+                        p_da[t] = q_da[t];
+                        p_dd[t] = q_dd[t];
+                        if (ll_scratch)
+                            p_ll[t] = f_aa[t];
+                        else
+                            p_aa[t] = q_aa[t];
+                    }
                 }
             }
             p_aa += Wc;
@@ -321,7 +375,7 @@ __device__ __forceinline__ void dwt_fwd_task(const FwdK &p, int tx, int ty, int 
     }
 }
 
-template <typename Tin, int WID, int NP>
+template <typename Tin, int WID, int NP, bool UNIT_M, bool LAST>
 __global__ void __launch_bounds__(FW_WARPS * 32) dwt_fwd_level_kernel(const FwdK p)
 {
     constexpr int F = Wav<WID>::F;
@@ -344,7 +398,7 @@ __global__ void __launch_bounds__(FW_WARPS * 32) dwt_fwd_level_kernel(const FwdK
                            (long long)z * p.src_h * p.src_w * (long long)sizeof(Tin);
     const bool aligned = ((size_t)p.src_w * sizeof(Tin)) % VB == 0 &&
                          (base + (long long)gc_first * (long long)sizeof(Tin)) % VB == 0;
-    dwt_fwd_task<Tin, WID, NP>(p, tx, ty, z, ring, aligned);
+    dwt_fwd_task<Tin, WID, NP, UNIT_M, LAST>(p, tx, ty, z, ring, aligned);
 }
 
 // zero the gaps coeffs_to_array leaves between a level's off-diagonal blocks
@@ -419,7 +473,17 @@ static int launch_level(spihtb_ctx *ctx, FwdK k, int nz)
         set_error("forward DWT grid too large");
         return SPIHTB_ESHAPE;
     }
-    dwt_fwd_level_kernel<Tin, WID, NP><<<(unsigned)nb, FW_WARPS * 32, 0, ctx->stream>>>(k);
+    bool unit = true;
+    for (int c = 0; c < k.C && c < 8; ++c) unit = unit && k.scale[c] == 1.0;
+    const dim3 grid((unsigned)nb), block(FW_WARPS * 32);
+    if (unit && k.last)
+        dwt_fwd_level_kernel<Tin, WID, NP, true, true><<<grid, block, 0, ctx->stream>>>(k);
+    else if (unit)
+        dwt_fwd_level_kernel<Tin, WID, NP, true, false><<<grid, block, 0, ctx->stream>>>(k);
+    else if (k.last)
+        dwt_fwd_level_kernel<Tin, WID, NP, false, true><<<grid, block, 0, ctx->stream>>>(k);
+    else
+        dwt_fwd_level_kernel<Tin, WID, NP, false, false><<<grid, block, 0, ctx->stream>>>(k);
     ctx->launches++;
     return SPIHTB_OK;
 }
