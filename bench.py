@@ -343,7 +343,8 @@ def run_b200(args):
         "dwt_inv_coarse": coef_bytes - det1,
         "dwt_inv_level1": px_bytes + det1,
     }
-    stage_ms = {k: (v[0] / v[1] if v[1] else 0.0) for k, v in stages.items()}
+    # a stage may be launched several times per step (image groups): per-step time = total / steps
+    stage_ms = {k: (v[0] / args.steps if v[1] else 0.0) for k, v in stages.items()}
     enc_stages = ("dwt_fwd_level1", "dwt_fwd_rest", "pyramid_base", "pyramid_rest", "spiht_encode")
     dom = max(enc_stages, key=lambda k: stage_ms[k])
     dom_gbs = alg[dom] * B / (stage_ms[dom] / 1e3) / 1e9 if stage_ms[dom] > 0 else 0.0

@@ -13,6 +13,7 @@
 //     (or, at the last level, quantised into the LL corner).
 // analysis (non-periodization): out[k] = sum_j f[j] x_ext[2k + 1 - j]
 // periodization:                out[k] = sum_j f[j] x_per[(2k + F/2 - j) mod Np]
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -535,32 +536,43 @@ int launch_forward(spihtb_ctx *ctx, const void *pixels, const XformArgs &x, int3
         src_is_f64 = true;
     }
 
-    for (int l = 0; l < L; ++l) {
+    // One launch per level over the whole batch.  (Running the first levels image group by image group,
+    // so that a group's float64 approximation planes stay in L2 for the next level, was measured slower
+    // on B200: the short launches leave the SMs idle at every kernel boundary.)
+    auto run_level = [&](int l, int z0, int nzg) -> int {
+        const bool in_f64 = l > 0 || x.pixel_dtype == SPIHTB_F64 || x.color == SPIHTB_COLOR_IPT;
+        const size_t esz = in_f64 ? sizeof(double) : sizeof(float);
         FwdK k;
-        k.src = src;
+        const void *lsrc = l == 0 ? src : (((l - 1) & 1) ? ctx->tmpb.p : ctx->tmpa.p);
         k.src_h = g.in_h[l];
         k.src_w = g.in_w[l];
+        k.src = static_cast<const char *>(lsrc) + (size_t)z0 * k.src_h * k.src_w * esz;
         k.bh = g.band_h[l];
         k.bw = g.band_w[l];
         k.last = (l == L - 1);
-        k.dst_ll = k.last ? nullptr : static_cast<double *>((l & 1) ? ctx->tmpb.p : ctx->tmpa.p);
-        k.coeffs = coeffs;
+        k.dst_ll = k.last ? nullptr
+                          : static_cast<double *>((l & 1) ? ctx->tmpb.p : ctx->tmpa.p) + (size_t)z0 * k.bh * k.bw;
         k.Hc = g.enc_h;
         k.Wc = g.enc_w;
+        k.coeffs = coeffs + (size_t)z0 * k.Hc * k.Wc;
         k.sh = g.off_h[l];
         k.sw = g.off_w[l];
         k.mode = g.mode;
         k.C = x.C;
         for (int c = 0; c < 8; ++c) k.scale[c] = x.scale[c];
         k.q = x.q;
-        if (l == 0) ctx->stage_begin(0);
-        if (l == 1) ctx->stage_begin(1);
-        rc = src_is_f64 ? launch_level_w<double>(ctx, g.wavelet, k, nz) : launch_level_w<float>(ctx, g.wavelet, k, nz);
+        const int st = l == 0 ? 0 : 1;
+        ctx->stage_begin(st);
+        const int r = in_f64 ? launch_level_w<double>(ctx, g.wavelet, k, nzg)
+                             : launch_level_w<float>(ctx, g.wavelet, k, nzg);
+        ctx->stage_end(st);
+        return r;
+    };
+    for (int l = 0; l < L; ++l) {
+        rc = run_level(l, 0, nz);
         if (rc) return rc;
-        if (l == 0) ctx->stage_end(0);
-        src = k.dst_ll;
-        src_is_f64 = true;
     }
+    (void)src_is_f64;
     {
         GapK gk;
         gk.coeffs = coeffs;
@@ -576,12 +588,12 @@ int launch_forward(spihtb_ctx *ctx, const void *pixels, const XformArgs &x, int3
             gk.sw[l] = g.off_w[l];
             any |= (gk.sh[l] > gk.bh[l]) || (gk.sw[l] > gk.bw[l]);
         }
-        if (L == 1) ctx->stage_begin(1);
         if (any) {
+            ctx->stage_begin(1);
             gap_fill_kernel<<<dim3(8, std::min(nz, 65535)), 256, 0, ctx->stream>>>(gk);
             ctx->launches++;
+            ctx->stage_end(1);
         }
-        ctx->stage_end(1);
     }
     SPIHTB_CUDA_CHECK(cudaGetLastError());
     return SPIHTB_OK;
