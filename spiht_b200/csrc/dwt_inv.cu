@@ -2,15 +2,26 @@
 // (optional IPT->RGB).  Replaces spiht_wrapper.py:259-281 ((x / m_c) / q,
 // pywt.array_to_coeffs, pywt.waverec2, colour.convert).
 //
-// One kernel per level, coarsest first.  A CTA produces a 32x64 tile of the
-// level's output for one (image, channel) plane: it stages the needed window
-// of the four bands in shared memory (details are dequantised on load from
-// their place in the coefficient array), synthesises along axis -1 then along
-// axis -2 (PyWavelets' idwtn order) in float64.
+// One kernel per level, coarsest first.  The mirror of the forward kernel: one
+// warp = one task, a strip of NOUT = 32 - (F/2 - 1) coefficient columns (2 NOUT
+// output columns) by RH output row pairs of one (image, channel) plane.  Lane j
+// owns coefficient column kc = q0 + S/2 - (F/2-1) + j of the four bands and
+// streams down the coefficient rows:
+//   axis -1: the output column pair (2q, 2q+1), q = q0 + j, needs the columns
+//            of lanes j .. j+F/2-1 (warp shuffle down):
+//              X[2q]   = sum_u g[2u]   c[q + S/2 - u],
+//              X[2q+1] = sum_u g[2u+1] c[q + S/2 - u]     (g = rec_lo on the
+//            approximation / 'da' band, rec_hi on the 'ad' / 'dd' band);
+//   axis -2: a register window of F/2 rows of (X_lo, X_hi) gives the output row
+//            pair (2p, 2p+1) the same way.
+// PyWavelets' idwtn order (axis -1 first), float64.  Details are dequantised
+// on load from their place in the coefficient array.  No shared memory, no
+// barrier; rows are prefetched PD steps ahead in registers; every lane stores
+// two adjacent outputs per row (whole sectors per warp).
 // synthesis (non-periodization): rec[n] = sum_t g[t] c[(n + F-2 - t)/2]   for even n+F-2-t, 0 <= k < m
 // periodization:                 rec[n] = sum_t g[t] c[((n + F/2-1 - t)/2) mod m]
 // waverec2 drops the approximation's trailing row/column when it is one
-// longer than the detail band (odd sizes); the window simply never reads it.
+// longer than the detail band (odd sizes); the strips simply never read it.
 #include <algorithm>
 
 #include "common.cuh"
@@ -19,7 +30,7 @@
 
 namespace spihtb {
 
-constexpr int IV_TH = 32, IV_TW = 64, IV_NT = 256;
+constexpr int IV_WARPS = 4;
 
 struct InvK {
     const double *src_a;  // approximation planes [nz][a_h][a_w] (null at the coarsest level: LL corner of coeffs)
@@ -29,140 +40,182 @@ struct InvK {
     int bh, bw;   // band size
     int oh, ow;   // output size of this level
     void *dst;    // [nz][oh][ow] double scratch, or the final pixels
-    int dst_f32;  // final level only: 1 = float32 output
     int mode, C;
-    int tiles_x, tiles_y;
-    double scale[8];
-    double q;
+    int tiles_x, tiles_y, RH;  // strips across, chunks of RH output row pairs down
+    long long ntasks;
+    double rscale[8];  // 1 / m_c
+    double rq;         // 1 / q
 };
 
-__device__ __forceinline__ int floor_div2(int a) { return a >> 1; }  // arithmetic shift = floor for negatives
+template <typename Tout>
+struct Out2;
+template <>
+struct Out2<float> {
+    using type = float2;
+    static __device__ __forceinline__ float2 make(double a, double b) { return make_float2((float)a, (float)b); }
+};
+template <>
+struct Out2<double> {
+    using type = double2;
+    static __device__ __forceinline__ double2 make(double a, double b) { return make_double2(a, b); }
+};
 
-template <int WID>
-__global__ void __launch_bounds__(IV_NT) dwt_inv_level_kernel(const InvK p)
+// spiht_wrapper.py:270-274: (x / m_c) / q.  Evaluated as (x * (1/m_c)) * (1/q): at most 2 ulp from the
+// reference's two divisions, far inside the float tolerance of the inverse path.
+template <typename Tout, int WID, bool LLQ>
+__global__ void __launch_bounds__(IV_WARPS * 32) dwt_inv_level_kernel(const InvK p)
 {
     constexpr int F = Wav<WID>::F;
-    constexpr int KH = IV_TH / 2 + F / 2 + 1, KW = IV_TW / 2 + F / 2 + 1;
-    extern __shared__ __align__(16) unsigned char smem[];
-    double *s_b = reinterpret_cast<double *>(smem);  // [4][KH][KW]: aa, ad, da, dd
-    double *s_h = s_b + 4 * KH * KW;                 // [2][KH][IV_TW]
-
-    const int tid = threadIdx.x;
-    uint32_t bid = blockIdx.x;
-    const int tx = bid % p.tiles_x;
-    bid /= p.tiles_x;
-    const int ty = bid % p.tiles_y;
-    const int z = bid / p.tiles_y;
-    const int n0r = ty * IV_TH, n0c = tx * IV_TW;
+    constexpr int HF = F / 2;
+    constexpr int NOUT = 32 - (HF - 1);
+    constexpr int PD = (HF % 3 == 0) ? 3 : HF;  // prefetch distance in rows; divides HF
+    constexpr unsigned FULL = 0xffffffffu;
+    long long task = (long long)blockIdx.x * IV_WARPS + (threadIdx.x >> 5);
+    if (task >= p.ntasks) return;
+    const int tx = (int)(task % p.tiles_x);
+    task /= p.tiles_x;
+    const int ty = (int)(task % p.tiles_y);
+    const int z = (int)(task / p.tiles_y);
+    const int lane = threadIdx.x & 31;
     const bool per = p.mode == SPIHTB_MODE_PERIODIZATION;
-    const int S = per ? (F / 2 - 1) : (F - 2);
-    const int klo_r = floor_div2(n0r + S - (F - 1)), klo_c = floor_div2(n0c + S - (F - 1));
+    const int S2 = per ? (HF - 1) / 2 : HF - 1;
+    const int bh = p.bh, bw = p.bw, Wc = p.Wc;
+    const int q0 = tx * NOUT, p0 = ty * p.RH;
+    const int npair = min(p.RH, p.oh / 2 - p0);  // output row pairs of this chunk
 
+    // this lane's coefficient column
+    int kc = q0 + S2 - (HF - 1) + lane;
+    if (per) {
+        kc %= bw;
+        if (kc < 0) kc += bw;
+    } else {
+        kc = min(kc, bw - 1);  // lanes past the band only feed dropped outputs
+    }
     const int zc = z % p.C;
-    const double m = p.scale[zc], q = p.q;
-    const int32_t *cz = p.coeffs + (size_t)z * p.Hc * p.Wc;
-    const double *az = p.src_a ? p.src_a + (size_t)z * p.a_h * p.a_w : nullptr;
+    const double rm = p.rscale[zc], rq = p.rq;
+    const int32_t *cz = p.coeffs + (size_t)z * p.Hc * Wc;
+    const int32_t *c_ad = cz + p.sw + kc;
+    const int32_t *c_da = cz + (size_t)p.sh * Wc + kc;
+    const int32_t *c_dd = c_da + p.sw;
+    const int32_t *c_aa = cz + kc;
+    const double *a_aa = LLQ ? nullptr : p.src_a + (size_t)z * p.a_h * p.a_w + kc;
+    const int a_w = p.a_w;
 
-    for (int idx = tid; idx < KH * KW; idx += IV_NT) {
-        const int lr = idx / KW, lc = idx - lr * KW;
-        int kr = klo_r + lr, kc = klo_c + lc;
-        bool ok = true;
+    struct Raw {
+        int32_t ad, da, dd, aaq;
+        double aa;
+    };
+    // coefficient row of stream index j (any j >= 0; rows past the chunk's need are clamped / wrapped)
+    const int rbase = p0 + S2 - (HF - 1);
+    auto load_row = [&](int j, Raw &r) {
+        int row = rbase + j;
         if (per) {
-            kr %= p.bh;
-            if (kr < 0) kr += p.bh;
-            kc %= p.bw;
-            if (kc < 0) kc += p.bw;
+            row %= bh;
+            if (row < 0) row += bh;
         } else {
-            ok = kr >= 0 && kr < p.bh && kc >= 0 && kc < p.bw;
+            row = min(row, bh - 1);
         }
-        double aa = 0.0, ad = 0.0, da = 0.0, dd = 0.0;
-        if (ok) {
-            // spiht_wrapper.py:270-274: (x / m_c) / q
-            aa = az ? az[(size_t)kr * p.a_w + kc] : ((double)cz[(size_t)kr * p.Wc + kc] / m) / q;
-            ad = ((double)cz[(size_t)kr * p.Wc + p.sw + kc] / m) / q;
-            da = ((double)cz[(size_t)(p.sh + kr) * p.Wc + kc] / m) / q;
-            dd = ((double)cz[(size_t)(p.sh + kr) * p.Wc + p.sw + kc] / m) / q;
-        }
-        s_b[idx] = aa;
-        s_b[KH * KW + idx] = ad;
-        s_b[2 * KH * KW + idx] = da;
-        s_b[3 * KH * KW + idx] = dd;
-    }
-    __syncthreads();
+        const size_t o = (size_t)row * Wc;
+        r.ad = __ldg(c_ad + o);
+        r.da = __ldg(c_da + o);
+        r.dd = __ldg(c_dd + o);
+        if (LLQ)
+            r.aaq = __ldg(c_aa + o);
+        else
+            r.aa = __ldg(a_aa + (size_t)row * a_w);
+    };
 
-    // axis -1: every staged coefficient row -> IV_TW output columns
-    for (int idx = tid; idx < KH * IV_TW; idx += IV_NT) {
-        const int lr = idx / IV_TW, c = idx - lr * IV_TW;
-        const int n = n0c + c;
-        const int par = (n + S) & 1;
-        const int kbase = ((n + S - par) >> 1) - klo_c;  // local index of tap t = par
-        double lo = 0.0, hi = 0.0;
-        const double *ra = s_b + lr * KW;
-        if (par == 0) {
+    // X[slot][0/1] = (even, odd) output column of the row-synthesised lo / hi signal of stream row j, slot = j % HF
+    double xlo[HF][2], xhi[HF][2];
+    auto h_synth = [&](const Raw &r, int slot) {
+        const double aa = LLQ ? ((double)r.aaq * rm) * rq : r.aa;
+        const double ad = ((double)r.ad * rm) * rq;
+        const double da = ((double)r.da * rm) * rq;
+        const double dd = ((double)r.dd * rm) * rq;
+        double le = 0.0, lo = 0.0, he = 0.0, ho = 0.0;
 #pragma unroll
-            for (int u = 0; u < F / 2; ++u) {
-                const int t = 2 * u;
-                const int kk = kbase - u;
-                if (Wav<WID>::rec_lo(t) != 0.0) {
-                    lo = fma(Wav<WID>::rec_lo(t), ra[kk], lo);
-                    hi = fma(Wav<WID>::rec_lo(t), ra[2 * KH * KW + kk], hi);
-                }
-                if (wav_rec_hi<WID>(t) != 0.0) {
-                    lo = fma(wav_rec_hi<WID>(t), ra[KH * KW + kk], lo);
-                    hi = fma(wav_rec_hi<WID>(t), ra[3 * KH * KW + kk], hi);
-                }
+        for (int u = 0; u < HF; ++u) {
+            const int d = HF - 1 - u;  // lane j + d holds column q + S/2 - u
+            const double vaa = d ? __shfl_down_sync(FULL, aa, d) : aa;
+            const double vad = d ? __shfl_down_sync(FULL, ad, d) : ad;
+            const double vda = d ? __shfl_down_sync(FULL, da, d) : da;
+            const double vdd = d ? __shfl_down_sync(FULL, dd, d) : dd;
+            if (Wav<WID>::rec_lo(2 * u) != 0.0) {
+                le = fma(Wav<WID>::rec_lo(2 * u), vaa, le);
+                he = fma(Wav<WID>::rec_lo(2 * u), vda, he);
             }
-        } else {
-#pragma unroll
-            for (int u = 0; u < F / 2; ++u) {
-                const int t = 2 * u + 1;
-                const int kk = kbase - u;
-                if (Wav<WID>::rec_lo(t) != 0.0) {
-                    lo = fma(Wav<WID>::rec_lo(t), ra[kk], lo);
-                    hi = fma(Wav<WID>::rec_lo(t), ra[2 * KH * KW + kk], hi);
-                }
-                if (wav_rec_hi<WID>(t) != 0.0) {
-                    lo = fma(wav_rec_hi<WID>(t), ra[KH * KW + kk], lo);
-                    hi = fma(wav_rec_hi<WID>(t), ra[3 * KH * KW + kk], hi);
-                }
+            if (wav_rec_hi<WID>(2 * u) != 0.0) {
+                le = fma(wav_rec_hi<WID>(2 * u), vad, le);
+                he = fma(wav_rec_hi<WID>(2 * u), vdd, he);
+            }
+            if (Wav<WID>::rec_lo(2 * u + 1) != 0.0) {
+                lo = fma(Wav<WID>::rec_lo(2 * u + 1), vaa, lo);
+                ho = fma(Wav<WID>::rec_lo(2 * u + 1), vda, ho);
+            }
+            if (wav_rec_hi<WID>(2 * u + 1) != 0.0) {
+                lo = fma(wav_rec_hi<WID>(2 * u + 1), vad, lo);
+                ho = fma(wav_rec_hi<WID>(2 * u + 1), vdd, ho);
             }
         }
-        s_h[idx] = lo;
-        s_h[KH * IV_TW + idx] = hi;
-    }
-    __syncthreads();
+        xlo[slot][0] = le;
+        xlo[slot][1] = lo;
+        xhi[slot][0] = he;
+        xhi[slot][1] = ho;
+    };
 
-    // axis -2
-    for (int idx = tid; idx < IV_TH * IV_TW; idx += IV_NT) {
-        const int r = idx / IV_TW, c = idx - r * IV_TW;
-        const int n = n0r + r;
-        const int par = (n + S) & 1;
-        const int kbase = ((n + S - par) >> 1) - klo_r;
-        double v = 0.0;
-        if (par == 0) {
+    Raw q[PD];
 #pragma unroll
-            for (int u = 0; u < F / 2; ++u) {
-                const int t = 2 * u;
-                const int kk = (kbase - u) * IV_TW + c;
-                if (Wav<WID>::rec_lo(t) != 0.0) v = fma(Wav<WID>::rec_lo(t), s_h[kk], v);
-                if (wav_rec_hi<WID>(t) != 0.0) v = fma(wav_rec_hi<WID>(t), s_h[KH * IV_TW + kk], v);
-            }
-        } else {
+    for (int s = 0; s < PD; ++s) load_row(s, q[s]);
+    // rows 0 .. HF-2 of the stream fill the window
+    static_assert(PD >= 1, "prefetch");
+    int jn = PD;  // next stream row to load
 #pragma unroll
-            for (int u = 0; u < F / 2; ++u) {
-                const int t = 2 * u + 1;
-                const int kk = (kbase - u) * IV_TW + c;
-                if (Wav<WID>::rec_lo(t) != 0.0) v = fma(Wav<WID>::rec_lo(t), s_h[kk], v);
-                if (wav_rec_hi<WID>(t) != 0.0) v = fma(wav_rec_hi<WID>(t), s_h[KH * IV_TW + kk], v);
+    for (int j = 0; j < HF - 1; ++j) {
+        h_synth(q[j % PD], j % HF);
+        load_row(jn++, q[j % PD]);
+    }
+
+    using O2 = Out2<Tout>;
+    const int q_out = q0 + lane;
+    const bool col_ok = lane < NOUT && q_out < p.ow / 2;
+    Tout *dst = static_cast<Tout *>(p.dst) + (size_t)z * p.oh * p.ow + (size_t)(2 * p0) * p.ow + 2 * q_out;
+    const int ow = p.ow;
+
+    const int niter = (npair + HF - 1) / HF;
+    for (int it = 0; it < niter; ++it) {
+#pragma unroll
+        for (int u0 = 0; u0 < HF; ++u0) {
+            const int i = it * HF + u0;  // output row pair of the chunk
+            const int j = u0 + HF - 1;   // stream row completing it (up to a multiple of HF)
+            h_synth(q[j % PD], j % HF);
+            load_row(jn++, q[j % PD]);
+            // axis -2: stream row (j - u) holds coefficient row p + S/2 - u
+            double e0 = 0.0, e1 = 0.0, o0 = 0.0, o1 = 0.0;  // rows 2p (e) and 2p+1 (o), columns 2q, 2q+1
+#pragma unroll
+            for (int u = 0; u < HF; ++u) {
+                const int slot = ((j - u) % HF + HF) % HF;
+                if (Wav<WID>::rec_lo(2 * u) != 0.0) {
+                    e0 = fma(Wav<WID>::rec_lo(2 * u), xlo[slot][0], e0);
+                    e1 = fma(Wav<WID>::rec_lo(2 * u), xlo[slot][1], e1);
+                }
+                if (wav_rec_hi<WID>(2 * u) != 0.0) {
+                    e0 = fma(wav_rec_hi<WID>(2 * u), xhi[slot][0], e0);
+                    e1 = fma(wav_rec_hi<WID>(2 * u), xhi[slot][1], e1);
+                }
+                if (Wav<WID>::rec_lo(2 * u + 1) != 0.0) {
+                    o0 = fma(Wav<WID>::rec_lo(2 * u + 1), xlo[slot][0], o0);
+                    o1 = fma(Wav<WID>::rec_lo(2 * u + 1), xlo[slot][1], o1);
+                }
+                if (wav_rec_hi<WID>(2 * u + 1) != 0.0) {
+                    o0 = fma(wav_rec_hi<WID>(2 * u + 1), xhi[slot][0], o0);
+                    o1 = fma(wav_rec_hi<WID>(2 * u + 1), xhi[slot][1], o1);
+                }
             }
-        }
-        const int gc = n0c + c;
-        if (n < p.oh && gc < p.ow) {
-            const size_t o = ((size_t)z * p.oh + n) * p.ow + gc;
-            if (p.dst_f32)
-                static_cast<float *>(p.dst)[o] = (float)v;
-            else
-                static_cast<double *>(p.dst)[o] = v;
+            if (col_ok && i < npair) {
+                *reinterpret_cast<typename O2::type *>(dst) = O2::make(e0, e1);
+                *reinterpret_cast<typename O2::type *>(dst + ow) = O2::make(o0, o1);
+            }
+            dst += 2 * (size_t)ow;
         }
     }
 }
@@ -214,23 +267,34 @@ static void inv3(const double a[9], double r[9])
 }
 
 template <int WID>
-static int launch_inv_level(spihtb_ctx *ctx, const InvK &k, int nz)
+static int launch_inv_level(spihtb_ctx *ctx, InvK k, int nz, bool out_f32)
 {
     constexpr int F = Wav<WID>::F;
-    constexpr int KH = IV_TH / 2 + F / 2 + 1, KW = IV_TW / 2 + F / 2 + 1;
-    const size_t smem = (4 * KH * KW + 2 * KH * IV_TW) * sizeof(double);
-    auto kern = dwt_inv_level_kernel<WID>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        SPIHTB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
-    const long long nb = (long long)k.tiles_x * k.tiles_y * nz;
+    constexpr int NOUT = 32 - (F / 2 - 1);
+    constexpr int RHMAX = 32;  // output row pairs per chunk
+    const int opw = k.ow / 2, oph = k.oh / 2;
+    k.tiles_x = (opw + NOUT - 1) / NOUT;
+    k.tiles_y = (oph + RHMAX - 1) / RHMAX;
+    k.RH = (oph + k.tiles_y - 1) / k.tiles_y;
+    k.ntasks = (long long)k.tiles_x * k.tiles_y * nz;
+    const long long nb = (k.ntasks + IV_WARPS - 1) / IV_WARPS;
     if (nb > 0x7fffffffLL) {
         set_error("inverse DWT grid too large");
         return SPIHTB_ESHAPE;
     }
-    kern<<<(unsigned)nb, IV_NT, smem, ctx->stream>>>(k);
+    const dim3 grid((unsigned)nb), block(IV_WARPS * 32);
+    const bool llq = k.src_a == nullptr;
+    if (out_f32) {
+        if (llq)
+            dwt_inv_level_kernel<float, WID, true><<<grid, block, 0, ctx->stream>>>(k);
+        else
+            dwt_inv_level_kernel<float, WID, false><<<grid, block, 0, ctx->stream>>>(k);
+    } else {
+        if (llq)
+            dwt_inv_level_kernel<double, WID, true><<<grid, block, 0, ctx->stream>>>(k);
+        else
+            dwt_inv_level_kernel<double, WID, false><<<grid, block, 0, ctx->stream>>>(k);
+    }
     ctx->launches++;
     return SPIHTB_OK;
 }
@@ -290,21 +354,19 @@ int launch_inverse(spihtb_ctx *ctx, const int32_t *coeffs, const XformArgs &x, v
         }
         k.mode = g.mode;
         k.C = x.C;
-        k.tiles_x = (k.ow + IV_TW - 1) / IV_TW;
-        k.tiles_y = (k.oh + IV_TH - 1) / IV_TH;
-        for (int c = 0; c < 8; ++c) k.scale[c] = x.scale[c];
-        k.q = x.q;
+        for (int c = 0; c < 8; ++c) k.rscale[c] = 1.0 / x.scale[c];
+        k.rq = 1.0 / x.q;
+        bool out_f32 = false;
         if (l == 0) {
             k.dst = color ? ctx->io2.p : pixels_out;
-            k.dst_f32 = (!color && x.pixel_dtype == SPIHTB_F32) ? 1 : 0;
+            out_f32 = !color && x.pixel_dtype == SPIHTB_F32;
         } else {
             k.dst = ((L - 1 - l) & 1) ? ctx->tmpb.p : ctx->tmpa.p;
-            k.dst_f32 = 0;
         }
         switch (g.wavelet) {
-            case SPIHTB_WAVELET_BIOR22: rc = launch_inv_level<SPIHTB_WAVELET_BIOR22>(ctx, k, nz); break;
-            case SPIHTB_WAVELET_BIOR44: rc = launch_inv_level<SPIHTB_WAVELET_BIOR44>(ctx, k, nz); break;
-            case SPIHTB_WAVELET_BIOR68: rc = launch_inv_level<SPIHTB_WAVELET_BIOR68>(ctx, k, nz); break;
+            case SPIHTB_WAVELET_BIOR22: rc = launch_inv_level<SPIHTB_WAVELET_BIOR22>(ctx, k, nz, out_f32); break;
+            case SPIHTB_WAVELET_BIOR44: rc = launch_inv_level<SPIHTB_WAVELET_BIOR44>(ctx, k, nz, out_f32); break;
+            case SPIHTB_WAVELET_BIOR68: rc = launch_inv_level<SPIHTB_WAVELET_BIOR68>(ctx, k, nz, out_f32); break;
             default: set_error("unknown wavelet id %d", g.wavelet); rc = SPIHTB_EINVAL;
         }
         if (rc) return rc;
