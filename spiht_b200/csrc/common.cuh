@@ -167,6 +167,40 @@ __device__ __forceinline__ uint64_t block_exscan(uint64_t v, uint64_t *warp_tot,
     total = tot;
     return base + inc - v;
 }
+// Same scan with two barriers and far fewer instructions per thread: warp 0 scans the warp totals.
+// `buf` is shared scratch of 2 x (NT/32 + 1) entries, `parity` a per-thread (CTA-uniform) toggle that
+// alternates the two halves so that back-to-back calls need no extra barrier.
+template <int NT, typename T>
+__device__ __forceinline__ T block_exscan2(T v, T (*buf)[NT / 32 + 1], int &parity, T &total)
+{
+    constexpr int NW = NT / 32;
+    static_assert(NW <= 32, "one warp scans the warp totals");
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    T *b = buf[parity];
+    parity ^= 1;
+    T inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        T t = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += t;
+    }
+    if (lane == 31) b[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        const T t = lane < NW ? b[lane] : (T)0;
+        T ti = t;
+#pragma unroll
+        for (int d = 1; d < NW; d <<= 1) {
+            T u = __shfl_up_sync(0xffffffffu, ti, d);
+            if (lane >= d) ti += u;
+        }
+        if (lane < NW) b[lane] = ti - t;
+        if (lane == NW - 1) b[NW] = ti;
+    }
+    __syncthreads();
+    total = b[NW];
+    return b[wid] + inc - v;
+}
 #endif  // __CUDACC__
 
 }  // namespace spihtb

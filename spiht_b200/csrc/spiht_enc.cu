@@ -23,9 +23,13 @@
 namespace spihtb {
 
 constexpr int ENC_NT = 512;
+constexpr int ENC_ITEMS = 4;                          // consecutive list entries per thread and scan
+constexpr int ENC_CHUNK = ENC_NT * ENC_ITEMS;
 constexpr int ENC_REF_ITEMS = 8;                      // refinement: entries per thread per flush
-constexpr int ENC_STAGE_WORDS = ENC_NT * 9 / 32 + 4;  // a chunk emits at most 9 bits per thread
-constexpr int ENC_SLACK = 16 * ENC_NT;                // list slack for the chunk that crosses the budget
+constexpr int ENC_RING = 1024;                        // staging ring in words; a chunk emits at most 9 bits per entry
+constexpr int ENC_SLACK = 4 * ENC_CHUNK + 64;         // list slack for the chunk that crosses the budget
+static_assert(ENC_CHUNK * 9 / 32 + 8 < ENC_RING, "staging ring too small");
+static_assert((ENC_RING & (ENC_RING - 1)) == 0, "ring size must be a power of two");
 
 struct EncK {
     const int32_t *coeffs;
@@ -48,45 +52,51 @@ struct EncK {
     unsigned int *counter;
 };
 
-__device__ __forceinline__ void bw_emit(uint32_t *stage, uint64_t wbase, uint64_t limit, uint64_t off, uint32_t val,
-                                        int nb)
+// OR `nb` (<= 40) bits of `val` into the staging ring at stream position `off`; bits at or past `limit` are dropped
+__device__ __forceinline__ void bw_emit(uint32_t *ring, uint64_t limit, uint64_t off, uint64_t val, int nb)
 {
     if (nb == 0 || off >= limit) return;
     if (off + (uint64_t)nb > limit) {
         nb = (int)(limit - off);
-        val &= (1u << nb) - 1u;  // here 1 <= nb < 32
+        val &= (1ull << nb) - 1ull;  // here 1 <= nb < 40
     }
-    const uint32_t rel = (uint32_t)((off >> 5) - wbase);
+    const uint32_t w = (uint32_t)(off >> 5);
     const int sh = (int)(off & 31);
-    atomicOr(&stage[rel], val << sh);
-    if (sh + nb > 32) atomicOr(&stage[rel + 1], val >> (32 - sh));
-}
-
-// Write out the complete words of the staging window; keep the partial one.
-// Callers must place a __syncthreads() (or a block_exscan) before the next emit.
-__device__ __forceinline__ void bw_flush(uint32_t *stage, uint32_t *outrow, uint64_t &wbase, uint64_t end)
-{
-    __syncthreads();
-    const uint32_t nfull = (uint32_t)((end >> 5) - wbase);
-    for (uint32_t i = threadIdx.x; i < nfull; i += ENC_NT) outrow[wbase + i] = stage[i];
-    const uint32_t carry = stage[nfull];
-    __syncthreads();
-    if (nfull) {
-        for (uint32_t i = threadIdx.x; i <= nfull; i += ENC_NT) stage[i] = i ? 0u : carry;
+    const uint32_t first = (uint32_t)(val << sh);
+    if (first) atomicOr(&ring[w & (ENC_RING - 1)], first);
+    const uint64_t rest = sh ? (val >> (32 - sh)) : (val >> 32);
+    if (rest) {
+        atomicOr(&ring[(w + 1) & (ENC_RING - 1)], (uint32_t)rest);
+        if (rest >> 32) atomicOr(&ring[(w + 2) & (ENC_RING - 1)], (uint32_t)(rest >> 32));
     }
-    wbase += nfull;
 }
 
-__global__ void __launch_bounds__(ENC_NT) spiht_encode_kernel(const EncK p)
+// Write out (and clear) the complete words below stream position `end`.  The partial word stays.  The
+// next emits only touch words at or above it, and a cleared slot is reused no earlier than a whole ring
+// later, which is at least one barrier away.
+__device__ __forceinline__ void bw_flush(uint32_t *ring, uint32_t *outrow, uint64_t &wflushed, uint64_t end)
 {
-    __shared__ uint32_t s_stage[ENC_STAGE_WORDS];
-    __shared__ uint64_t s_wtot[ENC_NT / 32];
+    __syncthreads();
+    const uint64_t wend = end >> 5;
+    for (uint64_t w = wflushed + threadIdx.x; w < wend; w += ENC_NT) {
+        outrow[w] = ring[w & (ENC_RING - 1)];
+        ring[w & (ENC_RING - 1)] = 0u;
+    }
+    wflushed = wend;
+}
+
+__global__ void __launch_bounds__(ENC_NT, 2) spiht_encode_kernel(const EncK p)
+{
+    __shared__ uint32_t s_ring[ENC_RING];
+    __shared__ uint64_t s_scan[2][ENC_NT / 32 + 1];
+    __shared__ int4 s_x[ENC_CHUNK];  // the four offspring of the chunk's fired A sets
     __shared__ int s_img;
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const KeyFmt kf = p.kf;
     const uint32_t H = p.H, W = p.W, NH = p.NH, NW = p.NW, ll_h = p.ll_h, ll_w = p.ll_w, C = p.C;
+    int parity = 0;
 
     int32_t *lip = p.lip + (size_t)blockIdx.x * p.pix_cap;
     uint32_t *lsp = p.lsp + (size_t)blockIdx.x * p.pix_cap;
@@ -114,8 +124,8 @@ __global__ void __launch_bounds__(ENC_NT) spiht_encode_kernel(const EncK p)
         const uint64_t cap_bits = p.out_stride_words * 32ull;
         const uint64_t limit = want < cap_bits ? want : cap_bits;
 
-        for (int i = tid; i < ENC_STAGE_WORDS; i += ENC_NT) s_stage[i] = 0;
-        uint64_t wbase = 0, bitpos = 0;
+        for (int i = tid; i < ENC_RING; i += ENC_NT) s_ring[i] = 0;
+        uint64_t wflushed = 0, bitpos = 0;
 
         // ---- list initialisation (encoder_decoder.rs:170-190): i, j, channel innermost
         const uint32_t T0 = ll_h * ll_w * C;
@@ -134,7 +144,7 @@ __global__ void __launch_bounds__(ENC_NT) spiht_encode_kernel(const EncK p)
                 root = ((i | j) & 1u) != 0;
             }
             uint64_t tot;
-            const uint64_t ex = block_exscan<ENC_NT>(root ? 1ull : 0ull, s_wtot, tot);
+            const uint64_t ex = block_exscan2<ENC_NT, uint64_t>(root ? 1ull : 0ull, s_scan, parity, tot);
             if (root)
                 R[r_len + (uint32_t)ex] =
                     make_uint2(0x80000000u | key_pack(kf, k, i, j), dpll[((size_t)k * ll_h + i) * ll_w + j]);
@@ -147,25 +157,56 @@ __global__ void __launch_bounds__(ENC_NT) spiht_encode_kernel(const EncK p)
             const uint32_t thr = 1u << n;
             const uint32_t lsp_len0 = lsp_len;
 
-            // ---- LIP pass (encoder_decoder.rs:207-222): in-place stable compaction
+            // ---- LIP pass (encoder_decoder.rs:207-222): in-place stable compaction.
+            // A thread takes ENC_ITEMS consecutive entries: record = "0" | "1 sign".
             uint32_t keep = 0;
-            for (uint32_t base = 0; base < lip_len && !done; base += ENC_NT) {
-                const uint32_t e = base + tid;
-                const bool valid = e < lip_len;
-                const int32_t v = valid ? lip[e] : 0;
-                const bool sig = valid && absu(v) >= thr;
-                const int nb = valid ? (sig ? 2 : 1) : 0;
-                const uint32_t val = sig ? (1u | ((v >= 0) ? 2u : 0u)) : 0u;
-                const uint64_t pack = (uint64_t)nb | ((uint64_t)(valid && !sig) << 14) | ((uint64_t)sig << 25);
+            for (uint32_t base = 0; base < lip_len && !done; base += ENC_CHUNK) {
+                const uint32_t e0 = base + tid * ENC_ITEMS;
+                const uint32_t nval = e0 < lip_len ? min((uint32_t)ENC_ITEMS, lip_len - e0) : 0u;
+                int32_t v[ENC_ITEMS];
+                if (nval == ENC_ITEMS) {
+                    const int4 q = *reinterpret_cast<const int4 *>(lip + e0);
+                    v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+                } else {
+#pragma unroll
+                    for (int t = 0; t < ENC_ITEMS; ++t) v[t] = (uint32_t)t < nval ? lip[e0 + t] : 0;
+                }
+                uint32_t sigm = 0, nb = 0;
+                uint64_t val = 0;
+#pragma unroll
+                for (int t = 0; t < ENC_ITEMS; ++t) {
+                    if ((uint32_t)t < nval) {
+                        if (absu(v[t]) >= thr) {
+                            sigm |= 1u << t;
+                            val |= (uint64_t)(1u | ((v[t] >= 0) ? 2u : 0u)) << nb;
+                            nb += 2;
+                        } else {
+                            nb += 1;
+                        }
+                    }
+                }
+                const uint32_t nsig = __popc(sigm);
+                // one scan: entries before this thread (valid ones are dense) and significant ones before it
                 uint64_t tot;
-                const uint64_t ex = block_exscan<ENC_NT>(pack, s_wtot, tot);
-                bw_emit(s_stage, wbase, limit, bitpos + (ex & 0x3fff), val, nb);
-                if (valid && !sig) lip[keep + (uint32_t)((ex >> 14) & 0x7ff)] = v;
-                if (sig) lsp[lsp_len + (uint32_t)((ex >> 25) & 0x1fff)] = absu(v);
-                keep += (uint32_t)((tot >> 14) & 0x7ff);
-                lsp_len += (uint32_t)((tot >> 25) & 0x1fff);
-                bitpos += tot & 0x3fff;
-                bw_flush(s_stage, outrow, wbase, bitpos < limit ? bitpos : limit);
+                const uint64_t ex = block_exscan2<ENC_NT, uint64_t>((uint64_t)nsig | ((uint64_t)nval << 32), s_scan,
+                                                                    parity, tot);
+                const uint32_t sig_before = (uint32_t)ex, val_before = (uint32_t)(ex >> 32);
+                bw_emit(s_ring, limit, bitpos + val_before + sig_before, val, (int)nb);
+                uint32_t ok = keep + val_before - sig_before, os = lsp_len + sig_before;
+#pragma unroll
+                for (int t = 0; t < ENC_ITEMS; ++t) {
+                    if ((uint32_t)t < nval) {
+                        if (sigm & (1u << t))
+                            lsp[os++] = absu(v[t]);
+                        else
+                            lip[ok++] = v[t];
+                    }
+                }
+                const uint32_t tsig = (uint32_t)tot, tval = (uint32_t)(tot >> 32);
+                keep += tval - tsig;
+                lsp_len += tsig;
+                bitpos += tval + tsig;
+                bw_flush(s_ring, outrow, wflushed, bitpos < limit ? bitpos : limit);
                 done = bitpos >= limit;
             }
             if (done) break;
@@ -178,91 +219,126 @@ __global__ void __launch_bounds__(ENC_NT) spiht_encode_kernel(const EncK p)
                 int gen = 0;
                 while (cur_len > 0 && !done) {
                     uint32_t nxt_len = 0;
-                    for (uint32_t base = 0; base < cur_len && !done; base += ENC_NT) {
-                        const uint32_t e = base + tid;
-                        const bool valid = e < cur_len;
-                        const uint2 ent = valid ? cur[e] : make_uint2(0u, 0u);
-                        const uint32_t key = ent.x;
-                        const bool isA = (key >> 31) != 0;
-                        uint32_t k, i, j;
-                        key_unpack(kf, key, k, i, j);
-                        const bool fire = valid && ent.y >= (uint32_t)(n + 1);
-                        uint32_t val = fire ? 1u : 0u;
-                        int nb = valid ? 1 : 0;
-                        uint32_t nlsp = 0, nlip = 0, nnext = 0, sigmask = 0;
-                        int32_t x[4] = {0, 0, 0, 0};
-                        uint32_t nfp[4] = {0, 0, 0, 0};
-                        uint32_t ci = 0, cj = 0;
-                        if (fire) {
-                            offspring_corner(i, j, H, W, ll_h, ll_w, ci, cj);
-                            if (isA) {
-                                const int32_t *a = img + ((size_t)k * H + ci) * W + cj;
-                                x[0] = a[0];
-                                x[1] = a[1];
-                                x[2] = a[W];
-                                x[3] = a[W + 1];
-                                if (has_desc_past_offspring(i, j, H, W)) {
-                                    nnext = 1;
-                                    if (i < ll_h && j < ll_w)
-                                        nfp[0] = lpll[((size_t)k * ll_h + i) * ll_w + j];
-                                    else if (i < NH && j < NW)
-                                        nfp[0] = lp[((size_t)k * NH + i) * NW + j];
-                                }
+                    for (uint32_t base = 0; base < cur_len && !done; base += ENC_CHUNK) {
+                        const uint32_t e0 = base + tid * ENC_ITEMS;
+                        const uint32_t nval = e0 < cur_len ? min((uint32_t)ENC_ITEMS, cur_len - e0) : 0u;
+                        uint2 ent[ENC_ITEMS];
+                        if (nval == ENC_ITEMS) {
+                            const uint4 q0 = *reinterpret_cast<const uint4 *>(cur + e0);
+                            const uint4 q1 = *reinterpret_cast<const uint4 *>(cur + e0 + 2);
+                            ent[0] = make_uint2(q0.x, q0.y); ent[1] = make_uint2(q0.z, q0.w);
+                            ent[2] = make_uint2(q1.x, q1.y); ent[3] = make_uint2(q1.z, q1.w);
+                        } else {
 #pragma unroll
-                                for (int r = 0; r < 4; ++r) {
-                                    const bool sg = absu(x[r]) >= thr;
-                                    val |= (uint32_t)sg << nb;
-                                    ++nb;
-                                    if (sg) {
-                                        val |= (uint32_t)(x[r] >= 0) << nb;
-                                        ++nb;
-                                        ++nlsp;
-                                        sigmask |= 1u << r;
+                            for (int t = 0; t < ENC_ITEMS; ++t)
+                                ent[t] = (uint32_t)t < nval ? cur[e0 + t] : make_uint2(0u, 0u);
+                        }
+                        // phase 1: which sets fire; offspring of fired A sets -> shared stash + record bits
+                        uint32_t firem = 0, amask = 0, bnext = 0;  // bnext: fired A sets that leave a B set
+                        uint32_t sigmv = 0;                        // 4 bits per item: significant offspring
+                        uint32_t nlsp = 0, nb = 0;
+                        uint64_t val = 0;
+#pragma unroll
+                        for (int t = 0; t < ENC_ITEMS; ++t) {
+                            if ((uint32_t)t < nval) {
+                                const uint32_t key = ent[t].x;
+                                const bool fire = ent[t].y >= (uint32_t)(n + 1);
+                                uint64_t rec = fire ? 1u : 0u;
+                                uint32_t rb = 1;
+                                if (fire) {
+                                    firem |= 1u << t;
+                                    if (key >> 31) {
+                                        amask |= 1u << t;
+                                        uint32_t k, i, j, ci = 0, cj = 0;
+                                        key_unpack(kf, key, k, i, j);
+                                        offspring_corner(i, j, H, W, ll_h, ll_w, ci, cj);
+                                        const int32_t *a = img + ((size_t)k * H + ci) * W + cj;
+                                        const int4 x = make_int4(a[0], a[1], a[W], a[W + 1]);
+                                        s_x[tid * ENC_ITEMS + t] = x;
+                                        if (has_desc_past_offspring(i, j, H, W)) bnext |= 1u << t;
+                                        const int32_t xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+                                        for (int r = 0; r < 4; ++r) {
+                                            const bool sg = absu(xs[r]) >= thr;
+                                            rec |= (uint64_t)sg << rb;
+                                            ++rb;
+                                            if (sg) {
+                                                rec |= (uint64_t)(xs[r] >= 0) << rb;
+                                                ++rb;
+                                                ++nlsp;
+                                                sigmv |= 1u << (4 * t + r);
+                                            }
+                                        }
                                     }
                                 }
-                                nlip = 4 - nlsp;
-                            } else {
-#pragma unroll
-                                for (int r = 0; r < 4; ++r) {
-                                    const uint32_t y = ci + (r >> 1), xx = cj + (r & 1);
-                                    if (y < NH && xx < NW) nfp[r] = dp[((size_t)k * NH + y) * NW + xx];
-                                }
-                                nnext = 4;
+                                val |= rec << nb;
+                                nb += rb;
                             }
                         }
-                        const uint64_t pack = (uint64_t)nb | ((uint64_t)(valid && !fire) << 14) |
-                                              ((uint64_t)nlsp << 25) | ((uint64_t)nlip << 38) |
-                                              ((uint64_t)nnext << 51);
+                        const uint32_t nfa = __popc(amask), nfb = __popc(firem & ~amask), nfab = __popc(bnext);
+                        // one scan: entries, significant offspring, fired A, fired A leaving a B, fired B
                         uint64_t tot;
-                        const uint64_t ex = block_exscan<ENC_NT>(pack, s_wtot, tot);
-                        bw_emit(s_stage, wbase, limit, bitpos + (ex & 0x3fff), val, nb);
-                        if (valid && !fire) R[rkeep + (uint32_t)((ex >> 14) & 0x7ff)] = ent;
-                        if (fire) {
-                            uint32_t on = nxt_len + (uint32_t)(ex >> 51);
-                            if (isA) {
-                                uint32_t os = lsp_len + (uint32_t)((ex >> 25) & 0x1fff);
-                                uint32_t oi = lip_len + (uint32_t)((ex >> 38) & 0x1fff);
+                        const uint64_t pack = (uint64_t)nlsp | ((uint64_t)nfa << 14) | ((uint64_t)nfab << 26) |
+                                              ((uint64_t)nfb << 38) | ((uint64_t)nval << 50);
+                        const uint64_t ex = block_exscan2<ENC_NT, uint64_t>(pack, s_scan, parity, tot);
+                        const uint32_t x_lsp = (uint32_t)(ex & 0x3fff), x_fa = (uint32_t)((ex >> 14) & 0xfff),
+                                       x_fab = (uint32_t)((ex >> 26) & 0xfff), x_fb = (uint32_t)((ex >> 38) & 0xfff),
+                                       x_val = (uint32_t)(ex >> 50);
+                        // bits before this thread: one per entry, four per fired A set, one per significant offspring
+                        bw_emit(s_ring, limit, bitpos + x_val + 4 * x_fa + x_lsp, val, (int)nb);
+                        // phase 2: retained sets, new pixels, next generation
+                        uint32_t ok = rkeep + x_val - x_fa - x_fb;
+                        uint32_t os = lsp_len + x_lsp, oi = lip_len + 4 * x_fa - x_lsp;
+                        uint32_t on = nxt_len + x_fab + 4 * x_fb;
 #pragma unroll
-                                for (int r = 0; r < 4; ++r) {
-                                    if (sigmask & (1u << r))
-                                        lsp[os++] = absu(x[r]);
-                                    else
-                                        lip[oi++] = x[r];
+                        for (int t = 0; t < ENC_ITEMS; ++t) {
+                            if ((uint32_t)t < nval) {
+                                const uint32_t key = ent[t].x;
+                                if (!(firem & (1u << t))) {
+                                    R[ok++] = ent[t];
+                                } else if (amask & (1u << t)) {
+                                    const int4 x = s_x[tid * ENC_ITEMS + t];
+                                    const int32_t xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+                                    for (int r = 0; r < 4; ++r) {
+                                        if (sigmv & (1u << (4 * t + r)))
+                                            lsp[os++] = absu(xs[r]);
+                                        else
+                                            lip[oi++] = xs[r];
+                                    }
+                                    if (bnext & (1u << t)) {
+                                        uint32_t k, i, j;
+                                        key_unpack(kf, key, k, i, j);
+                                        uint32_t f = 0;
+                                        if (i < ll_h && j < ll_w)
+                                            f = lpll[((size_t)k * ll_h + i) * ll_w + j];
+                                        else if (i < NH && j < NW)
+                                            f = lp[((size_t)k * NH + i) * NW + j];
+                                        nxt[on++] = make_uint2(key & 0x7fffffffu, f);
+                                    }
+                                } else {
+                                    uint32_t k, i, j, ci = 0, cj = 0;
+                                    key_unpack(kf, key, k, i, j);
+                                    offspring_corner(i, j, H, W, ll_h, ll_w, ci, cj);
+#pragma unroll
+                                    for (int r = 0; r < 4; ++r) {
+                                        const uint32_t y = ci + (r >> 1), xx = cj + (r & 1);
+                                        uint32_t f = 0;
+                                        if (y < NH && xx < NW) f = dp[((size_t)k * NH + y) * NW + xx];
+                                        nxt[on++] = make_uint2(0x80000000u | key_pack(kf, k, y, xx), f);
+                                    }
                                 }
-                                if (nnext) nxt[on] = make_uint2(key & 0x7fffffffu, nfp[0]);
-                            } else {
-#pragma unroll
-                                for (int r = 0; r < 4; ++r)
-                                    nxt[on + r] = make_uint2(
-                                        0x80000000u | key_pack(kf, k, ci + (r >> 1), cj + (r & 1)), nfp[r]);
                             }
                         }
-                        rkeep += (uint32_t)((tot >> 14) & 0x7ff);
-                        lsp_len += (uint32_t)((tot >> 25) & 0x1fff);
-                        lip_len += (uint32_t)((tot >> 38) & 0x1fff);
-                        nxt_len += (uint32_t)(tot >> 51);
-                        bitpos += tot & 0x3fff;
-                        bw_flush(s_stage, outrow, wbase, bitpos < limit ? bitpos : limit);
+                        const uint32_t t_lsp = (uint32_t)(tot & 0x3fff), t_fa = (uint32_t)((tot >> 14) & 0xfff),
+                                       t_fab = (uint32_t)((tot >> 26) & 0xfff), t_fb = (uint32_t)((tot >> 38) & 0xfff),
+                                       t_val = (uint32_t)(tot >> 50);
+                        rkeep += t_val - t_fa - t_fb;
+                        lsp_len += t_lsp;
+                        lip_len += 4 * t_fa - t_lsp;
+                        nxt_len += t_fab + 4 * t_fb;
+                        bitpos += t_val + 4 * t_fa + t_lsp;
+                        bw_flush(s_ring, outrow, wflushed, bitpos < limit ? bitpos : limit);
                         done = bitpos >= limit;
                     }
                     uint2 *old = cur;
@@ -277,21 +353,20 @@ __global__ void __launch_bounds__(ENC_NT) spiht_encode_kernel(const EncK p)
 
             // ---- refinement (encoder_decoder.rs:287-292): one bit per older LSP entry
             for (uint32_t base = 0; base < lsp_len0 && !done; base += ENC_NT * ENC_REF_ITEMS) {
-                __syncthreads();  // staging window reset by the previous flush is complete
 #pragma unroll
                 for (int r = 0; r < ENC_REF_ITEMS; ++r) {
                     const uint32_t e = base + r * ENC_NT + tid;
                     const uint32_t v = e < lsp_len0 ? lsp[e] : 0u;
                     const uint32_t word = __ballot_sync(0xffffffffu, (v >> n) & 1u);
-                    const uint32_t e0 = e - lane;
-                    if (lane == 0 && e0 < lsp_len0) {
-                        const uint32_t cnt = min(32u, lsp_len0 - e0);
-                        bw_emit(s_stage, wbase, limit, bitpos + (e0 - base),
-                                cnt < 32 ? (word & ((1u << cnt) - 1u)) : word, (int)cnt);
+                    const uint32_t eb = e - lane;
+                    if (lane == 0 && eb < lsp_len0) {
+                        const uint32_t cnt = min(32u, lsp_len0 - eb);
+                        bw_emit(s_ring, limit, bitpos + (eb - base), cnt < 32 ? (word & ((1u << cnt) - 1u)) : word,
+                                (int)cnt);
                     }
                 }
                 bitpos += min((uint32_t)(ENC_NT * ENC_REF_ITEMS), lsp_len0 - base);
-                bw_flush(s_stage, outrow, wbase, bitpos < limit ? bitpos : limit);
+                bw_flush(s_ring, outrow, wflushed, bitpos < limit ? bitpos : limit);
                 done = bitpos >= limit;
             }
             if (done || n == 0) break;
@@ -301,7 +376,7 @@ __global__ void __launch_bounds__(ENC_NT) spiht_encode_kernel(const EncK p)
         __syncthreads();
         const uint64_t end = bitpos < limit ? bitpos : limit;
         if (tid == 0) {
-            if (end & 31) outrow[wbase] = s_stage[0];
+            if (end & 31) outrow[wflushed] = s_ring[wflushed & (ENC_RING - 1)];
             p.nbits[b] = end;
             p.max_n[b] = max_n;
             if (p.status) p.status[b] = (bitpos >= limit && want > cap_bits) ? 1 : 0;
@@ -343,9 +418,9 @@ int launch_encode(spihtb_ctx *ctx, const EncArgs &a)
     const uint64_t chw = (uint64_t)a.C * a.H * a.W;
     uint64_t budget = a.dev_max_bits ? a.out_stride * 8 : (a.max_bits == 0 ? ~0ull : a.max_bits);
     budget = std::min<uint64_t>(budget, a.out_stride * 8);
-    const uint64_t pix_cap = std::min<uint64_t>(chw + T0, T0 + budget) + ENC_SLACK;
+    const uint64_t pix_cap = (std::min<uint64_t>(chw + T0, T0 + budget) + ENC_SLACK + 3) / 4 * 4;
     const uint64_t lis_shape = (uint64_t)a.C * (a.H / 2 + 2) * (a.W / 2 + 2) * 5 / 4 + T0;
-    const uint64_t lis_cap = std::min<uint64_t>(lis_shape, T0 + budget) + ENC_SLACK;
+    const uint64_t lis_cap = (std::min<uint64_t>(lis_shape, T0 + budget) + ENC_SLACK + 3) / 4 * 4;
     k.pix_cap = pix_cap;
     k.lis_cap = lis_cap;
     const size_t per_slot = pix_cap * 8 + lis_cap * 3 * sizeof(uint2);
