@@ -22,7 +22,14 @@ struct EncArgs {
     int32_t *max_n;       // [B]
     int32_t *status;      // optional [B]
 };
-int launch_encode(spihtb_ctx *ctx, const EncArgs &a);
+struct EncPlan {
+    uint64_t pix_cap, lis_cap;  // list capacities per resident CTA ("slot"), in entries
+    size_t per_slot;            // bytes of list storage per slot
+    int max_slots;              // CTAs of the coder the device can hold at once
+};
+int plan_encode(spihtb_ctx *ctx, const EncArgs &a, EncPlan *pl);
+int launch_encode(spihtb_ctx *ctx, const EncArgs &a, const EncPlan &pl, void *lists, int slots, unsigned int *counter);
+int launch_encode(spihtb_ctx *ctx, const EncArgs &a);  // whole batch, context workspace
 
 // ---- spiht_dec.cu
 struct DecArgs {

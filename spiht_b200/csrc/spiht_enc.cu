@@ -52,6 +52,34 @@ struct EncK {
     unsigned int *counter;
 };
 
+// ---- gathers through cp.async (LDGSTS): 4-byte copies global -> shared
+__device__ __forceinline__ void cp_async4(uint32_t saddr, const void *gptr)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(saddr), "l"(gptr) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+// the aligned 32-bit word holding byte *p, and that byte's value within the word
+__device__ __forceinline__ const void *word_of(const uint8_t *p)
+{
+    return reinterpret_cast<const void *>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)3);
+}
+__device__ __forceinline__ uint32_t byte_of(uint32_t word, const uint8_t *p)
+{
+    return (word >> (8u * (uint32_t)(reinterpret_cast<uintptr_t>(p) & 3u))) & 0xffu;
+}
+__device__ __forceinline__ int4 lds_int4(uint32_t saddr)
+{
+    int4 v;
+    asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t saddr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
+    return v;
+}
+
 // OR `nb` (<= 40) bits of `val` into the staging ring at stream position `off`; bits at or past `limit` are dropped
 __device__ __forceinline__ void bw_emit(uint32_t *ring, uint64_t limit, uint64_t off, uint64_t val, int nb)
 {
@@ -85,11 +113,29 @@ __device__ __forceinline__ void bw_flush(uint32_t *ring, uint32_t *outrow, uint6
     wflushed = wend;
 }
 
+__device__ unsigned long long g_enc_prof[16];
+extern "C" int spihtb_debug_enc_prof(unsigned long long *out16)
+{
+    unsigned long long z[16] = {0};
+    if (cudaMemcpyFromSymbol(out16, g_enc_prof, sizeof(z)) != cudaSuccess) return SPIHTB_ECUDA;
+    if (cudaMemcpyToSymbol(g_enc_prof, z, sizeof(z)) != cudaSuccess) return SPIHTB_ECUDA;
+    return SPIHTB_OK;
+}
+#define ENC_T0() const long long _t0 = clock64()
+#define ENC_ADD(slot, cnt)                                                              \
+    do {                                                                                \
+        if (tid == 0 && b == 0) {                                                       \
+            g_enc_prof[slot] += (unsigned long long)(clock64() - _t0);                  \
+            g_enc_prof[slot + 8] += (cnt);                                              \
+        }                                                                               \
+    } while (0)
+
 __global__ void __launch_bounds__(ENC_NT, 2) spiht_encode_kernel(const EncK p)
 {
     __shared__ uint32_t s_ring[ENC_RING];
     __shared__ uint64_t s_scan[2][ENC_NT / 32 + 1];
-    __shared__ int4 s_x[ENC_CHUNK];  // the four offspring of the chunk's fired A sets
+    __shared__ int4 s_x[ENC_CHUNK];      // per entry: the offspring coefficients (fired A) / firing-plane words (fired B)
+    __shared__ uint32_t s_f[ENC_CHUNK];  // per entry: the word holding the firing plane of the B set a fired A leaves
     __shared__ int s_img;
 
     const int tid = threadIdx.x;
@@ -97,6 +143,8 @@ __global__ void __launch_bounds__(ENC_NT, 2) spiht_encode_kernel(const EncK p)
     const KeyFmt kf = p.kf;
     const uint32_t H = p.H, W = p.W, NH = p.NH, NW = p.NW, ll_h = p.ll_h, ll_w = p.ll_w, C = p.C;
     int parity = 0;
+    uint32_t a_sx = (uint32_t)__cvta_generic_to_shared(s_x), a_sf = (uint32_t)__cvta_generic_to_shared(s_f);
+    asm volatile("" : "+r"(a_sx), "+r"(a_sf));  // keep the shared addresses in registers
 
     int32_t *lip = p.lip + (size_t)blockIdx.x * p.pix_cap;
     uint32_t *lsp = p.lsp + (size_t)blockIdx.x * p.pix_cap;
@@ -126,6 +174,7 @@ __global__ void __launch_bounds__(ENC_NT, 2) spiht_encode_kernel(const EncK p)
 
         for (int i = tid; i < ENC_RING; i += ENC_NT) s_ring[i] = 0;
         uint64_t wflushed = 0, bitpos = 0;
+        const long long _timg = clock64();
 
         // ---- list initialisation (encoder_decoder.rs:170-190): i, j, channel innermost
         const uint32_t T0 = ll_h * ll_w * C;
@@ -161,6 +210,7 @@ __global__ void __launch_bounds__(ENC_NT, 2) spiht_encode_kernel(const EncK p)
             // A thread takes ENC_ITEMS consecutive entries: record = "0" | "1 sign".
             uint32_t keep = 0;
             for (uint32_t base = 0; base < lip_len && !done; base += ENC_CHUNK) {
+                ENC_T0();
                 const uint32_t e0 = base + tid * ENC_ITEMS;
                 const uint32_t nval = e0 < lip_len ? min((uint32_t)ENC_ITEMS, lip_len - e0) : 0u;
                 int32_t v[ENC_ITEMS];
@@ -208,6 +258,7 @@ __global__ void __launch_bounds__(ENC_NT, 2) spiht_encode_kernel(const EncK p)
                 bitpos += tval + tsig;
                 bw_flush(s_ring, outrow, wflushed, bitpos < limit ? bitpos : limit);
                 done = bitpos >= limit;
+                ENC_ADD(0, 1);
             }
             if (done) break;
             lip_len = keep;
@@ -220,6 +271,7 @@ __global__ void __launch_bounds__(ENC_NT, 2) spiht_encode_kernel(const EncK p)
                 while (cur_len > 0 && !done) {
                     uint32_t nxt_len = 0;
                     for (uint32_t base = 0; base < cur_len && !done; base += ENC_CHUNK) {
+                        ENC_T0();
                         const uint32_t e0 = base + tid * ENC_ITEMS;
                         const uint32_t nval = e0 < cur_len ? min((uint32_t)ENC_ITEMS, cur_len - e0) : 0u;
                         uint2 ent[ENC_ITEMS];
@@ -233,41 +285,70 @@ __global__ void __launch_bounds__(ENC_NT, 2) spiht_encode_kernel(const EncK p)
                             for (int t = 0; t < ENC_ITEMS; ++t)
                                 ent[t] = (uint32_t)t < nval ? cur[e0 + t] : make_uint2(0u, 0u);
                         }
-                        // phase 1: which sets fire; offspring of fired A sets -> shared stash + record bits
+                        // phase 1a: which sets fire.  Everything a fired set needs from HBM is gathered with
+                        // cp.async straight into the shared stash, all items at once (one memory round trip per
+                        // chunk, no registers held): a fired A set its four offspring coefficients and, if it
+                        // leaves a B set, the word holding that set's firing plane; a fired B set the words
+                        // holding its four offspring's firing planes.
                         uint32_t firem = 0, amask = 0, bnext = 0;  // bnext: fired A sets that leave a B set
-                        uint32_t sigmv = 0;                        // 4 bits per item: significant offspring
+                        const uint32_t st_x = a_sx + (tid * ENC_ITEMS) * 16, st_f = a_sf + (tid * ENC_ITEMS) * 4;
+#pragma unroll
+                        for (int t = 0; t < ENC_ITEMS; ++t) {
+                            if ((uint32_t)t < nval && ent[t].y >= (uint32_t)(n + 1)) {
+                                const uint32_t key = ent[t].x;
+                                firem |= 1u << t;
+                                uint32_t k, i, j, ci = 0, cj = 0;
+                                key_unpack(kf, key, k, i, j);
+                                offspring_corner(i, j, H, W, ll_h, ll_w, ci, cj);
+                                if (key >> 31) {
+                                    amask |= 1u << t;
+                                    const int32_t *a = img + ((size_t)k * H + ci) * W + cj;
+                                    cp_async4(st_x + 16 * t, a);
+                                    cp_async4(st_x + 16 * t + 4, a + 1);
+                                    cp_async4(st_x + 16 * t + 8, a + W);
+                                    cp_async4(st_x + 16 * t + 12, a + W + 1);
+                                    if (has_desc_past_offspring(i, j, H, W)) {
+                                        bnext |= 1u << t;
+                                        const uint8_t *f = nullptr;
+                                        if (i < ll_h && j < ll_w)
+                                            f = lpll + ((size_t)k * ll_h + i) * ll_w + j;
+                                        else if (i < NH && j < NW)
+                                            f = lp + ((size_t)k * NH + i) * NW + j;
+                                        if (f) cp_async4(st_f + 4 * t, word_of(f));
+                                    }
+                                } else {
+#pragma unroll
+                                    for (int r = 0; r < 4; ++r) {
+                                        const uint32_t y = ci + (r >> 1), xx = cj + (r & 1);
+                                        if (y < NH && xx < NW)
+                                            cp_async4(st_x + 16 * t + 4 * r, word_of(dp + ((size_t)k * NH + y) * NW + xx));
+                                    }
+                                }
+                            }
+                        }
+                        cp_async_wait_all();
+                        // phase 1b: record bits ("0" | B: "1" | A: "1" + four offspring records)
+                        uint32_t sigmv = 0;  // 4 bits per item: significant offspring
                         uint32_t nlsp = 0, nb = 0;
                         uint64_t val = 0;
 #pragma unroll
                         for (int t = 0; t < ENC_ITEMS; ++t) {
                             if ((uint32_t)t < nval) {
-                                const uint32_t key = ent[t].x;
-                                const bool fire = ent[t].y >= (uint32_t)(n + 1);
-                                uint64_t rec = fire ? 1u : 0u;
+                                uint64_t rec = (firem >> t) & 1u;
                                 uint32_t rb = 1;
-                                if (fire) {
-                                    firem |= 1u << t;
-                                    if (key >> 31) {
-                                        amask |= 1u << t;
-                                        uint32_t k, i, j, ci = 0, cj = 0;
-                                        key_unpack(kf, key, k, i, j);
-                                        offspring_corner(i, j, H, W, ll_h, ll_w, ci, cj);
-                                        const int32_t *a = img + ((size_t)k * H + ci) * W + cj;
-                                        const int4 x = make_int4(a[0], a[1], a[W], a[W + 1]);
-                                        s_x[tid * ENC_ITEMS + t] = x;
-                                        if (has_desc_past_offspring(i, j, H, W)) bnext |= 1u << t;
-                                        const int32_t xs[4] = {x.x, x.y, x.z, x.w};
+                                if (amask & (1u << t)) {
+                                    const int4 x = lds_int4(st_x + 16 * t);
+                                    const int32_t xs[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
-                                        for (int r = 0; r < 4; ++r) {
-                                            const bool sg = absu(xs[r]) >= thr;
-                                            rec |= (uint64_t)sg << rb;
+                                    for (int r = 0; r < 4; ++r) {
+                                        const bool sg = absu(xs[r]) >= thr;
+                                        rec |= (uint64_t)sg << rb;
+                                        ++rb;
+                                        if (sg) {
+                                            rec |= (uint64_t)(xs[r] >= 0) << rb;
                                             ++rb;
-                                            if (sg) {
-                                                rec |= (uint64_t)(xs[r] >= 0) << rb;
-                                                ++rb;
-                                                ++nlsp;
-                                                sigmv |= 1u << (4 * t + r);
-                                            }
+                                            ++nlsp;
+                                            sigmv |= 1u << (4 * t + r);
                                         }
                                     }
                                 }
@@ -286,7 +367,7 @@ __global__ void __launch_bounds__(ENC_NT, 2) spiht_encode_kernel(const EncK p)
                                        x_val = (uint32_t)(ex >> 50);
                         // bits before this thread: one per entry, four per fired A set, one per significant offspring
                         bw_emit(s_ring, limit, bitpos + x_val + 4 * x_fa + x_lsp, val, (int)nb);
-                        // phase 2: retained sets, new pixels, next generation
+                        // phase 2: retained sets, new pixels, next generation (everything comes from the stash)
                         uint32_t ok = rkeep + x_val - x_fa - x_fb;
                         uint32_t os = lsp_len + x_lsp, oi = lip_len + 4 * x_fa - x_lsp;
                         uint32_t on = nxt_len + x_fab + 4 * x_fb;
@@ -297,7 +378,7 @@ __global__ void __launch_bounds__(ENC_NT, 2) spiht_encode_kernel(const EncK p)
                                 if (!(firem & (1u << t))) {
                                     R[ok++] = ent[t];
                                 } else if (amask & (1u << t)) {
-                                    const int4 x = s_x[tid * ENC_ITEMS + t];
+                                    const int4 x = lds_int4(st_x + 16 * t);
                                     const int32_t xs[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
                                     for (int r = 0; r < 4; ++r) {
@@ -311,20 +392,22 @@ __global__ void __launch_bounds__(ENC_NT, 2) spiht_encode_kernel(const EncK p)
                                         key_unpack(kf, key, k, i, j);
                                         uint32_t f = 0;
                                         if (i < ll_h && j < ll_w)
-                                            f = lpll[((size_t)k * ll_h + i) * ll_w + j];
+                                            f = byte_of(lds_u32(st_f + 4 * t), lpll + ((size_t)k * ll_h + i) * ll_w + j);
                                         else if (i < NH && j < NW)
-                                            f = lp[((size_t)k * NH + i) * NW + j];
+                                            f = byte_of(lds_u32(st_f + 4 * t), lp + ((size_t)k * NH + i) * NW + j);
                                         nxt[on++] = make_uint2(key & 0x7fffffffu, f);
                                     }
                                 } else {
                                     uint32_t k, i, j, ci = 0, cj = 0;
                                     key_unpack(kf, key, k, i, j);
                                     offspring_corner(i, j, H, W, ll_h, ll_w, ci, cj);
+                                    const int4 wd = lds_int4(st_x + 16 * t);
+                                    const uint32_t ws[4] = {(uint32_t)wd.x, (uint32_t)wd.y, (uint32_t)wd.z, (uint32_t)wd.w};
 #pragma unroll
                                     for (int r = 0; r < 4; ++r) {
                                         const uint32_t y = ci + (r >> 1), xx = cj + (r & 1);
                                         uint32_t f = 0;
-                                        if (y < NH && xx < NW) f = dp[((size_t)k * NH + y) * NW + xx];
+                                        if (y < NH && xx < NW) f = byte_of(ws[r], dp + ((size_t)k * NH + y) * NW + xx);
                                         nxt[on++] = make_uint2(0x80000000u | key_pack(kf, k, y, xx), f);
                                     }
                                 }
@@ -340,6 +423,7 @@ __global__ void __launch_bounds__(ENC_NT, 2) spiht_encode_kernel(const EncK p)
                         bitpos += t_val + 4 * t_fa + t_lsp;
                         bw_flush(s_ring, outrow, wflushed, bitpos < limit ? bitpos : limit);
                         done = bitpos >= limit;
+                        ENC_ADD(1, 1);
                     }
                     uint2 *old = cur;
                     cur = nxt;
@@ -353,6 +437,7 @@ __global__ void __launch_bounds__(ENC_NT, 2) spiht_encode_kernel(const EncK p)
 
             // ---- refinement (encoder_decoder.rs:287-292): one bit per older LSP entry
             for (uint32_t base = 0; base < lsp_len0 && !done; base += ENC_NT * ENC_REF_ITEMS) {
+                ENC_T0();
 #pragma unroll
                 for (int r = 0; r < ENC_REF_ITEMS; ++r) {
                     const uint32_t e = base + r * ENC_NT + tid;
@@ -368,6 +453,7 @@ __global__ void __launch_bounds__(ENC_NT, 2) spiht_encode_kernel(const EncK p)
                 bitpos += min((uint32_t)(ENC_NT * ENC_REF_ITEMS), lsp_len0 - base);
                 bw_flush(s_ring, outrow, wflushed, bitpos < limit ? bitpos : limit);
                 done = bitpos >= limit;
+                ENC_ADD(2, 1);
             }
             if (done || n == 0) break;
         }
@@ -380,12 +466,33 @@ __global__ void __launch_bounds__(ENC_NT, 2) spiht_encode_kernel(const EncK p)
             p.nbits[b] = end;
             p.max_n[b] = max_n;
             if (p.status) p.status[b] = (bitpos >= limit && want > cap_bits) ? 1 : 0;
+            if (b == 0) g_enc_prof[3] += (unsigned long long)(clock64() - _timg);
         }
         __syncthreads();
     }
 }
 
-int launch_encode(spihtb_ctx *ctx, const EncArgs &a)
+// List capacities: bounded by the shape and by the bit budget (every entry created costs at least one
+// emitted bit), see DESIGN.md.  max_slots: CTAs of the coder that can be resident at once.
+int plan_encode(spihtb_ctx *ctx, const EncArgs &a, EncPlan *pl)
+{
+    int occ = 1;
+    SPIHTB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, spiht_encode_kernel, ENC_NT, 0));
+    if (occ < 1) occ = 1;
+    pl->max_slots = ctx->sm_count * occ;
+    const uint64_t T0 = (uint64_t)a.ll_h * a.ll_w * a.C;
+    const uint64_t chw = (uint64_t)a.C * a.H * a.W;
+    uint64_t budget = a.dev_max_bits ? a.out_stride * 8 : (a.max_bits == 0 ? ~0ull : a.max_bits);
+    budget = std::min<uint64_t>(budget, a.out_stride * 8);
+    pl->pix_cap = (std::min<uint64_t>(chw + T0, T0 + budget) + ENC_SLACK + 3) / 4 * 4;
+    const uint64_t lis_shape = (uint64_t)a.C * (a.H / 2 + 2) * (a.W / 2 + 2) * 5 / 4 + T0;
+    pl->lis_cap = (std::min<uint64_t>(lis_shape, T0 + budget) + ENC_SLACK + 3) / 4 * 4;
+    pl->per_slot = pl->pix_cap * 8 + pl->lis_cap * 3 * sizeof(uint2);
+    return SPIHTB_OK;
+}
+
+// `lists`: a region of per_slot * slots bytes (256-byte aligned); `counter`: one zero-initialised-here word.
+int launch_encode(spihtb_ctx *ctx, const EncArgs &a, const EncPlan &pl, void *lists, int slots, unsigned int *counter)
 {
     EncK k;
     if (!make_keyfmt(a.C, a.H, a.W, &k.kf)) {
@@ -406,33 +513,13 @@ int launch_encode(spihtb_ctx *ctx, const EncArgs &a)
     k.out = reinterpret_cast<uint32_t *>(a.out);
     k.out_stride_words = a.out_stride / 4;
     k.nbits = a.nbits; k.max_n = a.max_n; k.status = a.status;
-
-    int occ = 1;
-    SPIHTB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, spiht_encode_kernel, ENC_NT, 0));
-    if (occ < 1) occ = 1;
-    const int slots = std::min(a.B, ctx->sm_count * occ);
-
-    // list capacities: bounded by the shape and by the bit budget (every entry
-    // created costs at least one emitted bit), see DESIGN.md
-    const uint64_t T0 = (uint64_t)a.ll_h * a.ll_w * a.C;
-    const uint64_t chw = (uint64_t)a.C * a.H * a.W;
-    uint64_t budget = a.dev_max_bits ? a.out_stride * 8 : (a.max_bits == 0 ? ~0ull : a.max_bits);
-    budget = std::min<uint64_t>(budget, a.out_stride * 8);
-    const uint64_t pix_cap = (std::min<uint64_t>(chw + T0, T0 + budget) + ENC_SLACK + 3) / 4 * 4;
-    const uint64_t lis_shape = (uint64_t)a.C * (a.H / 2 + 2) * (a.W / 2 + 2) * 5 / 4 + T0;
-    const uint64_t lis_cap = (std::min<uint64_t>(lis_shape, T0 + budget) + ENC_SLACK + 3) / 4 * 4;
-    k.pix_cap = pix_cap;
-    k.lis_cap = lis_cap;
-    const size_t per_slot = pix_cap * 8 + lis_cap * 3 * sizeof(uint2);
-    int rc = ctx->ensure(ctx->lists, per_slot * slots + 256);
-    if (rc) return rc;
-    rc = ctx->ensure(ctx->misc, 256);
-    if (rc) return rc;
-    uint8_t *base = static_cast<uint8_t *>(ctx->lists.p);
+    k.pix_cap = pl.pix_cap;
+    k.lis_cap = pl.lis_cap;
+    uint8_t *base = static_cast<uint8_t *>(lists);
     k.lis = reinterpret_cast<uint2 *>(base);
-    k.lip = reinterpret_cast<int32_t *>(base + (size_t)slots * lis_cap * 3 * sizeof(uint2));
-    k.lsp = reinterpret_cast<uint32_t *>(base + (size_t)slots * (lis_cap * 3 * sizeof(uint2) + pix_cap * 4));
-    k.counter = static_cast<unsigned int *>(ctx->misc.p);
+    k.lip = reinterpret_cast<int32_t *>(base + (size_t)slots * pl.lis_cap * 3 * sizeof(uint2));
+    k.lsp = reinterpret_cast<uint32_t *>(base + (size_t)slots * (pl.lis_cap * 3 * sizeof(uint2) + pl.pix_cap * 4));
+    k.counter = counter;
     SPIHTB_CUDA_CHECK(cudaMemsetAsync(k.counter, 0, sizeof(unsigned int), ctx->stream));
     ctx->stage_begin(4);
     spiht_encode_kernel<<<slots, ENC_NT, 0, ctx->stream>>>(k);
@@ -440,6 +527,20 @@ int launch_encode(spihtb_ctx *ctx, const EncArgs &a)
     ctx->stage_end(4);
     SPIHTB_CUDA_CHECK(cudaGetLastError());
     return SPIHTB_OK;
+}
+
+// single launch over the whole batch with the context's workspace
+int launch_encode(spihtb_ctx *ctx, const EncArgs &a)
+{
+    EncPlan pl;
+    int rc = plan_encode(ctx, a, &pl);
+    if (rc) return rc;
+    const int slots = std::min(a.B, pl.max_slots);
+    rc = ctx->ensure(ctx->lists, pl.per_slot * slots + 256);
+    if (rc) return rc;
+    rc = ctx->ensure(ctx->misc, 256);
+    if (rc) return rc;
+    return launch_encode(ctx, a, pl, ctx->lists.p, slots, static_cast<unsigned int *>(ctx->misc.p));
 }
 
 }  // namespace spihtb

@@ -19,6 +19,10 @@ s, nbits, max_n, status, coeffs = batch.encode_images(px, g, st, mb)
 nbytes = (nbits + 7) // 8
 out = (ctypes.c_ulonglong * 16)()
 lib = _lib.lib()
+lib.spihtb_debug_enc_prof(out)
+v = list(out)
+print("encoder (image 0): cycles", {"lip": v[0], "lis": v[1], "refine": v[2], "image_total": v[3]},
+      "chunks", {"lip": v[8], "lis": v[9], "refine": v[10]})
 for it in range(3):
     batch.decode_images(s, nbytes, max_n, 3, g, st, dtype=torch.float32)
     torch.cuda.synchronize()
