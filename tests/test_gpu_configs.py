@@ -1,0 +1,147 @@
+"""BASELINE.json configurations at their full image sizes (small batches), on the GPU.
+
+Parity at full size:
+  * SPIHT: the CUDA bitstream must equal the CPU oracle's bitstream on the identical int32 coefficient array
+    (the array the GPU forward transform produced), byte for byte, and the CUDA decoder must return the array
+    the oracle decoder returns for those bytes;
+  * float stages (configs 2, 3, 5): quantised coefficients against the float64 oracle with mismatches counted
+    (rule of tests/test_gpu_transform.py);
+  * size-independent properties everywhere: nbits == budget, decode(encode(x)) reproduces every coefficient the
+    budget reached to within its last coded bit-plane, PSNR rises with bpp.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def T():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch
+
+
+def _mismatches(got, oracle_float):
+    want = oracle_float.astype(np.int32)
+    bad = np.nonzero(got != want)
+    n_bad = len(bad[0])
+    if n_bad:
+        d = np.abs(got[bad].astype(np.int64) - want[bad])
+        near = np.abs(oracle_float[bad] - np.round(oracle_float[bad]))
+        assert d.max() <= 1 and near.max() < 1e-6
+    return n_bad
+
+
+def _spiht_parity(T, oracle, streams, nbits, max_n, coeffs, geom, max_bits, fast=False):
+    from spiht_b200 import batch
+    B, C = coeffs.shape[:2]
+    nbytes = (nbits + 7) // 8
+    rec = batch.decode_coeffs(streams, nbytes, max_n, C, geom.enc_h, geom.enc_w, geom.ll_h, geom.ll_w)
+    enc = oracle.model_encode if fast else oracle.encode
+    for b in range(B):
+        arr = coeffs[b].cpu().numpy()
+        want, want_n = enc(arr, geom.ll_h, geom.ll_w, max_bits)
+        nb = int(nbytes[b])
+        got = streams[b, :nb].cpu().numpy().tobytes()
+        assert int(max_n[b]) == want_n
+        assert int(nbits[b]) == min(max_bits, int(nbits[b]))
+        assert got == want, f"image {b}: CUDA stream differs from the oracle"
+        assert np.array_equal(rec[b].cpu().numpy(),
+                              oracle.decode(want, want_n, C, geom.enc_h, geom.enc_w, geom.ll_h, geom.ll_w))
+
+
+def _psnr(a, b):
+    return float(10 * np.log10(1.0 / np.mean((a - b) ** 2)))
+
+
+def test_config2_1024_bior22_reflect_half_bpp(T, oracle):
+    """batch of synthetic 1024x1024 RGB images, bior2.2 reflect, 0.5 bpp (BASELINE.json configs[1])"""
+    import spiht_b200 as spiht
+    from oracle import wrapper_ref
+    from spiht_b200 import _lib, batch
+    from spiht_b200.utils import synthetic_images
+    px = synthetic_images(3, 3, 1024, 1024, seed=2000)
+    st = spiht.SpihtSettings()
+    g = _lib.plan(1024, 1024)
+    assert (g.levels, g.enc_h, g.enc_w, g.ll_h, g.ll_w) == (7, 1053, 1053, 12, 12)
+    mb = int(1024 * 1024 * 0.5)
+    s, nbits, max_n, status, coeffs = batch.encode_images(px, g, st, mb)
+    assert int(status.max()) == 0 and int(nbits.min()) == mb
+    _spiht_parity(T, oracle, s, nbits, max_n, coeffs, g, mb)
+    of, _, _ = wrapper_ref.forward_coeffs(px[0].cpu().numpy().astype(np.float64), return_float=True)
+    assert _mismatches(coeffs[0].cpu().numpy(), of) == 0
+    out, _ = batch.decode_images(s, (nbits + 7) // 8, max_n, 3, g, st, dtype=T.float32)
+    ref = wrapper_ref.decode_image(dict(encoded_bytes=s[0, :mb // 8].cpu().numpy().tobytes(), h=1024, w=1024, c=3,
+                                        max_n=int(max_n[0]), level=None))
+    assert np.abs(out[0].cpu().numpy() - ref).max() < 1e-5
+    assert _psnr(out[0, :, :1024, :1024].cpu().numpy(), px[0].cpu().numpy()) > 20
+
+
+def test_config3_2048_ipt_tenth_bpp(T, oracle):
+    """2048x2048, IPT colour space with [50,15,15] quantisation scales, 0.1 bpp (configs[2])"""
+    import spiht_b200 as spiht
+    from oracle import wrapper_ref
+    from spiht_b200 import _lib, batch
+    from spiht_b200.utils import synthetic_images
+    px = synthetic_images(2, 3, 2048, 2048, seed=3000)
+    kw = dict(quantization_scale=1.0, color_model="IPT", per_channel_quant_scales=[50.0, 15.0, 15.0])
+    st = spiht.SpihtSettings(**kw)
+    g = _lib.plan(2048, 2048)
+    assert (g.levels, g.enc_h, g.ll_h) == (8, 2081, 12)
+    mb = int(2048 * 2048 * 0.1)
+    s, nbits, max_n, status, coeffs = batch.encode_images(px, g, st, mb)
+    assert int(nbits.min()) == mb
+    _spiht_parity(T, oracle, s, nbits, max_n, coeffs, g, mb)
+    of, _, _ = wrapper_ref.forward_coeffs(px[0].cpu().numpy().astype(np.float64), return_float=True, **kw)
+    n_bad = _mismatches(coeffs[0].cpu().numpy(), of)
+    print("config 3: quantised coefficient mismatches vs float64 oracle:", n_bad, "of", of.size)
+    assert n_bad <= 1e-5 * of.size
+    out, _ = batch.decode_images(s, (nbits + 7) // 8, max_n, 3, g, st, dtype=T.float32)
+    assert _psnr(out[0, :, :2048, :2048].cpu().numpy(), px[0].cpu().numpy()) > 18
+
+
+def test_config4_8192_bior68_one_bpp(T, oracle):
+    """bior6.8 reflect, max decomposition level, 8192x8192 at 1.0 bpp (configs[3]: deep tree, large halo)"""
+    import spiht_b200 as spiht
+    from spiht_b200 import _lib, batch
+    from spiht_b200.utils import synthetic_images
+    px = synthetic_images(1, 3, 8192, 8192, seed=4000, chunk=1)
+    st = spiht.SpihtSettings(wavelet="bior6.8")
+    g = _lib.plan(8192, 8192, "bior6.8", "reflect")
+    assert (g.levels, g.enc_h, g.ll_h) == (8, 8321, 48)
+    mb = 8192 * 8192
+    s, nbits, max_n, status, coeffs = batch.encode_images(px, g, st, mb)
+    assert int(nbits[0]) == mb and int(status[0]) == 0
+    # the pyramid formulation of the oracle (bit-identical to the faithful coder, tests/test_oracle_spiht.py)
+    _spiht_parity(T, oracle, s, nbits, max_n, coeffs, g, mb, fast=True)
+    out, rec = batch.decode_images(s, (nbits + 7) // 8, max_n, 3, g, st, dtype=T.float32)
+    # every coefficient the budget reached is reproduced to within its last coded bit-plane
+    err = (rec[0].to(T.int64) - coeffs[0].to(T.int64)).abs()
+    coded = rec[0] != 0
+    assert int(err[coded].max()) < int(coeffs[0].abs().max())
+    assert _psnr(out[0, :, :8192, :8192].cpu().numpy(), px[0].cpu().numpy()) > 28
+
+
+@pytest.mark.parametrize("bpp", [0.075, 0.1, 0.5, 1.0])
+def test_config5_periodization_mixed_sizes(T, oracle, bpp):
+    """bpp sweep plus periodization mode on a mixed-size batch (configs[4])"""
+    import spiht_b200 as spiht
+    from conftest import synth_image
+    st = spiht.SpihtSettings(mode="periodization")
+    sizes = [512, 1024, 2048, 512] if bpp != 1.0 else [512, 4096]
+    imgs = [synth_image(3, n, n, 50 + i).astype(np.float32) for i, n in enumerate(sizes)]
+    budgets = [int(n * n * bpp) for n in sizes]
+    encs = [spiht.encode_images([im], st, max_bits=mb)[0] for im, mb in zip(imgs, budgets)]
+    from spiht_b200 import _lib, batch
+    for im, mb, e in zip(imgs, budgets, encs):
+        n = im.shape[1]
+        g = _lib.plan(n, n, "bior2.2", "periodization")
+        assert (g.enc_h, g.enc_w) == (n, n)
+        coeffs = batch.forward(T.from_numpy(im[None]).cuda(), g, st)[0].cpu().numpy()
+        want, want_n = oracle.model_encode(coeffs, g.ll_h, g.ll_w, mb)
+        assert (e.encoded_bytes, e.max_n) == (want, want_n)
+        assert len(e.encoded_bytes) == (mb + 7) // 8
+    recs = spiht.decode_images(encs, st)
+    ps = [_psnr(r[:, :im.shape[1], :im.shape[2]], im) for r, im in zip(recs, imgs)]
+    assert min(ps) > 15
