@@ -66,7 +66,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
@@ -241,16 +241,23 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
+    # clocks are sampled from the start of the warm-up to the end of the timed region: the GPU is under the
+    # same load throughout, and the timed region alone (K steps of a few ms) is shorter than one nvidia-smi
+    # period.  Warm-up runs at least W >= 3 steps and at least ~0.8 s so that several samples land under load.
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    t_warm = time.perf_counter()
+    n_warm = 0
+    while n_warm < max(args.warmup, 3) or (time.perf_counter() - t_warm < 0.8 and n_warm < 400):
         res = step()
+        torch.cuda.synchronize()
+        n_warm += 1
     barrier()
 
     # ---- timed region: K steps, CUDA events on the launching stream, stage timers on
-    clocks = ClockSampler(local_rank)
     ctx.profile(True)
     ctx.profile_read(reset=True)
     launches0 = ctx.launch_count()
-    clocks.start()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -359,7 +366,7 @@ def run_b200(args):
 
     line = {
         "metric": "encode megapixels/sec at %.3g bpp" % args.bpp, "value": round(value, 1), "unit": "MP/s",
-        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 4),
+        "n_gpus": world, "steps": args.steps, "warmup": n_warm, "ms_per_step": round(ms_per_step, 4),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64/int32",
         "data": "synthetic",
         "config": {"workload": workload_name(args), "global_batch": world * B, "max_bits": max_bits,
