@@ -9,6 +9,8 @@
 // for the dyadic rule (encoder_decoder.rs:65-74) on the node grid
 // [0,h/2) x [0,w/2); dpll/lpll hold the same for the LL roots, whose offspring
 // follow the block rule of encoder_decoder.rs:44-62.
+#include <algorithm>
+
 #include "common.cuh"
 #include "kernels.cuh"
 
@@ -22,7 +24,7 @@ constexpr int PYR_UNROLL = 4;
 
 __global__ void __launch_bounds__(256) pyr_base_kernel(const int32_t *__restrict__ coeffs, int H, int W, int NH, int NW,
                                                        int gy, int C, uint8_t *__restrict__ dp,
-                                                       uint32_t *__restrict__ maxabs)
+                                                       uint8_t *__restrict__ lp, uint32_t *__restrict__ maxabs)
 {
     __shared__ uint32_t s_max[8];
     const int lane = threadIdx.x, wy = threadIdx.y;
@@ -37,6 +39,7 @@ __global__ void __launch_bounds__(256) pyr_base_kernel(const int32_t *__restrict
         const bool has1 = r0 + 1 < H;
         const int32_t *p1 = has1 ? p0 + W : p0;
         uint8_t *drow = dp + ((size_t)z * NH + (ip < NH ? ip : 0)) * NW;
+        uint8_t *lrow = lp + ((size_t)z * NH + (ip < NH ? ip : 0)) * NW;  // cleared: ring-1 nodes have no L-set
         const int ncell = (W + 1) >> 1;  // cells incl. a half cell in the last odd column
         for (int jb = 0; jb < ncell; jb += 32 * PYR_UNROLL) {
             uint32_t m[PYR_UNROLL];
@@ -55,7 +58,10 @@ __global__ void __launch_bounds__(256) pyr_base_kernel(const int32_t *__restrict
             for (int u = 0; u < PYR_UNROLL; ++u) {
                 const int j = jb + u * 32 + lane;
                 wmax = max(wmax, m[u]);
-                if (ip < NH && j < NW) drow[j] = (uint8_t)plane1(m[u]);
+                if (ip < NH && j < NW) {
+                    drow[j] = (uint8_t)plane1(m[u]);
+                    lrow[j] = 0;
+                }
             }
         }
     }
@@ -72,54 +78,93 @@ __global__ void __launch_bounds__(256) pyr_base_kernel(const int32_t *__restrict
 }
 
 // ---- ring t >= 2: nodes whose deepest child chain has length t ------------
-__global__ void __launch_bounds__(256) pyr_up_kernel(int NH, int NW, int RH, int RW, int IH, int IW, int nz,
-                                                     uint8_t *__restrict__ dp, uint8_t *__restrict__ lp)
+// node (i,j) of ring [0,RH) x [0,RW) minus the deeper rings [0,IH) x [0,IW):
+//   lp = max dp over its four child nodes, dp = max(dp, lp)
+__device__ __forceinline__ void pyr_up_node(uint8_t *__restrict__ d, uint8_t *__restrict__ l, int NH, int NW, int i, int j)
 {
-    const size_t per = (size_t)RH * RW;
-    const size_t total = per * nz;
-    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
-        const int z = (int)(t / per);
-        const int r = (int)(t % per);
-        const int i = r / RW, j = r % RW;
-        if (i < IH && j < IW) continue;  // deeper ring (or the self-referential node (0,0))
-        uint8_t *d = dp + (size_t)z * NH * NW;
-        uint32_t l = 0;
+    uint32_t m = 0;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            int ci = 2 * i + (q >> 1), cj = 2 * j + (q & 1);
-            if (ci < NH && cj < NW) l = max(l, (uint32_t)d[(size_t)ci * NW + cj]);
+    for (int q = 0; q < 4; ++q) {
+        const int ci = 2 * i + (q >> 1), cj = 2 * j + (q & 1);
+        if (ci < NH && cj < NW) m = max(m, (uint32_t)d[(size_t)ci * NW + cj]);
+    }
+    const size_t o = (size_t)i * NW + j;
+    l[o] = (uint8_t)m;
+    d[o] = (uint8_t)max((uint32_t)d[o], m);
+}
+
+// one large ring (ring 2 is a quarter of the node grid): blockDim (32, 8) tiles of nodes; a thread takes the
+// same node of PYR_ZPT planes with all their loads in flight together
+constexpr int PYR_ZPT = 8;
+__global__ void __launch_bounds__(256) pyr_ring_kernel(int NH, int NW, int RH, int RW, int IH, int IW, int nz,
+                                                       uint8_t *__restrict__ dp, uint8_t *__restrict__ lp)
+{
+    const int j = blockIdx.x * 32 + threadIdx.x, i = blockIdx.y * 8 + threadIdx.y;
+    if (i >= RH || j >= RW || (i < IH && j < IW)) return;  // outside / deeper ring (or the self-referential node (0,0))
+    const size_t plane = (size_t)NH * NW, o = (size_t)i * NW + j;
+    const bool r1 = 2 * i + 1 < NH, c1 = 2 * j + 1 < NW;  // 2i < NH and 2j < NW hold for every ring node
+    const size_t c00 = (size_t)(2 * i) * NW + 2 * j;
+    for (int z0 = blockIdx.z * PYR_ZPT; z0 < nz; z0 += gridDim.z * PYR_ZPT) {
+        uint32_t own[PYR_ZPT], m[PYR_ZPT];
+#pragma unroll
+        for (int q = 0; q < PYR_ZPT; ++q) {
+            own[q] = m[q] = 0;
+            if (z0 + q < nz) {
+                const uint8_t *d = dp + (size_t)(z0 + q) * plane;
+                own[q] = d[o];
+                uint32_t a = d[c00], b = c1 ? d[c00 + 1] : 0u;
+                uint32_t c = r1 ? d[c00 + NW] : 0u, e = (r1 && c1) ? d[c00 + NW + 1] : 0u;
+                m[q] = max(max(a, b), max(c, e));
+            }
         }
-        size_t o = (size_t)i * NW + j;
-        lp[(size_t)z * NH * NW + o] = (uint8_t)l;
-        d[o] = (uint8_t)max((uint32_t)d[o], l);
+#pragma unroll
+        for (int q = 0; q < PYR_ZPT; ++q) {
+            if (z0 + q < nz) {
+                lp[(size_t)(z0 + q) * plane + o] = (uint8_t)m[q];
+                dp[(size_t)(z0 + q) * plane + o] = (uint8_t)max(own[q], m[q]);
+            }
+        }
     }
 }
 
-// ---- LL roots --------------------------------------------------------------
-__global__ void __launch_bounds__(256) pyr_ll_kernel(const int32_t *__restrict__ coeffs, int H, int W, int NH, int NW,
-                                                     int ll_h, int ll_w, int nz, const uint8_t *__restrict__ dp,
-                                                     uint8_t *__restrict__ dpll, uint8_t *__restrict__ lpll)
+// the small rings t_start.. and the LL roots of one plane per CTA (each ring is a quarter of the one
+// before it: the rings of a plane are chained with barriers instead of one launch per ring)
+__global__ void __launch_bounds__(256) pyr_rest_kernel(const int32_t *__restrict__ coeffs, int H, int W, int NH, int NW,
+                                                       int ll_h, int ll_w, int t_start, uint8_t *__restrict__ dp,
+                                                       uint8_t *__restrict__ lp, uint8_t *__restrict__ dpll,
+                                                       uint8_t *__restrict__ lpll)
 {
-    const int per = ll_h * ll_w;
-    const size_t total = (size_t)per * nz;
-    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
-        const int z = (int)(t / per);
-        const int r = (int)(t % per);
+    const int z = blockIdx.x;
+    uint8_t *d = dp + (size_t)z * NH * NW;
+    uint8_t *l = lp + (size_t)z * NH * NW;
+    for (int t = t_start;; ++t) {
+        const long long s = 1LL << (t - 1);
+        const int RH = (int)((NH + s - 1) / s), RW = (int)((NW + s - 1) / s);
+        if (RH <= 1 && RW <= 1) break;
+        const int IH = (int)((NH + 2 * s - 1) / (2 * s)), IW = (int)((NW + 2 * s - 1) / (2 * s));
+        for (int r = threadIdx.x; r < RH * RW; r += blockDim.x) {
+            const int i = r / RW, j = r % RW;
+            if (i < IH && j < IW) continue;
+            pyr_up_node(d, l, NH, NW, i, j);
+        }
+        __syncthreads();  // the next ring reads this ring's dp
+    }
+    // LL roots (encoder_decoder.rs:44-62)
+    const int32_t *a = coeffs + (size_t)z * H * W;
+    for (int r = threadIdx.x; r < ll_h * ll_w; r += blockDim.x) {
         const uint32_t i = r / ll_w, j = r % ll_w;
         uint32_t ci, cj, dd = 0, ll = 0;
         if (offspring_corner(i, j, H, W, ll_h, ll_w, ci, cj)) {
-            const int32_t *a = coeffs + (size_t)z * H * W;
-            const uint8_t *d = dp + (size_t)z * NH * NW;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                uint32_t y = ci + (q >> 1), x = cj + (q & 1);
+                const uint32_t y = ci + (q >> 1), x = cj + (q & 1);
                 dd = max(dd, plane1(absu(a[(size_t)y * W + x])));
                 if (y < (uint32_t)NH && x < (uint32_t)NW) ll = max(ll, (uint32_t)d[(size_t)y * NW + x]);
             }
             dd = max(dd, ll);
         }
-        dpll[t] = (uint8_t)dd;
-        lpll[t] = (uint8_t)ll;
+        dpll[(size_t)z * ll_h * ll_w + r] = (uint8_t)dd;
+        lpll[(size_t)z * ll_h * ll_w + r] = (uint8_t)ll;
     }
 }
 
@@ -129,7 +174,6 @@ int launch_pyramid(spihtb_ctx *ctx, const int32_t *coeffs, int B, int C, int H, 
     cudaStream_t st = ctx->stream;
     const int NH = H / 2, NW = W / 2, nz = B * C;
     SPIHTB_CUDA_CHECK(cudaMemsetAsync(maxabs, 0, sizeof(uint32_t) * B, st));
-    SPIHTB_CUDA_CHECK(cudaMemsetAsync(lp, 0, (size_t)nz * NH * NW, st));  // ring-1 nodes have no L-set
     {
         const int gy = ((H + 1) / 2 + 7) / 8;
         const long long nb = (long long)gy * nz;
@@ -138,25 +182,26 @@ int launch_pyramid(spihtb_ctx *ctx, const int32_t *coeffs, int B, int C, int H, 
             return SPIHTB_ESHAPE;
         }
         ctx->stage_begin(2);
-        pyr_base_kernel<<<(unsigned)nb, dim3(32, 8), 0, st>>>(coeffs, H, W, NH, NW, gy, C, dp, maxabs);
+        pyr_base_kernel<<<(unsigned)nb, dim3(32, 8), 0, st>>>(coeffs, H, W, NH, NW, gy, C, dp, lp, maxabs);
         ctx->launches++;
         ctx->stage_end(2);
     }
     ctx->stage_begin(3);
-    for (int t = 2;; ++t) {
-        const long long s = 1LL << (t - 1);
-        const int RH = (int)((NH + s - 1) / s), RW = (int)((NW + s - 1) / s);
-        if (RH <= 1 && RW <= 1) break;
-        const int IH = (int)((NH + 2 * s - 1) / (2 * s)), IW = (int)((NW + 2 * s - 1) / (2 * s));
-        const size_t total = (size_t)RH * RW * nz;
-        const unsigned nb = (unsigned)std::min<size_t>((total + 255) / 256, (size_t)ctx->sm_count * 16);
-        pyr_up_kernel<<<nb, 256, 0, st>>>(NH, NW, RH, RW, IH, IW, nz, dp, lp);
-        ctx->launches++;
-    }
     {
-        const size_t total = (size_t)ll_h * ll_w * nz;
-        const unsigned nb = (unsigned)std::min<size_t>((total + 255) / 256, (size_t)ctx->sm_count * 16);
-        pyr_ll_kernel<<<nb, 256, 0, st>>>(coeffs, H, W, NH, NW, ll_h, ll_w, nz, dp, dpll, lpll);
+        // large rings: one launch each over all planes; from the first ring of at most 64 Ki nodes on, the
+        // remaining rings and the LL roots of a plane are chained inside one CTA
+        int t = 2;
+        for (;; ++t) {
+            const long long s = 1LL << (t - 1);
+            const int RH = (int)((NH + s - 1) / s), RW = (int)((NW + s - 1) / s);
+            if (RH <= 1 && RW <= 1) break;
+            if (t > 2 && (long long)RH * RW <= 65536) break;
+            const int IH = (int)((NH + 2 * s - 1) / (2 * s)), IW = (int)((NW + 2 * s - 1) / (2 * s));
+            const dim3 grid((RW + 31) / 32, (RH + 7) / 8, std::min((nz + PYR_ZPT - 1) / PYR_ZPT, 65535));
+            pyr_ring_kernel<<<grid, dim3(32, 8), 0, st>>>(NH, NW, RH, RW, IH, IW, nz, dp, lp);
+            ctx->launches++;
+        }
+        pyr_rest_kernel<<<(unsigned)nz, 256, 0, st>>>(coeffs, H, W, NH, NW, ll_h, ll_w, t, dp, lp, dpll, lpll);
         ctx->launches++;
     }
     ctx->stage_end(3);
