@@ -19,7 +19,6 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC",
     "-Xcompiler", "-O3",
     "--expt-relaxed-constexpr",
-    "-shared",
 ]
 
 
@@ -50,18 +49,46 @@ def build(force=False, verbose=False, extra_flags=()):
     """Compile every CUDA source into libspiht_b200.so; returns the path."""
     if not force and not needs_build():
         return LIB_PATH
-    cmd = [find_nvcc()] + NVCC_FLAGS + list(extra_flags) + ["-o", LIB_PATH] + sources()
-    if verbose:
-        print(" ".join(cmd))
-    proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
-    if verbose and proc.stdout:
-        print(proc.stdout)
+    # one nvcc process per translation unit (in parallel), objects under csrc/_obj, then one link
+    nvcc = find_nvcc()
+    objdir = os.path.join(CSRC, "_obj")
+    os.makedirs(objdir, exist_ok=True)
+    hdr_t = max(os.path.getmtime(d) for d in _deps() if not d.endswith(".cu"))
+    flag_tag = os.path.join(objdir, "flags.txt")
+    flags = NVCC_FLAGS + list(extra_flags)
+    same_flags = os.path.exists(flag_tag) and open(flag_tag).read() == " ".join(flags)
+    jobs, objs = [], []
+    for src in sources():
+        obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
+        objs.append(obj)
+        fresh = (not force and same_flags and os.path.exists(obj)
+                 and os.path.getmtime(obj) > max(os.path.getmtime(src), hdr_t))
+        if not fresh:
+            cmd = [nvcc] + flags + ["-c", "-o", obj, src]
+            if verbose:
+                print(" ".join(cmd))
+            jobs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    log = ""
+    failed = False
+    for cmd, proc in jobs:
+        out, _ = proc.communicate()
+        log += out or ""
+        failed = failed or proc.returncode != 0
+    if verbose and log:
+        print(log)
+    if failed:
+        raise RuntimeError("nvcc failed:\n" + log)
+    with open(flag_tag, "w") as f:
+        f.write(" ".join(flags))
+    link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH] + objs
+    proc = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if proc.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + proc.stdout)
+        raise RuntimeError("link failed:\n" + proc.stdout)
     return LIB_PATH
 
 
 if __name__ == "__main__":
     import sys
-    print(build(force="--force" in sys.argv, verbose=True,
-                extra_flags=("-Xptxas", "-v") if "--ptxas" in sys.argv else ()))
+    extra = ["-Xptxas", "-v"] if "--ptxas" in sys.argv else []
+    extra += [a for a in sys.argv[1:] if a.startswith("-D")]
+    print(build(force="--force" in sys.argv, verbose=True, extra_flags=tuple(extra)))

@@ -252,7 +252,7 @@ int spihtb_destroy(spihtb_ctx *ctx)
     if (!ctx) return SPIHTB_OK;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    DevBuf *bufs[] = {&ctx->pyr, &ctx->lists, &ctx->misc, &ctx->tmpa, &ctx->tmpb, &ctx->io, &ctx->io2};
+    DevBuf *bufs[] = {&ctx->pyr, &ctx->lists, &ctx->misc, &ctx->tmpa, &ctx->tmpb, &ctx->io, &ctx->io2, &ctx->fix};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
     for (int s = 0; s < SPIHTB_NSTAGES; ++s)
@@ -355,6 +355,34 @@ uint64_t spihtb_stream_bound(int32_t c, int32_t h, int32_t w, int32_t ll_h, int3
     return ((bits + 7) / 8 + 15) / 8 * 8;
 }
 
+}  // extern "C"
+
+// pyramid (all of it, or the rings when the forward transform already wrote the base pass) + coder
+static int encode_with_pyramid(spihtb_ctx *ctx, const int32_t *dev_coeffs, int B, int c, int h, int w, int ll_h, int ll_w,
+                               const spihtb::PyrBufs &pb, bool base_done, uint64_t max_bits,
+                               const uint64_t *dev_max_bits, uint8_t *dev_out, uint64_t out_stride,
+                               uint64_t *dev_nbits, int32_t *dev_max_n, int32_t *dev_status)
+{
+    using namespace spihtb;
+    int rc = launch_pyramid(ctx, dev_coeffs, B, c, h, w, ll_h, ll_w, pb.dp, pb.lp, pb.dpll, pb.lpll, pb.maxabs, base_done);
+    if (rc) return rc;
+    EncArgs a;
+    a.coeffs = dev_coeffs;
+    a.B = B; a.C = c; a.H = h; a.W = w; a.ll_h = ll_h; a.ll_w = ll_w;
+    a.dp = pb.dp; a.lp = pb.lp; a.dpll = pb.dpll; a.lpll = pb.lpll;
+    a.maxabs = pb.maxabs;
+    a.max_bits = max_bits;
+    a.dev_max_bits = dev_max_bits;
+    a.out = dev_out;
+    a.out_stride = out_stride;
+    a.nbits = dev_nbits;
+    a.max_n = dev_max_n;
+    a.status = dev_status;
+    return launch_encode(ctx, a);
+}
+
+extern "C" {
+
 int spihtb_encode_coeffs(spihtb_ctx *ctx, const int32_t *dev_coeffs, int32_t B, int32_t c, int32_t h, int32_t w,
                          int32_t ll_h, int32_t ll_w, uint64_t max_bits, const uint64_t *dev_max_bits,
                          uint8_t *dev_out, uint64_t out_stride, uint64_t *dev_nbits, int32_t *dev_max_n,
@@ -370,21 +398,8 @@ int spihtb_encode_coeffs(spihtb_ctx *ctx, const int32_t *dev_coeffs, int32_t B, 
     PyrBufs pb;
     rc = alloc_pyr(ctx, B, c, h, w, ll_h, ll_w, &pb);
     if (rc) return rc;
-    rc = launch_pyramid(ctx, dev_coeffs, B, c, h, w, ll_h, ll_w, pb.dp, pb.lp, pb.dpll, pb.lpll, pb.maxabs);
-    if (rc) return rc;
-    EncArgs a;
-    a.coeffs = dev_coeffs;
-    a.B = B; a.C = c; a.H = h; a.W = w; a.ll_h = ll_h; a.ll_w = ll_w;
-    a.dp = pb.dp; a.lp = pb.lp; a.dpll = pb.dpll; a.lpll = pb.lpll;
-    a.maxabs = pb.maxabs;
-    a.max_bits = max_bits;
-    a.dev_max_bits = dev_max_bits;
-    a.out = dev_out;
-    a.out_stride = out_stride;
-    a.nbits = dev_nbits;
-    a.max_n = dev_max_n;
-    a.status = dev_status;
-    return launch_encode(ctx, a);
+    return encode_with_pyramid(ctx, dev_coeffs, B, c, h, w, ll_h, ll_w, pb, false, max_bits, dev_max_bits, dev_out,
+                               out_stride, dev_nbits, dev_max_n, dev_status);
 }
 
 int spihtb_decode_coeffs(spihtb_ctx *ctx, const uint8_t *dev_in, uint64_t in_stride, const uint64_t *dev_nbytes,
@@ -563,10 +578,23 @@ int spihtb_encode_images(spihtb_ctx *ctx, const void *dev_pixels, int32_t pixel_
     }
     int rc = check_coder_geom(C, geom->enc_h, geom->enc_w, geom->ll_h, geom->ll_w);
     if (rc) return rc;
-    rc = spihtb_forward(ctx, dev_pixels, pixel_dtype, B, C, geom, color_model, ch_scales, q, dev_coeffs_scratch);
+    // forward transform with the pyramid base pass fused into its epilogue, then rings + coder
+    XformArgs x;
+    rc = fill_xform(&x, B, C, geom, color_model, ch_scales, q, pixel_dtype);
     if (rc) return rc;
-    return spihtb_encode_coeffs(ctx, dev_coeffs_scratch, B, C, geom->enc_h, geom->enc_w, geom->ll_h, geom->ll_w,
-                                max_bits, dev_max_bits, dev_out, out_stride, dev_nbits, dev_max_n, dev_status);
+    if (!ctx || !dev_pixels || !dev_out || !dev_nbits || !dev_max_n || B <= 0) {
+        set_error("null pointer or empty batch");
+        return SPIHTB_EINVAL;
+    }
+    SPIHTB_CUDA_CHECK(cudaSetDevice(ctx->device));
+    PyrBufs pb;
+    rc = alloc_pyr(ctx, B, C, geom->enc_h, geom->enc_w, geom->ll_h, geom->ll_w, &pb);
+    if (rc) return rc;
+    const PyrFuse pf = {pb.dp, pb.maxabs};
+    rc = launch_forward(ctx, dev_pixels, x, dev_coeffs_scratch, &pf);
+    if (rc) return rc;
+    return encode_with_pyramid(ctx, dev_coeffs_scratch, B, C, geom->enc_h, geom->enc_w, geom->ll_h, geom->ll_w, pb,
+                               true, max_bits, dev_max_bits, dev_out, out_stride, dev_nbits, dev_max_n, dev_status);
 }
 
 int spihtb_decode_images(spihtb_ctx *ctx, const uint8_t *dev_in, uint64_t in_stride, const uint64_t *dev_nbytes,

@@ -17,6 +17,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <type_traits>
 
 #include "common.cuh"
 #include "kernels.cuh"
@@ -39,6 +40,10 @@ struct FwdK {
     long long ntasks;       // nz * tiles_y * tiles_x
     double scale[8];
     double q;
+    // fused pyramid base pass (PYR kernels): dp planes [nz][NH][NW] and the per-image maximum magnitude
+    uint8_t *dp;
+    uint32_t *maxabs;
+    int NH, NW;
 };
 
 // out-of-line boundary rule: keeps the division sequences out of the streaming loop's code
@@ -85,28 +90,53 @@ __device__ __forceinline__ void lds_frag(uint32_t saddr, Tin (&v)[NC])
     }
 }
 
-// A lane holds two adjacent int32 outputs (v0 at p[0], v1 at p[1]; ok0/ok1: inside the band).  When p is
-// 8-byte aligned (warp-uniform: lanes are 8 bytes apart) the pair goes out as one store; otherwise every
-// lane takes its left neighbour's v1 and stores (v1', v0) at p - 1, and the row's two end columns go out
-// alone.  `row_ok` is warp-uniform.
-__device__ __forceinline__ void store_pair(int32_t *p, int32_t v0, int32_t v1, bool row_ok, bool ok0, bool ok1,
-                                           bool ok_prev, bool ok_next)
+// A lane holds two adjacent int32 outputs (v0 at p[0], v1 at p[1]).  When p is 8-byte aligned
+// (warp-uniform: lanes are 8 bytes apart) the pair goes out as one store; otherwise every lane takes its
+// left neighbour's v1 and stores (v1', v0) at p - 1, and the row's two end columns go out alone.  `fl` is
+// the lane's store plan, fixed for the strip (no branches in the streaming loop):
+//   bit 0: both columns inside the band          bit 1: only the first one
+//   bit 2: first column and the neighbour's v1   bit 3: first column, no neighbour before it
+//   bit 4: second column with no neighbour after it
+// `mis`: p is not 8-byte aligned (warp-uniform).  Returns the left neighbour's v1 (the fused pyramid pass pairs it with v0 when the band starts at an
+// odd column).
+enum : uint32_t { SP_BOTH = 1, SP_FIRST = 2, SP_PAIR_PREV = 4, SP_V0_ALONE = 8, SP_V1_ALONE = 16 };
+__device__ __forceinline__ int32_t store_pair(int32_t *p, bool mis, int32_t v0, int32_t v1, uint32_t fl)
 {
-    if ((reinterpret_cast<uintptr_t>(p) & 7) == 0) {
-        if (row_ok && ok0 && ok1)
-            *reinterpret_cast<int2 *>(p) = make_int2(v0, v1);
-        else if (row_ok && ok0)
-            p[0] = v0;
-    } else {
-        const int32_t up = __shfl_up_sync(0xffffffffu, v1, 1);
-        if (row_ok && ok0) {
-            if (ok_prev)
-                *reinterpret_cast<int2 *>(p - 1) = make_int2(up, v0);
-            else
-                p[0] = v0;
-        }
-        if (row_ok && ok1 && !ok_next) p[1] = v1;
-    }
+    const int32_t up = __shfl_up_sync(0xffffffffu, v1, 1);
+    // four predicated stores, no address selects and no branches
+    if (!mis && (fl & SP_BOTH)) *reinterpret_cast<int2 *>(p) = make_int2(v0, v1);
+    if (mis && (fl & SP_PAIR_PREV)) *reinterpret_cast<int2 *>(p - 1) = make_int2(up, v0);
+    if (fl & (mis ? SP_V0_ALONE : SP_FIRST)) p[0] = v0;
+    if (mis && (fl & SP_V1_ALONE)) p[1] = v1;
+    return up;
+}
+
+// 64-bit shuffle as two 32-bit shuffles on explicitly split halves
+__device__ __forceinline__ double shfl_up_f64(double v, int d)
+{
+    const int lo = __shfl_up_sync(0xffffffffu, __double2loint(v), d);
+    const int hi = __shfl_up_sync(0xffffffffu, __double2hiint(v), d);
+    return __hiloint2double(hi, lo);
+}
+
+// Fused pyramid base pass.  A tree node (a, b) owns the 2x2 cell rows 2a, 2a+1 x cols 2b, 2b+1 of the
+// coefficient array; its dp byte is 1 + floor(log2 max|x|) over the cell (pyramid.cu).  While a warp
+// streams a band, a lane sees both columns of a cell (its own pair, or its left neighbour's second column
+// and its own first when the band starts at an odd column) and keeps the maximum over the cell's first
+// row; on the cell's second row it writes the byte.  Cells that straddle two row chunks, two strips or
+// two bands are left to pyr_fix_kernel, which recomputes them from the finished array (fix_rects_level).
+struct CellTrack {
+    uint32_t prev;  // cell maximum over the previous row
+    int off;        // byte offset (within the plane's dp) of the cell this lane completes next
+};
+// cm: maximum over the lane's cell columns in the current row; odd: the row is the second row of its cell
+// (warp-uniform); wr: this lane's cell has both columns in this strip and both rows in this chunk
+__device__ __forceinline__ void cell_row(CellTrack &ct, uint32_t cm, bool odd, bool wr, uint8_t *dpz, int NW)
+{
+    const uint32_t m = max(ct.prev, cm);
+    ct.prev = cm;
+    if (odd && wr) dpz[ct.off] = (uint8_t)plane1(m);
+    ct.off += odd ? NW : 0;
 }
 
 template <int WID>
@@ -118,6 +148,8 @@ struct FwdCfg {
     static constexpr int NOUT = 32 * NP - (HF - 1);
     // prefetch ring depth in row pairs: a multiple of HF (static slot offsets in the unrolled loop)
     static constexpr int DEPTH = HF == 3 ? 6 : HF;
+    // resident CTAs per SM the register allocation must allow (bior2.2: 4 x 128 threads x 128 registers)
+    static constexpr int MINB = HF == 3 ? 4 : 1;
 };
 
 // One warp = one task: a strip of NOUT = 32 NP - (F/2 - 1) output columns by RH output
@@ -136,7 +168,7 @@ struct FwdCfg {
 // the next level, details quantised).  A lane whose columns lie inside the plane
 // (and whose rows are vector-aligned) copies its fragment as one vector; the halo
 // lanes of the edge strips go through the boundary map one element at a time.
-template <typename Tin, int WID, int NP, bool UNIT_M, bool LAST>
+template <typename Tin, int WID, int NP, bool UNIT_M, bool LAST, bool PYR>
 __device__ __forceinline__ void dwt_fwd_task(const FwdK &p, int tx, int ty, int z, uint32_t ring, bool aligned)
 {
     constexpr int F = Wav<WID>::F;
@@ -160,6 +192,7 @@ __device__ __forceinline__ void dwt_fwd_task(const FwdK &p, int tx, int ty, int 
 
     const Tin *plane = static_cast<const Tin *>(p.src) + (size_t)z * src_h * src_w;
     const bool lane_vec = aligned && gc >= 0 && gc + NC <= src_w;
+    const bool warp_vec = __all_sync(0xffffffffu, lane_vec);
     int col[NC];
 #pragma unroll
     for (int c = 0; c < NC; ++c) col[c] = lane_vec ? gc + c : ext_index(gc + c, src_w, mode);
@@ -176,8 +209,14 @@ __device__ __forceinline__ void dwt_fwd_task(const FwdK &p, int tx, int ty, int 
             pb = plane + (size_t)ext_index_slow(gr + 1, src_h, mode) * src_w;
         }
         const uint32_t sa = my + slot_off, sb = sa + 32 * FRAG;
-        if (lane_vec) {
-            constexpr int VB = FRAG >= 16 ? 16 : 8;
+        constexpr int VB = FRAG >= 16 ? 16 : 8;
+        if (warp_vec) {  // interior strips: every lane copies its fragment as vectors (no per-lane predicates)
+#pragma unroll
+            for (int o = 0; o < FRAG; o += VB) {
+                cp_async<VB>(sa + o, reinterpret_cast<const char *>(pa + gc) + o);
+                cp_async<VB>(sb + o, reinterpret_cast<const char *>(pb + gc) + o);
+            }
+        } else if (lane_vec) {
 #pragma unroll
             for (int o = 0; o < FRAG; o += VB) {
                 cp_async<VB>(sa + o, reinterpret_cast<const char *>(pa + gc) + o);
@@ -231,14 +270,54 @@ __device__ __forceinline__ void dwt_fwd_task(const FwdK &p, int tx, int ty, int 
     const bool ok_prev = lane >= 1 && lane - 1 >= HL && kf - 1 < p.bw;
     const bool ok_next = lane < 31 && lane + 1 >= HL && kf + NP < p.bw;
     const int Wc = p.Wc;
-    int32_t *cz = p.coeffs + (size_t)z * p.Hc * Wc;
-    int32_t *p_aa = cz + (ptrdiff_t)r0 * Wc + kf;           // LL corner (last level only)
-    int32_t *p_ad = p_aa + p.sw;                            // rows lo, cols hi: top right
-    int32_t *p_da = cz + (ptrdiff_t)(p.sh + r0) * Wc + kf;  // rows hi, cols lo: bottom left
-    int32_t *p_dd = p_da + p.sw;
+    // coefficient rows: one running pointer (array row r0 + i, column kf); the bands sit at offsets that
+    // depend on the launch parameters only:  ad +sw (rows lo, cols hi: top right), da +sh Wc (rows hi, cols
+    // lo: bottom left), dd +sh Wc + sw, and at the last level aa +0 (the LL corner)
+    int32_t *prow = p.coeffs + (size_t)z * p.Hc * Wc + (ptrdiff_t)r0 * Wc + kf;
+    const int o_ad = p.sw, o_da = p.sh * Wc, o_dd = p.sh * Wc + p.sw;
     constexpr bool ll_scratch = !LAST;
     double *p_ll = ll_scratch ? p.dst_ll + ((size_t)z * p.bh + r0) * p.bw + kf : nullptr;
     const int bw = p.bw;
+    // the lane's store plan (see store_pair) and magnitude masks, fixed for the strip
+    const bool ok0 = col_ok[0], ok1 = NP == 2 ? col_ok[NP - 1] : false;
+    uint32_t fl = 0;
+    if (ok0 && ok1) fl |= SP_BOTH;
+    if (ok0 && !ok1) fl |= SP_FIRST;
+    if (ok0 && ok_prev) fl |= SP_PAIR_PREV;
+    if (ok0 && !ok_prev) fl |= SP_V0_ALONE;
+    if (ok1 && !ok_next) fl |= SP_V1_ALONE;
+    const uint32_t k0m = ok0 ? ~0u : 0u, k1m = ok1 ? ~0u : 0u, kpm = ok_prev ? ~0u : 0u;
+    // fused pyramid base pass: one cell tracker per detail band (band rows from ro, columns from co)
+    CellTrack ct_ad, ct_da, ct_dd;
+    uint32_t mx = 0;
+    const int pyrNW = p.NW;
+    uint8_t *dpz = PYR ? p.dp + (size_t)z * p.NH * p.NW : nullptr;
+    bool wr_lo, wr_hi;  // lane's cell complete in this strip: bands starting at column 0 / at column sw
+    auto cell_init = [&](CellTrack &ct, int ro, int co, bool &wr) {
+        const int c = co + kf, a = ro + r0;
+        ct.prev = 0;
+        ct.off = (a >> 1) * p.NW + (c >> 1);
+        if (NP == 2)
+            wr = (c & 1) ? (ok0 && ok_prev) : (ok0 && ok1);
+        else
+            wr = (c & 1) && ok0 && ok_prev;
+    };
+    cell_init(ct_ad, 0, p.sw, wr_hi);
+    cell_init(ct_da, p.sh, 0, wr_lo);
+    cell_init(ct_dd, p.sh, p.sw, wr_hi);
+    const int par_ad = r0 & 1, par_lo = (p.sh + r0) & 1;  // parity of the chunk's first row in the array
+    const bool codd_hi = ((p.sw + kf) & 1) != 0, codd_lo = (kf & 1) != 0;  // first column odd (warp-uniform for NP == 2)
+    // cell maximum of one band row and the running maximum of everything stored
+    auto cell_max = [&](int32_t v0, int32_t v1, int32_t up, bool codd) -> uint32_t {
+        const uint32_t m0 = absu(v0) & k0m;
+        if (NP == 2) {
+            const uint32_t t = max(m0, absu(v1) & k1m);
+            mx = max(mx, t);
+            return codd ? max(absu(up) & kpm, m0) : t;
+        }
+        mx = max(mx, m0);
+        return max(absu(up) & kpm, m0);
+    };
 
     // the loop body is unrolled over HF rows so that the window slots are static
     const int niter = (nrows + HF - 1) / HF;
@@ -294,8 +373,8 @@ __device__ __forceinline__ void dwt_fwd_task(const FwdK &p, int tx, int ty, int 
                                 used = used || Wav<WID>::dec_lo(tap) != 0.0 || wav_dec_hi<WID>(tap) != 0.0;
                             }
                         }
-                        xlo[j][eo] = used ? __shfl_up_sync(FULL, lo[2 * idx + eo], d) : 0.0;
-                        xhi[j][eo] = used ? __shfl_up_sync(FULL, hi[2 * idx + eo], d) : 0.0;
+                        xlo[j][eo] = used ? shfl_up_f64(lo[2 * idx + eo], d) : 0.0;
+                        xhi[j][eo] = used ? shfl_up_f64(hi[2 * idx + eo], d) : 0.0;
                     }
                 }
             }
@@ -338,46 +417,63 @@ __device__ __forceinline__ void dwt_fwd_task(const FwdK &p, int tx, int ty, int 
                 q_aa[t] = ll_scratch ? 0 : quantise1(aa, qs);
                 f_aa[t] = aa;
             }
-            if constexpr (NP == 2) {
-                // both columns of a lane go out as one 8-byte store (whole 32-byte sectors per warp)
-                store_pair(p_ad, q_ad[0], q_ad[1], row_ok, col_ok[0], col_ok[1], ok_prev, ok_next);
-                store_pair(p_da, q_da[0], q_da[1], row_ok, col_ok[0], col_ok[1], ok_prev, ok_next);
-                store_pair(p_dd, q_dd[0], q_dd[1], row_ok, col_ok[0], col_ok[1], ok_prev, ok_next);
-                if (ll_scratch) {
-                    if (row_ok && col_ok[0] && col_ok[1] && (reinterpret_cast<uintptr_t>(p_ll) & 15) == 0) {
-                        *reinterpret_cast<double2 *>(p_ll) = make_double2(f_aa[0], f_aa[1]);
+            if (row_ok) {  // warp-uniform; false only for the padding rows after the chunk's last row
+                int32_t u_ad, u_da, u_dd;
+                if constexpr (NP == 2) {
+                    // both columns of a lane go out as one 8-byte store (whole 32-byte sectors per warp)
+                    const int mrow = (int)(reinterpret_cast<uintptr_t>(prow) >> 2);  // bit 0: row pointer odd
+                    u_ad = store_pair(prow + o_ad, ((mrow + o_ad) & 1) != 0, q_ad[0], q_ad[1], fl);
+                    u_da = store_pair(prow + o_da, ((mrow + o_da) & 1) != 0, q_da[0], q_da[1], fl);
+                    u_dd = store_pair(prow + o_dd, ((mrow + o_dd) & 1) != 0, q_dd[0], q_dd[1], fl);
+                    if (ll_scratch) {
+                        const bool pair = (fl & SP_BOTH) && (reinterpret_cast<uintptr_t>(p_ll) & 15) == 0;
+                        if (pair) *reinterpret_cast<double2 *>(p_ll) = make_double2(f_aa[0], f_aa[1]);
+                        if (ok0 && !pair) p_ll[0] = f_aa[0];
+                        if (ok1 && !pair) p_ll[1] = f_aa[1];
                     } else {
-                        if (row_ok && col_ok[0]) p_ll[0] = f_aa[0];
-                        if (row_ok && col_ok[1]) p_ll[1] = f_aa[1];
+                        store_pair(prow, (mrow & 1) != 0, q_aa[0], q_aa[1], fl);
                     }
                 } else {
-                    store_pair(p_aa, q_aa[0], q_aa[1], row_ok, col_ok[0], col_ok[1], ok_prev, ok_next);
-                }
-            } else {
-#pragma unroll
-                for (int t = 0; t < NP; ++t) {
-                    if (row_ok && col_ok[t]) {
-                        p_ad[t] = q_ad[t];
-                        p_da[t] = q_da[t];
-                        p_dd[t] = q_dd[t];
+                    if (ok0) {
+                        prow[o_ad] = q_ad[0];
+                        prow[o_da] = q_da[0];
+                        prow[o_dd] = q_dd[0];
                         if (ll_scratch)
-                            p_ll[t] = f_aa[t];
+                            p_ll[0] = f_aa[0];
                         else
-                            p_aa[t] = q_aa[t];
+                            prow[0] = q_aa[0];
+                    }
+                    if constexpr (PYR) {
+                        u_ad = __shfl_up_sync(FULL, q_ad[0], 1);
+                        u_da = __shfl_up_sync(FULL, q_da[0], 1);
+                        u_dd = __shfl_up_sync(FULL, q_dd[0], 1);
+                    }
+                }
+                if constexpr (PYR) {
+                    const bool not_first = i > 0;
+                    const bool odd_ad = ((i ^ par_ad) & 1) != 0, odd_lo = ((i ^ par_lo) & 1) != 0;
+                    cell_row(ct_ad, cell_max(q_ad[0], q_ad[NP - 1], u_ad, codd_hi), odd_ad, wr_hi && not_first, dpz, pyrNW);
+                    cell_row(ct_da, cell_max(q_da[0], q_da[NP - 1], u_da, codd_lo), odd_lo, wr_lo && not_first, dpz, pyrNW);
+                    cell_row(ct_dd, cell_max(q_dd[0], q_dd[NP - 1], u_dd, codd_hi), odd_lo, wr_hi && not_first, dpz, pyrNW);
+                    if (!ll_scratch) {
+                        mx = max(mx, absu(q_aa[0]) & k0m);
+                        if (NP == 2) mx = max(mx, absu(q_aa[NP - 1]) & k1m);
                     }
                 }
             }
-            p_aa += Wc;
-            p_ad += Wc;
-            p_da += Wc;
-            p_dd += Wc;
+            prow += Wc;
             if (ll_scratch) p_ll += bw;
         }
     }
+    if constexpr (PYR) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) mx = max(mx, __shfl_xor_sync(FULL, mx, d));
+        if (lane == 0 && mx) atomicMax(p.maxabs + z / p.C, mx);
+    }
 }
 
-template <typename Tin, int WID, int NP, bool UNIT_M, bool LAST>
-__global__ void __launch_bounds__(FW_WARPS * 32) dwt_fwd_level_kernel(const FwdK p)
+template <typename Tin, int WID, int NP, bool UNIT_M, bool LAST, bool PYR>
+__global__ void __launch_bounds__(FW_WARPS * 32, FwdCfg<WID>::MINB) dwt_fwd_level_kernel(const FwdK p)
 {
     constexpr int F = Wav<WID>::F;
     constexpr int NOUT = 32 * NP - (F / 2 - 1);
@@ -399,7 +495,7 @@ __global__ void __launch_bounds__(FW_WARPS * 32) dwt_fwd_level_kernel(const FwdK
                            (long long)z * p.src_h * p.src_w * (long long)sizeof(Tin);
     const bool aligned = ((size_t)p.src_w * sizeof(Tin)) % VB == 0 &&
                          (base + (long long)gc_first * (long long)sizeof(Tin)) % VB == 0;
-    dwt_fwd_task<Tin, WID, NP, UNIT_M, LAST>(p, tx, ty, z, ring, aligned);
+    dwt_fwd_task<Tin, WID, NP, UNIT_M, LAST, PYR>(p, tx, ty, z, ring, aligned);
 }
 
 // zero the gaps coeffs_to_array leaves between a level's off-diagonal blocks
@@ -477,14 +573,21 @@ static int launch_level(spihtb_ctx *ctx, FwdK k, int nz)
     bool unit = true;
     for (int c = 0; c < k.C && c < 8; ++c) unit = unit && k.scale[c] == 1.0;
     const dim3 grid((unsigned)nb), block(FW_WARPS * 32);
+    auto go = [&](auto unit_c, auto last_c) {
+        constexpr bool U = decltype(unit_c)::value, LA = decltype(last_c)::value;
+        if (k.dp)
+            dwt_fwd_level_kernel<Tin, WID, NP, U, LA, true><<<grid, block, 0, ctx->stream>>>(k);
+        else
+            dwt_fwd_level_kernel<Tin, WID, NP, U, LA, false><<<grid, block, 0, ctx->stream>>>(k);
+    };
     if (unit && k.last)
-        dwt_fwd_level_kernel<Tin, WID, NP, true, true><<<grid, block, 0, ctx->stream>>>(k);
+        go(std::true_type{}, std::true_type{});
     else if (unit)
-        dwt_fwd_level_kernel<Tin, WID, NP, true, false><<<grid, block, 0, ctx->stream>>>(k);
+        go(std::true_type{}, std::false_type{});
     else if (k.last)
-        dwt_fwd_level_kernel<Tin, WID, NP, false, true><<<grid, block, 0, ctx->stream>>>(k);
+        go(std::false_type{}, std::true_type{});
     else
-        dwt_fwd_level_kernel<Tin, WID, NP, false, false><<<grid, block, 0, ctx->stream>>>(k);
+        go(std::false_type{}, std::false_type{});
     ctx->launches++;
     return SPIHTB_OK;
 }
@@ -501,7 +604,103 @@ static int launch_level_w(spihtb_ctx *ctx, int wid, const FwdK &k, int nz)
     return SPIHTB_EINVAL;
 }
 
-int launch_forward(spihtb_ctx *ctx, const void *pixels, const XformArgs &x, int32_t *coeffs)
+// Cells of the node grid the fused base pass leaves open (a superset is harmless: the fix-up pass
+// recomputes a cell from the finished array).  Per level and detail band (rows from `ro`, columns from
+// `co`): the cell row of a chunk's first row when that row is odd and of its last row when that is even;
+// the cell column of a strip's first column when odd and of its last column when even; and the LL block.
+template <int WID>
+static void fix_rects_level(std::vector<FixRect> &out, int bh, int bw, int sh, int sw, int NH, int NW)
+{
+    constexpr int NOUT = FwdCfg<WID>::NOUT;
+    constexpr int RHMAX = 64;
+    const int tiles_x = (bw + NOUT - 1) / NOUT, tiles_y = (bh + RHMAX - 1) / RHMAX;
+    const int RH = (bh + tiles_y - 1) / tiles_y;
+    auto add = [&](int a0, int a1, int b0, int b1) {
+        a1 = std::min(a1, NH);
+        b1 = std::min(b1, NW);
+        if (a0 < a1 && b0 < b1) out.push_back(FixRect{a0, a1, b0, b1});
+    };
+    const int bands[3][2] = {{0, sw}, {sh, 0}, {sh, sw}};  // ad, da, dd: (ro, co)
+    for (const auto &bd : bands) {
+        const int ro = bd[0], co = bd[1];
+        const int b0 = co >> 1, b1 = ((co + bw - 1) >> 1) + 1;
+        const int a0 = ro >> 1, a1 = ((ro + bh - 1) >> 1) + 1;
+        for (int ty = 0; ty < tiles_y; ++ty) {
+            const int r0 = ty * RH, nrows = std::min(RH, bh - r0);
+            if (nrows <= 0) break;
+            const int first = ro + r0, last = ro + r0 + nrows - 1;
+            if (first & 1) add(first >> 1, (first >> 1) + 1, b0, b1);
+            if (!(last & 1)) add(last >> 1, (last >> 1) + 1, b0, b1);
+        }
+        for (int tx = 0; tx < tiles_x; ++tx) {
+            const int first = co + tx * NOUT, last = co + std::min((tx + 1) * NOUT, bw) - 1;
+            if (first & 1) add(a0, a1, first >> 1, (first >> 1) + 1);
+            if (!(last & 1)) add(a0, a1, last >> 1, (last >> 1) + 1);
+        }
+    }
+}
+
+static int upload_fix_rects(spihtb_ctx *ctx, const spihtb_geom &g, const FixRect **rects, const uint32_t **prefix,
+                            int *nrect, uint32_t *total)
+{
+    // key: everything the rectangle list depends on
+    int32_t key[32] = {0};
+    key[0] = g.wavelet; key[1] = g.levels; key[2] = g.enc_h; key[3] = g.enc_w; key[4] = g.ll_h; key[5] = g.ll_w;
+    for (int l = 0; l < g.levels && l < 6; ++l) {
+        key[6 + 4 * l] = g.band_h[l]; key[7 + 4 * l] = g.band_w[l];
+        key[8 + 4 * l] = g.off_h[l]; key[9 + 4 * l] = g.off_w[l];
+    }
+    key[31] = 0x5eed;
+    std::vector<int32_t> &h = ctx->fix_host;
+    const bool hit = h.size() >= 34 && memcmp(h.data(), key, sizeof(key)) == 0 && ctx->fix.p;
+    if (!hit) {
+        const int NH = g.enc_h / 2, NW = g.enc_w / 2;
+        std::vector<FixRect> r;
+        for (int l = 0; l < g.levels; ++l) {
+            switch (g.wavelet) {
+                case SPIHTB_WAVELET_BIOR22:
+                    fix_rects_level<SPIHTB_WAVELET_BIOR22>(r, g.band_h[l], g.band_w[l], g.off_h[l], g.off_w[l], NH, NW);
+                    break;
+                case SPIHTB_WAVELET_BIOR44:
+                    fix_rects_level<SPIHTB_WAVELET_BIOR44>(r, g.band_h[l], g.band_w[l], g.off_h[l], g.off_w[l], NH, NW);
+                    break;
+                default:
+                    fix_rects_level<SPIHTB_WAVELET_BIOR68>(r, g.band_h[l], g.band_w[l], g.off_h[l], g.off_w[l], NH, NW);
+                    break;
+            }
+        }
+        r.push_back(FixRect{0, std::min((g.ll_h + 1) / 2, NH), 0, std::min((g.ll_w + 1) / 2, NW)});  // LL block
+        h.assign(key, key + 32);
+        h.push_back((int32_t)r.size());
+        h.push_back(0);
+        uint64_t tot = 0;
+        std::vector<uint32_t> pre;
+        for (const FixRect &q : r) {
+            pre.push_back((uint32_t)tot);
+            tot += (uint64_t)(q.a1 - q.a0) * (q.b1 - q.b0);
+            h.push_back(q.a0); h.push_back(q.a1); h.push_back(q.b0); h.push_back(q.b1);
+        }
+        pre.push_back((uint32_t)tot);
+        if (tot > 0x7fffffffull) {
+            set_error("pyramid fix-up list too large");
+            return SPIHTB_ESHAPE;
+        }
+        h[33] = (int32_t)tot;
+        for (uint32_t v : pre) h.push_back((int32_t)v);
+        int rc = ctx->ensure(ctx->fix, h.size() * sizeof(int32_t) + 256);
+        if (rc) return rc;
+        SPIHTB_CUDA_CHECK(cudaMemcpyAsync(ctx->fix.p, h.data(), h.size() * sizeof(int32_t), cudaMemcpyHostToDevice,
+                                          ctx->stream));
+    }
+    *nrect = h[32];
+    *total = (uint32_t)h[33];
+    const int32_t *d = static_cast<const int32_t *>(ctx->fix.p);
+    *rects = reinterpret_cast<const FixRect *>(d + 34);
+    *prefix = reinterpret_cast<const uint32_t *>(d + 34 + 4 * (size_t)h[32]);
+    return SPIHTB_OK;
+}
+
+int launch_forward(spihtb_ctx *ctx, const void *pixels, const XformArgs &x, int32_t *coeffs, const PyrFuse *pf)
 {
     const spihtb_geom &g = x.g;
     const int nz = x.B * x.C;
@@ -561,6 +760,10 @@ int launch_forward(spihtb_ctx *ctx, const void *pixels, const XformArgs &x, int3
         k.C = x.C;
         for (int c = 0; c < 8; ++c) k.scale[c] = x.scale[c];
         k.q = x.q;
+        k.dp = pf ? pf->dp + (size_t)z0 * (g.enc_h / 2) * (g.enc_w / 2) : nullptr;
+        k.maxabs = pf ? pf->maxabs : nullptr;  // indexed by z / C: z0 is a multiple of C
+        k.NH = g.enc_h / 2;
+        k.NW = g.enc_w / 2;
         const int st = l == 0 ? 0 : 1;
         ctx->stage_begin(st);
         const int r = in_f64 ? launch_level_w<double>(ctx, g.wavelet, k, nzg)
@@ -568,6 +771,13 @@ int launch_forward(spihtb_ctx *ctx, const void *pixels, const XformArgs &x, int3
         ctx->stage_end(st);
         return r;
     };
+    if (pf) {
+        // gap cells stay 0; per-image maxima start from 0
+        ctx->stage_begin(2);
+        SPIHTB_CUDA_CHECK(cudaMemsetAsync(pf->dp, 0, (size_t)nz * (g.enc_h / 2) * (g.enc_w / 2), ctx->stream));
+        SPIHTB_CUDA_CHECK(cudaMemsetAsync(pf->maxabs, 0, sizeof(uint32_t) * x.B, ctx->stream));
+        ctx->stage_end(2);
+    }
     for (int l = 0; l < L; ++l) {
         rc = run_level(l, 0, nz);
         if (rc) return rc;
@@ -596,6 +806,18 @@ int launch_forward(spihtb_ctx *ctx, const void *pixels, const XformArgs &x, int3
         }
     }
     SPIHTB_CUDA_CHECK(cudaGetLastError());
+    if (pf) {
+        const FixRect *rects;
+        const uint32_t *prefix;
+        int nrect;
+        uint32_t total;
+        rc = upload_fix_rects(ctx, g, &rects, &prefix, &nrect, &total);
+        if (rc) return rc;
+        ctx->stage_begin(2);
+        rc = launch_pyr_fix(ctx, coeffs, nz, g.enc_h, g.enc_w, pf->dp, rects, prefix, nrect, total);
+        ctx->stage_end(2);
+        if (rc) return rc;
+    }
     return SPIHTB_OK;
 }
 

@@ -5,8 +5,16 @@
 namespace spihtb {
 
 // ---- pyramid.cu
+// base_done: dp already holds every node's 2x2-cell plane and maxabs the per-image maximum (the forward
+// transform wrote them, see PyrFuse); only the rings and the LL roots remain.
 int launch_pyramid(spihtb_ctx *ctx, const int32_t *coeffs, int B, int C, int H, int W, int ll_h, int ll_w,
-                   uint8_t *dp, uint8_t *lp, uint8_t *dpll, uint8_t *lpll, uint32_t *maxabs);
+                   uint8_t *dp, uint8_t *lp, uint8_t *dpll, uint8_t *lpll, uint32_t *maxabs, bool base_done = false);
+// cells [a0,a1) x [b0,b1) of the node grid recomputed from the finished coefficient array
+struct FixRect {
+    int a0, a1, b0, b1;
+};
+int launch_pyr_fix(spihtb_ctx *ctx, const int32_t *coeffs, int nz, int H, int W, uint8_t *dp, const FixRect *dev_rects,
+                   const uint32_t *dev_prefix, int nrect, uint32_t total);
 
 // ---- spiht_enc.cu
 struct EncArgs {
@@ -51,7 +59,14 @@ struct XformArgs {
     double q;
     int pixel_dtype;
 };
-int launch_forward(spihtb_ctx *ctx, const void *pixels, const XformArgs &x, int32_t *coeffs);
+// Pyramid base pass fused into the forward transform: dp planes [B*C][enc_h/2][enc_w/2] and maxabs [B]
+// are complete when launch_forward returns (stream order).
+struct PyrFuse {
+    uint8_t *dp;
+    uint32_t *maxabs;
+};
+int launch_forward(spihtb_ctx *ctx, const void *pixels, const XformArgs &x, int32_t *coeffs,
+                   const PyrFuse *pf = nullptr);
 int launch_inverse(spihtb_ctx *ctx, const int32_t *coeffs, const XformArgs &x, void *pixels_out);
 
 }  // namespace spihtb

@@ -168,13 +168,63 @@ __global__ void __launch_bounds__(256) pyr_rest_kernel(const int32_t *__restrict
     }
 }
 
+// ---- cells the fused base pass of the forward transform could not finish (dwt_fwd.cu: fix_rects) -----
+struct FixK {
+    const int32_t *coeffs;
+    int H, W, NH, NW, nz;
+    uint8_t *dp;
+    const FixRect *rects;
+    const uint32_t *prefix;  // [nrect + 1] running cell counts
+    int nrect;
+    uint32_t total;
+};
+__global__ void __launch_bounds__(256) pyr_fix_kernel(const FixK p)
+{
+    const uint32_t t = blockIdx.x * 256u + threadIdx.x;
+    if (t >= p.total) return;
+    int lo = 0, hi = p.nrect;  // last rect with prefix[r] <= t
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(p.prefix + mid) <= t)
+            lo = mid;
+        else
+            hi = mid;
+    }
+    const FixRect r = p.rects[lo];
+    const uint32_t local = t - __ldg(p.prefix + lo), w = (uint32_t)(r.b1 - r.b0);
+    const int a = r.a0 + (int)(local / w), b = r.b0 + (int)(local % w);
+    for (int z = blockIdx.y; z < p.nz; z += gridDim.y) {
+        const int32_t *x = p.coeffs + ((size_t)z * p.H + 2 * a) * p.W + 2 * b;  // 2a+1 < H, 2b+1 < W inside the node grid
+        const uint32_t m = max(max(absu(x[0]), absu(x[1])), max(absu(x[p.W]), absu(x[p.W + 1])));
+        p.dp[((size_t)z * p.NH + a) * p.NW + b] = (uint8_t)plane1(m);
+    }
+}
+
+int launch_pyr_fix(spihtb_ctx *ctx, const int32_t *coeffs, int nz, int H, int W, uint8_t *dp, const FixRect *dev_rects,
+                   const uint32_t *dev_prefix, int nrect, uint32_t total)
+{
+    if (nrect == 0 || total == 0) return SPIHTB_OK;
+    FixK k;
+    k.coeffs = coeffs;
+    k.H = H; k.W = W; k.NH = H / 2; k.NW = W / 2; k.nz = nz;
+    k.dp = dp;
+    k.rects = dev_rects;
+    k.prefix = dev_prefix;
+    k.nrect = nrect;
+    k.total = total;
+    pyr_fix_kernel<<<dim3((total + 255) / 256, std::min(nz, 65535)), 256, 0, ctx->stream>>>(k);
+    ctx->launches++;
+    SPIHTB_CUDA_CHECK(cudaGetLastError());
+    return SPIHTB_OK;
+}
+
 int launch_pyramid(spihtb_ctx *ctx, const int32_t *coeffs, int B, int C, int H, int W, int ll_h, int ll_w,
-                   uint8_t *dp, uint8_t *lp, uint8_t *dpll, uint8_t *lpll, uint32_t *maxabs)
+                   uint8_t *dp, uint8_t *lp, uint8_t *dpll, uint8_t *lpll, uint32_t *maxabs, bool base_done)
 {
     cudaStream_t st = ctx->stream;
     const int NH = H / 2, NW = W / 2, nz = B * C;
-    SPIHTB_CUDA_CHECK(cudaMemsetAsync(maxabs, 0, sizeof(uint32_t) * B, st));
-    {
+    if (!base_done) {
+        SPIHTB_CUDA_CHECK(cudaMemsetAsync(maxabs, 0, sizeof(uint32_t) * B, st));
         const int gy = ((H + 1) / 2 + 7) / 8;
         const long long nb = (long long)gy * nz;
         if (nb > 0x7fffffffLL) {

@@ -30,6 +30,7 @@ constexpr int ENC_RING = 1024;                        // staging ring in words; 
 constexpr int ENC_SLACK = 4 * ENC_CHUNK + 64;         // list slack for the chunk that crosses the budget
 static_assert(ENC_CHUNK * 9 / 32 + 8 < ENC_RING, "staging ring too small");
 static_assert((ENC_RING & (ENC_RING - 1)) == 0, "ring size must be a power of two");
+static_assert(ENC_CHUNK <= 2048, "work-list words pack a chunk index into 11 bits and a rank into 12");
 
 struct EncK {
     const int32_t *coeffs;
@@ -121,7 +122,18 @@ extern "C" int spihtb_debug_enc_prof(unsigned long long *out16)
     if (cudaMemcpyToSymbol(g_enc_prof, z, sizeof(z)) != cudaSuccess) return SPIHTB_ECUDA;
     return SPIHTB_OK;
 }
-#define ENC_T0() const long long _t0 = clock64()
+#define ENC_T0() const long long _t0 = clock64(); [[maybe_unused]] long long _tl = _t0
+// lap timer (debug builds only): cycles since the previous lap of this chunk into g_enc_prof[slot]
+#ifdef SPIHTB_ENC_LAPS
+#define ENC_LAP(slot)                                                   \
+    do {                                                                \
+        const long long _n = clock64();                                 \
+        if (tid == 0 && b == 0) g_enc_prof[slot] += (unsigned long long)(_n - _tl); \
+        _tl = _n;                                                       \
+    } while (0)
+#else
+#define ENC_LAP(slot) do { } while (0)
+#endif
 #define ENC_ADD(slot, cnt)                                                              \
     do {                                                                                \
         if (tid == 0 && b == 0) {                                                       \
@@ -134,8 +146,10 @@ __global__ void __launch_bounds__(ENC_NT, 2) spiht_encode_kernel(const EncK p)
 {
     __shared__ uint32_t s_ring[ENC_RING];
     __shared__ uint64_t s_scan[2][ENC_NT / 32 + 1];
-    __shared__ int4 s_x[ENC_CHUNK];      // per entry: the offspring coefficients (fired A) / firing-plane words (fired B)
-    __shared__ uint32_t s_f[ENC_CHUNK];  // per entry: the word holding the firing plane of the B set a fired A leaves
+    __shared__ uint2 s_wa[ENC_CHUNK];          // fired D-sets of the chunk: {key, e | leaves-B << 11 | fired B before << 12}
+    __shared__ uint2 s_wb[ENC_CHUNK];          // fired L-sets of the chunk: {key, e | fired A before << 11}
+    __shared__ uint16_t s_pab[ENC_CHUNK + 1];  // by fired-A rank: fired A sets before it that leave a B set
+    __shared__ uint16_t s_psig[ENC_CHUNK + 1]; // by fired-A rank: significant offspring before it
     __shared__ int s_img;
 
     const int tid = threadIdx.x;
@@ -143,8 +157,6 @@ __global__ void __launch_bounds__(ENC_NT, 2) spiht_encode_kernel(const EncK p)
     const KeyFmt kf = p.kf;
     const uint32_t H = p.H, W = p.W, NH = p.NH, NW = p.NW, ll_h = p.ll_h, ll_w = p.ll_w, C = p.C;
     int parity = 0;
-    uint32_t a_sx = (uint32_t)__cvta_generic_to_shared(s_x), a_sf = (uint32_t)__cvta_generic_to_shared(s_f);
-    asm volatile("" : "+r"(a_sx), "+r"(a_sf));  // keep the shared addresses in registers
 
     int32_t *lip = p.lip + (size_t)blockIdx.x * p.pix_cap;
     uint32_t *lsp = p.lsp + (size_t)blockIdx.x * p.pix_cap;
@@ -263,7 +275,17 @@ __global__ void __launch_bounds__(ENC_NT, 2) spiht_encode_kernel(const EncK p)
             if (done) break;
             lip_len = keep;
 
-            // ---- LIS pass (encoder_decoder.rs:224-284), generation by generation
+            // ---- LIS pass (encoder_decoder.rs:224-284), generation by generation.
+            // A chunk of the queue is handled in two steps so that warps never diverge over the set type:
+            //   classify: every thread looks at ENC_ITEMS consecutive entries (fires <=> firing plane > n);
+            //             one packed scan ranks the fired A sets, the fired B sets and the retained ones;
+            //             retained entries go straight back to R, fired ones into two dense shared work lists;
+            //   dense A : one fired D-set per thread -- its four offspring coefficients (and the firing plane
+            //             of the L-set it leaves) are loaded by all lanes at once; a second scan over the
+            //             number of significant offspring gives the record's bit offset and the LSP/LIP slots;
+            //   dense B : one fired L-set per thread -- "1" bit, four child D-sets with their firing planes.
+            // An entry's bit position is  bitpos + e + 4 (fired A before it) + (significant offspring before it)
+            // (e = its index in the chunk: every entry costs one bit); "0" bits are never written.
             {
                 uint2 *cur = R, *nxt = G0;
                 uint32_t cur_len = r_len, rkeep = 0;
@@ -272,156 +294,162 @@ __global__ void __launch_bounds__(ENC_NT, 2) spiht_encode_kernel(const EncK p)
                     uint32_t nxt_len = 0;
                     for (uint32_t base = 0; base < cur_len && !done; base += ENC_CHUNK) {
                         ENC_T0();
-                        const uint32_t e0 = base + tid * ENC_ITEMS;
-                        const uint32_t nval = e0 < cur_len ? min((uint32_t)ENC_ITEMS, cur_len - e0) : 0u;
+                        const uint32_t chunk_n = min((uint32_t)ENC_CHUNK, cur_len - base);
+                        const uint32_t el = tid * ENC_ITEMS;  // first entry of this thread, chunk-relative
+                        const uint32_t nval = el < chunk_n ? min((uint32_t)ENC_ITEMS, chunk_n - el) : 0u;
                         uint2 ent[ENC_ITEMS];
                         if (nval == ENC_ITEMS) {
-                            const uint4 q0 = *reinterpret_cast<const uint4 *>(cur + e0);
-                            const uint4 q1 = *reinterpret_cast<const uint4 *>(cur + e0 + 2);
+                            const uint4 q0 = *reinterpret_cast<const uint4 *>(cur + base + el);
+                            const uint4 q1 = *reinterpret_cast<const uint4 *>(cur + base + el + 2);
                             ent[0] = make_uint2(q0.x, q0.y); ent[1] = make_uint2(q0.z, q0.w);
                             ent[2] = make_uint2(q1.x, q1.y); ent[3] = make_uint2(q1.z, q1.w);
                         } else {
 #pragma unroll
                             for (int t = 0; t < ENC_ITEMS; ++t)
-                                ent[t] = (uint32_t)t < nval ? cur[e0 + t] : make_uint2(0u, 0u);
+                                ent[t] = (uint32_t)t < nval ? cur[base + el + t] : make_uint2(0u, 0u);
                         }
-                        // phase 1a: which sets fire.  Everything a fired set needs from HBM is gathered with
-                        // cp.async straight into the shared stash, all items at once (one memory round trip per
-                        // chunk, no registers held): a fired A set its four offspring coefficients and, if it
-                        // leaves a B set, the word holding that set's firing plane; a fired B set the words
-                        // holding its four offspring's firing planes.
+                        // ---- classify
                         uint32_t firem = 0, amask = 0, bnext = 0;  // bnext: fired A sets that leave a B set
-                        const uint32_t st_x = a_sx + (tid * ENC_ITEMS) * 16, st_f = a_sf + (tid * ENC_ITEMS) * 4;
 #pragma unroll
                         for (int t = 0; t < ENC_ITEMS; ++t) {
                             if ((uint32_t)t < nval && ent[t].y >= (uint32_t)(n + 1)) {
-                                const uint32_t key = ent[t].x;
                                 firem |= 1u << t;
-                                uint32_t k, i, j, ci = 0, cj = 0;
-                                key_unpack(kf, key, k, i, j);
-                                offspring_corner(i, j, H, W, ll_h, ll_w, ci, cj);
-                                if (key >> 31) {
+                                if (ent[t].x >> 31) {
                                     amask |= 1u << t;
-                                    const int32_t *a = img + ((size_t)k * H + ci) * W + cj;
-                                    cp_async4(st_x + 16 * t, a);
-                                    cp_async4(st_x + 16 * t + 4, a + 1);
-                                    cp_async4(st_x + 16 * t + 8, a + W);
-                                    cp_async4(st_x + 16 * t + 12, a + W + 1);
-                                    if (has_desc_past_offspring(i, j, H, W)) {
-                                        bnext |= 1u << t;
-                                        const uint8_t *f = nullptr;
-                                        if (i < ll_h && j < ll_w)
-                                            f = lpll + ((size_t)k * ll_h + i) * ll_w + j;
-                                        else if (i < NH && j < NW)
-                                            f = lp + ((size_t)k * NH + i) * NW + j;
-                                        if (f) cp_async4(st_f + 4 * t, word_of(f));
-                                    }
-                                } else {
-#pragma unroll
-                                    for (int r = 0; r < 4; ++r) {
-                                        const uint32_t y = ci + (r >> 1), xx = cj + (r & 1);
-                                        if (y < NH && xx < NW)
-                                            cp_async4(st_x + 16 * t + 4 * r, word_of(dp + ((size_t)k * NH + y) * NW + xx));
-                                    }
+                                    uint32_t k, i, j;
+                                    key_unpack(kf, ent[t].x, k, i, j);
+                                    if (has_desc_past_offspring(i, j, H, W)) bnext |= 1u << t;
                                 }
                             }
                         }
-                        cp_async_wait_all();
-                        // phase 1b: record bits ("0" | B: "1" | A: "1" + four offspring records)
-                        uint32_t sigmv = 0;  // 4 bits per item: significant offspring
-                        uint32_t nlsp = 0, nb = 0;
-                        uint64_t val = 0;
-#pragma unroll
-                        for (int t = 0; t < ENC_ITEMS; ++t) {
-                            if ((uint32_t)t < nval) {
-                                uint64_t rec = (firem >> t) & 1u;
-                                uint32_t rb = 1;
-                                if (amask & (1u << t)) {
-                                    const int4 x = lds_int4(st_x + 16 * t);
-                                    const int32_t xs[4] = {x.x, x.y, x.z, x.w};
-#pragma unroll
-                                    for (int r = 0; r < 4; ++r) {
-                                        const bool sg = absu(xs[r]) >= thr;
-                                        rec |= (uint64_t)sg << rb;
-                                        ++rb;
-                                        if (sg) {
-                                            rec |= (uint64_t)(xs[r] >= 0) << rb;
-                                            ++rb;
-                                            ++nlsp;
-                                            sigmv |= 1u << (4 * t + r);
-                                        }
-                                    }
-                                }
-                                val |= rec << nb;
-                                nb += rb;
-                            }
-                        }
-                        const uint32_t nfa = __popc(amask), nfb = __popc(firem & ~amask), nfab = __popc(bnext);
-                        // one scan: entries, significant offspring, fired A, fired A leaving a B, fired B
+                        ENC_LAP(4);
                         uint64_t tot;
-                        const uint64_t pack = (uint64_t)nlsp | ((uint64_t)nfa << 14) | ((uint64_t)nfab << 26) |
-                                              ((uint64_t)nfb << 38) | ((uint64_t)nval << 50);
+                        const uint64_t pack = (uint64_t)__popc(amask) | ((uint64_t)__popc(bnext) << 16) |
+                                              ((uint64_t)__popc(firem & ~amask) << 32);
                         const uint64_t ex = block_exscan2<ENC_NT, uint64_t>(pack, s_scan, parity, tot);
-                        const uint32_t x_lsp = (uint32_t)(ex & 0x3fff), x_fa = (uint32_t)((ex >> 14) & 0xfff),
-                                       x_fab = (uint32_t)((ex >> 26) & 0xfff), x_fb = (uint32_t)((ex >> 38) & 0xfff),
-                                       x_val = (uint32_t)(ex >> 50);
-                        // bits before this thread: one per entry, four per fired A set, one per significant offspring
-                        bw_emit(s_ring, limit, bitpos + x_val + 4 * x_fa + x_lsp, val, (int)nb);
-                        // phase 2: retained sets, new pixels, next generation (everything comes from the stash)
-                        uint32_t ok = rkeep + x_val - x_fa - x_fb;
-                        uint32_t os = lsp_len + x_lsp, oi = lip_len + 4 * x_fa - x_lsp;
-                        uint32_t on = nxt_len + x_fab + 4 * x_fb;
+                        const uint32_t t_fa = (uint32_t)(tot & 0xffff), t_fab = (uint32_t)((tot >> 16) & 0xffff),
+                                       t_fb = (uint32_t)((tot >> 32) & 0xffff);
+                        {
+                            uint32_t x_fa = (uint32_t)(ex & 0xffff), x_fab = (uint32_t)((ex >> 16) & 0xffff),
+                                     x_fb = (uint32_t)((ex >> 32) & 0xffff);
+                            uint32_t ok = rkeep + el - x_fa - x_fb;
 #pragma unroll
-                        for (int t = 0; t < ENC_ITEMS; ++t) {
-                            if ((uint32_t)t < nval) {
-                                const uint32_t key = ent[t].x;
-                                if (!(firem & (1u << t))) {
-                                    R[ok++] = ent[t];
-                                } else if (amask & (1u << t)) {
-                                    const int4 x = lds_int4(st_x + 16 * t);
-                                    const int32_t xs[4] = {x.x, x.y, x.z, x.w};
-#pragma unroll
-                                    for (int r = 0; r < 4; ++r) {
-                                        if (sigmv & (1u << (4 * t + r)))
-                                            lsp[os++] = absu(xs[r]);
-                                        else
-                                            lip[oi++] = xs[r];
-                                    }
-                                    if (bnext & (1u << t)) {
-                                        uint32_t k, i, j;
-                                        key_unpack(kf, key, k, i, j);
-                                        uint32_t f = 0;
-                                        if (i < ll_h && j < ll_w)
-                                            f = byte_of(lds_u32(st_f + 4 * t), lpll + ((size_t)k * ll_h + i) * ll_w + j);
-                                        else if (i < NH && j < NW)
-                                            f = byte_of(lds_u32(st_f + 4 * t), lp + ((size_t)k * NH + i) * NW + j);
-                                        nxt[on++] = make_uint2(key & 0x7fffffffu, f);
-                                    }
-                                } else {
-                                    uint32_t k, i, j, ci = 0, cj = 0;
-                                    key_unpack(kf, key, k, i, j);
-                                    offspring_corner(i, j, H, W, ll_h, ll_w, ci, cj);
-                                    const int4 wd = lds_int4(st_x + 16 * t);
-                                    const uint32_t ws[4] = {(uint32_t)wd.x, (uint32_t)wd.y, (uint32_t)wd.z, (uint32_t)wd.w};
-#pragma unroll
-                                    for (int r = 0; r < 4; ++r) {
-                                        const uint32_t y = ci + (r >> 1), xx = cj + (r & 1);
-                                        uint32_t f = 0;
-                                        if (y < NH && xx < NW) f = byte_of(ws[r], dp + ((size_t)k * NH + y) * NW + xx);
-                                        nxt[on++] = make_uint2(0x80000000u | key_pack(kf, k, y, xx), f);
+                            for (int t = 0; t < ENC_ITEMS; ++t) {
+                                if ((uint32_t)t < nval) {
+                                    const uint32_t e = el + t;
+                                    if (!(firem & (1u << t))) {
+                                        R[ok++] = ent[t];
+                                    } else if (amask & (1u << t)) {
+                                        const uint32_t bn = (bnext >> t) & 1u;
+                                        s_wa[x_fa] = make_uint2(ent[t].x, e | (bn << 11) | (x_fb << 12));
+                                        s_pab[x_fa] = (uint16_t)x_fab;
+                                        ++x_fa;
+                                        x_fab += bn;
+                                    } else {
+                                        s_wb[x_fb] = make_uint2(ent[t].x, e | (x_fa << 11));
+                                        ++x_fb;
                                     }
                                 }
                             }
+                            if (tid == 0) s_pab[t_fa] = (uint16_t)t_fab;
                         }
-                        const uint32_t t_lsp = (uint32_t)(tot & 0x3fff), t_fa = (uint32_t)((tot >> 14) & 0xfff),
-                                       t_fab = (uint32_t)((tot >> 26) & 0xfff), t_fb = (uint32_t)((tot >> 38) & 0xfff),
-                                       t_val = (uint32_t)(tot >> 50);
-                        rkeep += t_val - t_fa - t_fb;
-                        lsp_len += t_lsp;
-                        lip_len += 4 * t_fa - t_lsp;
+                        __syncthreads();
+                        ENC_LAP(5);
+                        // ---- dense A
+                        uint32_t sig_carry = 0;
+                        for (uint32_t a0 = 0; a0 < t_fa; a0 += ENC_NT) {
+                            const uint32_t a = a0 + tid;
+                            const bool valid = a < t_fa;
+                            uint2 wa = make_uint2(0u, 0u);
+                            int32_t xs[4] = {0, 0, 0, 0};
+                            uint32_t fnext = 0;
+                            if (valid) {
+                                wa = s_wa[a];
+                                uint32_t k, i, j, ci = 0, cj = 0;
+                                key_unpack(kf, wa.x, k, i, j);
+                                offspring_corner(i, j, H, W, ll_h, ll_w, ci, cj);
+                                const int32_t *x = img + ((size_t)k * H + ci) * W + cj;
+                                xs[0] = x[0];
+                                xs[1] = x[1];
+                                xs[2] = x[W];
+                                xs[3] = x[W + 1];
+                                if (wa.y & (1u << 11)) {
+                                    if (i < ll_h && j < ll_w)
+                                        fnext = lpll[((size_t)k * ll_h + i) * ll_w + j];
+                                    else if (i < NH && j < NW)
+                                        fnext = lp[((size_t)k * NH + i) * NW + j];
+                                }
+                            }
+                            uint32_t sigm = 0, rb = 1;
+                            uint32_t rec = valid ? 1u : 0u;
+#pragma unroll
+                            for (int r = 0; r < 4; ++r) {
+                                const bool sg = absu(xs[r]) >= thr;
+                                rec |= (uint32_t)sg << rb;
+                                ++rb;
+                                if (sg) {
+                                    rec |= (uint32_t)(xs[r] >= 0) << rb;
+                                    ++rb;
+                                    sigm |= 1u << r;
+                                }
+                            }
+                            const uint32_t nl = valid ? __popc(sigm) : 0u;
+                            ENC_LAP(12);
+                            uint64_t tot2;
+                            const uint32_t x_sig =
+                                sig_carry + (uint32_t)block_exscan2<ENC_NT, uint64_t>((uint64_t)nl, s_scan, parity, tot2);
+                            ENC_LAP(13);
+                            if (valid) {
+                                s_psig[a] = (uint16_t)x_sig;
+                                const uint32_t e = wa.y & 0x7ffu;
+                                bw_emit(s_ring, limit, bitpos + e + 4 * a + x_sig, rec, (int)rb);
+                                uint32_t os = lsp_len + x_sig, oi = lip_len + 4 * a - x_sig;
+#pragma unroll
+                                for (int r = 0; r < 4; ++r) {
+                                    if (sigm & (1u << r))
+                                        lsp[os++] = absu(xs[r]);
+                                    else
+                                        lip[oi++] = xs[r];
+                                }
+                                if (wa.y & (1u << 11))
+                                    nxt[nxt_len + s_pab[a] + 4 * (wa.y >> 12)] = make_uint2(wa.x & 0x7fffffffu, fnext);
+                            }
+                            sig_carry += (uint32_t)tot2;
+                            ENC_LAP(14);
+                        }
+                        if (tid == 0) s_psig[t_fa] = (uint16_t)sig_carry;
+                        __syncthreads();
+                        ENC_LAP(6);
+                        // ---- dense B
+                        for (uint32_t b0 = 0; b0 < t_fb; b0 += ENC_NT) {
+                            const uint32_t bi = b0 + tid;
+                            if (bi < t_fb) {
+                                const uint2 wb = s_wb[bi];
+                                const uint32_t e = wb.y & 0x7ffu, xa = wb.y >> 11;
+                                uint32_t k, i, j, ci = 0, cj = 0;
+                                key_unpack(kf, wb.x, k, i, j);
+                                offspring_corner(i, j, H, W, ll_h, ll_w, ci, cj);
+                                uint32_t f[4];
+#pragma unroll
+                                for (int r = 0; r < 4; ++r) {
+                                    const uint32_t y = ci + (r >> 1), xx = cj + (r & 1);
+                                    f[r] = (y < NH && xx < NW) ? (uint32_t)dp[((size_t)k * NH + y) * NW + xx] : 0u;
+                                }
+                                bw_emit(s_ring, limit, bitpos + e + 4 * xa + s_psig[xa], 1ull, 1);
+                                uint2 *o = nxt + nxt_len + s_pab[xa] + 4 * bi;
+#pragma unroll
+                                for (int r = 0; r < 4; ++r)
+                                    o[r] = make_uint2(0x80000000u | key_pack(kf, k, ci + (r >> 1), cj + (r & 1)), f[r]);
+                            }
+                        }
+                        ENC_LAP(7);
+                        rkeep += chunk_n - t_fa - t_fb;
+                        lsp_len += sig_carry;
+                        lip_len += 4 * t_fa - sig_carry;
                         nxt_len += t_fab + 4 * t_fb;
-                        bitpos += t_val + 4 * t_fa + t_lsp;
+                        bitpos += chunk_n + 4 * t_fa + sig_carry;
                         bw_flush(s_ring, outrow, wflushed, bitpos < limit ? bitpos : limit);
+                        ENC_LAP(11);
                         done = bitpos >= limit;
                         ENC_ADD(1, 1);
                     }

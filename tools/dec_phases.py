@@ -22,7 +22,9 @@ lib = _lib.lib()
 lib.spihtb_debug_enc_prof(out)
 v = list(out)
 print("encoder (image 0): cycles", {"lip": v[0], "lis": v[1], "refine": v[2], "image_total": v[3]},
-      "chunks", {"lip": v[8], "lis": v[9], "refine": v[10]})
+      "chunks", {"lip": v[8], "lis": v[9], "refine": v[10]},
+      "lis laps (SPIHTB_ENC_LAPS builds)", {"load+classify": v[4], "scan1+worklists": v[5], "denseA_tail": v[6], "denseB": v[7],
+                                            "flush": v[11], "A_load+record": v[12], "A_scan2": v[13], "A_emit+append": v[14]})
 for it in range(3):
     batch.decode_images(s, nbytes, max_n, 3, g, st, dtype=torch.float32)
     torch.cuda.synchronize()
