@@ -44,7 +44,8 @@ namespace spihtb {
 
 constexpr int DEC_NT = 512;
 constexpr int DEC_NW = DEC_NT / 32;
-constexpr int DEC_CH = 8192;           // LIS entries per chain round
+constexpr int DEC_CH = 2048;           // LIS entries per chain round
+constexpr int DEC_PLW = DEC_CH * 9 / 32 + 8;  // staged stream words per round (an entry takes at most 9 bits)
 constexpr int DEC_SLACK = 8 * DEC_NT + 64;
 constexpr int DEC_DQ = 4 * DEC_NT;     // ordered write queue (odd LL sizes only)
 
@@ -68,6 +69,11 @@ __device__ unsigned long long g_dec_prof[16];
     do {                                                                          \
         if (tid == 0 && b == 0) g_dec_prof[slot] += (unsigned long long)(clock64() - _t0); \
     } while (0)
+#ifdef SPIHTB_DEC_CHAIN_COUNTS
+#define DEC_CHAIN_CNT(x) ((x) += 1)
+#else
+#define DEC_CHAIN_CNT(x) ((void)0)
+#endif
 #define DEC_PROF_CNT(slot, v)                                  \
     do {                                                       \
         if (tid == 0 && b == 0) g_dec_prof[slot] += (v);       \
@@ -195,6 +201,11 @@ __global__ void __launch_bounds__(DEC_NT, 2) spiht_decode_kernel(const DecK p)
     __shared__ uint64_t s_wtot[DEC_NW];
     __shared__ uint32_t s_wfn[DEC_NW];
     __shared__ uint64_t s_chain_p;
+    // staged for the chain: the stream words the round can reach, bit-reversed (MSB-first), and for every
+    // bit position the child-bit length of a fired A record whose "1" sits there
+    __shared__ uint32_t s_sw[DEC_PLW];
+    __shared__ __align__(32) uint8_t s_lp[DEC_PLW * 32];
+    __shared__ uint32_t s_na;  // A sets with offspring in the round
     __shared__ uint8_t s_len[256];  // child-bit length of a fired A record from its next 8 bits
     __shared__ int s_img;
     __shared__ uint2 s_dq[DEC_DQ];  // {cell key | refine flag << 31, value or bit}
@@ -222,6 +233,7 @@ __global__ void __launch_bounds__(DEC_NT, 2) spiht_decode_kernel(const DecK p)
         }
         s_len[tid] = (uint8_t)len;
     }
+    if (tid == 0) s_na = 0;
     // bits per thread in a LIP round; the ordered write queue bounds it when cells can be duplicated
     const int BPT = has_dups ? 4 : 32;
 
@@ -429,85 +441,112 @@ __global__ void __launch_bounds__(DEC_NT, 2) spiht_decode_kernel(const DecK p)
                                 a_with_children = offspring_corner(i, j, H, W, ll_h, ll_w, ci, cj);
                             }
                             const uint32_t m = __ballot_sync(0xffffffffu, a_with_children);
-                            if (lane == 0) s_tmask[w] = __brev(m);  // MSB-first for the chain
+                            if (lane == 0) {
+                                s_tmask[w] = __brev(m);  // MSB-first for the chain
+                                if (m) atomicAdd(&s_na, (uint32_t)__popc(m));
+                            }
                             if (e < DEC_CH) s_x[e] = 0;
+                        }
+                        __syncthreads();
+                        // stage what the chain reads (all threads): the stream words the round can reach,
+                        // bit-reversed (MSB-first) and cleared from `limit` on, then for every bit position
+                        // the child-bit length of a fired A record whose "1" sits there
+                        {
+                            const uint64_t remaining = pos < limit ? limit - pos : 0ull;
+                            const uint64_t reach = (uint64_t)cnt + 8ull * s_na;
+                            const uint32_t bound = (uint32_t)(reach < remaining ? reach : remaining);
+                            const uint32_t npw = min((uint32_t)DEC_PLW - 2, (((uint32_t)(pos & 31) + bound + 31) >> 5) + 3);
+                            const uint64_t wbase = pos >> 5;
+                            for (uint32_t w = tid; w < npw + 2; w += DEC_NT) {
+                                const uint64_t gw = wbase + w;
+                                uint32_t x = __brev(br.word(gw));
+                                const uint64_t first = gw << 5;  // stream position of the word's first bit
+                                if (first + 32 > limit) x = first >= limit ? 0u : (x & ~(0xffffffffu >> (uint32_t)(limit - first)));
+                                s_sw[w] = x;
+                            }
+                            __syncthreads();
+                            for (uint32_t w = wid; w < npw; w += DEC_NW) {
+                                // lane l: record whose "1" is bit l (MSB-first) of word w; its child bits follow
+                                const uint32_t v = __funnelshift_lc(s_sw[w + 1], s_sw[w], lane + 1) >> 24;
+                                s_lp[w * 32 + lane] = s_len[v];
+                            }
                         }
                         __syncthreads();
                         DEC_PROF_ADD(1);
                         // ---- chain: one thread jumps from fired A set to fired A set
                         if (tid == 0) {
                             const long long _tc = clock64();
-                            uint32_t n_it = 0, n_ev = 0;
-                            // Everything is kept MSB-first (words bit-reversed on load) so that the next
-                            // fired A set is one count-leading-zeros away.  r0..r2: stream words, sS =
-                            // consumed bits of r0, r3/r4 prefetched; t0, t1: set-type words, sT likewise.
-                            // Shared memory is addressed with 32-bit shared-space addresses.
-                            const uint64_t avail = limit - pos;
-                            const uint32_t pmax = avail > 0xfffffff0ull ? 0xfffffff0u : (uint32_t)avail;
-                            const uint32_t *wp = br.row + (pos >> 5);
-                            const uint32_t *const wend = br.row + br.nwords;
-                            auto next_word = [&]() -> uint32_t {
-                                const uint32_t v = wp < wend ? __ldg(wp) : 0u;
-                                ++wp;
-                                return __brev(v);
-                            };
-                            uint32_t sS = (uint32_t)(pos & 31), sT = 0;
-                            uint32_t r0 = next_word(), r1 = next_word(), r2 = next_word(), r3 = next_word(),
-                                     r4 = next_word();
-                            uint32_t a_lut = (uint32_t)__cvta_generic_to_shared(s_len);
-                            uint32_t a_x = (uint32_t)__cvta_generic_to_shared(s_x);
+                            // Everything is kept MSB-first so that the next fired A set is one
+                            // count-leading-zeros away.  r0, r1 (r2 prefetched): stream words, sS = consumed
+                            // bits of r0; t0, t1 (t2): set-type words, sT likewise; all from shared memory
+                            // (32-bit addresses).  A step looks at the next 24 entries, so it consumes at most
+                            // 24 + 8 bits and one word rotation per step is enough.  The record length is one
+                            // byte load from the per-position table, under whose latency the bookkeeping
+                            // issues; bits from `limit` on are staged as zeros, so the walk needs no end test
+                            // of its own: it runs out of entries one bit per entry.
+                            // A lone warp issues roughly one instruction every four cycles here, so the
+                            // step is written for instruction count: the stream position q is kept as the
+                            // table address itself (the table is 32-byte aligned, so q mod 32 is the shift
+                            // of the stream window and the funnel shift wraps it), the entry index e is the
+                            // shift of the set-type window, and both word rotations and the step without a
+                            // fired set sit behind one rarely taken branch.
+                            uint32_t a_sw = (uint32_t)__cvta_generic_to_shared(s_sw);
+                            uint32_t q = (uint32_t)__cvta_generic_to_shared(s_lp) + (uint32_t)(pos & 31);
+                            uint32_t a_x31 = (uint32_t)__cvta_generic_to_shared(s_x) + 31u;
                             uint32_t a_t = (uint32_t)__cvta_generic_to_shared(s_tmask);
+                            uint32_t a_swe = a_sw + (DEC_PLW - 1) * 4;  // last staged word
+                            const uint32_t q0 = q;
                             // keep the addresses in registers (the compiler would otherwise rebuild them
                             // from a special register inside the loop)
-                            asm volatile("" : "+r"(a_lut), "+r"(a_x), "+r"(a_t));
+                            asm volatile("" : "+r"(a_sw), "+r"(q), "+r"(a_x31), "+r"(a_t), "+r"(a_swe));
+                            uint32_t r0 = lds_u32(a_sw), r1 = lds_u32(a_sw + 4), r2 = lds_u32(a_sw + 8);
+                            a_sw += 12;
                             uint32_t t0 = lds_u32(a_t), t1 = lds_u32(a_t + 4), t2 = lds_u32(a_t + 8);
                             a_t += 12;
-                            uint32_t e = 0, pr = 0;  // entries / bits consumed in this round
-                            while (e < cnt && pr < pmax) {
-                                const uint32_t w0 = __funnelshift_l(r1, r0, sS), w1 = __funnelshift_l(r2, r1, sS);
-                                const uint32_t tt = __funnelshift_l(t1, t0, sT);
-                                const uint32_t nl = min(32u, cnt - e);
-                                const uint32_t lz = (uint32_t)__clz((int)(w0 & tt));  // 32: no fired A set ahead
-                                const bool ev = lz < 32;
-                                const uint32_t sh = ev ? lz + 1 : nl;
-                                uint32_t len = 0;
-                                if (ev) {
-                                    len = lds_u8(a_lut + (__funnelshift_lc(w1, w0, sh) >> 24));
-                                    sts_u8(a_x + e + lz, len);
+                            uint32_t e = 0;                         // entries consumed in this round
+                            uint32_t nextq = (q & ~31u) + 32, nexte = 32;  // where the windows run out of their first word
+                            uint32_t n_it = 0, n_ev = 0;
+#pragma unroll 1
+                            while (e < cnt) {
+                                const uint32_t w0 = __funnelshift_l(r1, r0, q);
+                                const uint32_t tt = __funnelshift_l(t1, t0, e);
+                                const uint32_t m = w0 & tt & 0xffffff00u;
+                                uint32_t hb;
+                                asm("bfind.u32 %0, %1;" : "=r"(hb) : "r"(m));  // 31 - distance of the fired set
+                                const uint32_t at = q - hb;                     // table address of the set, minus 31
+                                const uint32_t len = lds_u8(at + 31u);
+                                const uint32_t e1 = e - hb + 32u;
+                                if (__builtin_expect(m != 0, 1)) {
+                                    sts_u8(a_x31 + e - hb, len);
+                                    e = e1;
+                                    q = at + len + 32u;
+                                    DEC_CHAIN_CNT(n_ev);
+                                } else {  // no fired A set within the next 24 entries
+                                    const uint32_t sh = min(24u, cnt - e);
+                                    e += sh;
+                                    q += sh;
                                 }
-                                n_it += 1;
-                                n_ev += ev ? 1u : 0u;
-                                e += sh;
-                                sT += sh;
-                                const uint32_t adv = sh + len;
-                                pr += adv;
-                                sS += adv;
-                                if (sT >= 32) {
-                                    sT -= 32;
-                                    t0 = t1;
-                                    t1 = t2;
-                                    t2 = lds_u32(a_t);
-                                    a_t += 4;
-                                }
-                                if (sS >= 32) {
-                                    sS -= 32;
-                                    r0 = r1;
-                                    r1 = r2;
-                                    r2 = r3;
-                                    r3 = r4;
-                                    r4 = next_word();
-                                    if (sS >= 32) {
-                                        sS -= 32;
+                                DEC_CHAIN_CNT(n_it);
+                                if (__builtin_expect(q >= nextq || e >= nexte, 0)) {
+                                    if (q >= nextq) {
+                                        nextq += 32;
                                         r0 = r1;
                                         r1 = r2;
-                                        r2 = r3;
-                                        r3 = r4;
-                                        r4 = next_word();
+                                        r2 = lds_u32(min(a_sw, a_swe));
+                                        a_sw += 4;
+                                    }
+                                    if (e >= nexte) {
+                                        nexte += 32;
+                                        t0 = t1;
+                                        t1 = t2;
+                                        t2 = lds_u32(a_t);
+                                        a_t += 4;
                                     }
                                 }
                             }
-                            const uint64_t cp = pos + pr;
-                            s_chain_p = cp + (cnt - e);  // entries past the end of the stream: one bit each
+                            // bits consumed: every entry one, every fired A set its child bits
+                            s_chain_p = pos + (q - q0);
+                            s_na = 0;
                             if (b == 0) {
                                 g_dec_prof[2] += (unsigned long long)(clock64() - _tc);
                                 g_dec_prof[9] += n_it;
