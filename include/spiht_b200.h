@@ -89,8 +89,8 @@ int spihtb_sync(spihtb_ctx *ctx);
 int64_t spihtb_launch_count(spihtb_ctx *ctx);
 
 /* ---- stage timers (CUDA events on the context's stream; used by bench.py for the roofline) ----
- * Stages: 0 forward DWT level 1, 1 forward remaining levels (+ colour, gap fill), 2 pyramid base pass,
- * 3 pyramid upper rings + LL roots, 4 SPIHT encode kernel, 5 SPIHT decode (zero fill + kernel),
+ * Stages: 0 forward DWT level 1, 1 forward remaining levels (+ colour, gap fill), 2 pyramid base pass (with
+ * spihtb_encode_images: zero fill + fix-up of the cells the fused epilogue leaves open), 3 pyramid upper rings + LL roots, 4 SPIHT encode kernel, 5 SPIHT decode (zero fill + kernel),
  * 6 inverse DWT coarse levels, 7 inverse DWT finest level (+ colour). */
 #define SPIHTB_NSTAGES 8
 int spihtb_profile_enable(spihtb_ctx *ctx, int enable);

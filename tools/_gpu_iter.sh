@@ -1,3 +1,3 @@
-python -m pytest tests/test_gpu_transform.py tests/test_gpu_configs.py -m gpu -x -q 2>&1 | tail -2
-python bench.py --no-cpu-baseline --no-decode --e2e-steps 1 2>&1 | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['stages_ms'])"
-ncu --set full --clock-control none --import-source on -k regex:"dwt_fwd_level_kernel" -c 2 -o gpurun_out/prof_tmp -f python tools/profile_step.py --batch 64 --steps 1 > gpurun_out/ncu_tmp.log 2>&1; tail -1 gpurun_out/ncu_tmp.log
+python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu_10.log 2>&1; tail -3 gpurun_out/pytest_gpu_10.log
+python bench.py > gpurun_out/bench_20.log 2>&1; tail -1 gpurun_out/bench_20.log | cut -c1-300
+python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref_20.log 2>&1; tail -1 gpurun_out/bench_ref_20.log | cut -c1-400
