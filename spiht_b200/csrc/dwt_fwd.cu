@@ -500,31 +500,35 @@ __global__ void __launch_bounds__(FW_WARPS * 32, FwdCfg<WID>::MINB) dwt_fwd_leve
 
 // zero the gaps coeffs_to_array leaves between a level's off-diagonal blocks
 // and the square of coarser levels: rows [bh,sh) x cols [sw,sw+bw) and
-// rows [sh,sh+bh) x cols [bw,sw)
+// rows [sh,sh+bh) x cols [bw,sw).  The host lists them as rectangles; a warp takes
+// one row of one rectangle (blockDim (32, 8), blockIdx.x over the rows of all
+// rectangles, blockIdx.y over the planes), so there is no division per element.
+// With the fused pyramid pass the node cells that lie entirely inside a gap get
+// their zero byte here as well (every other cell is written by the transform's
+// epilogue or by pyr_fix_kernel).
 struct GapK {
     int32_t *coeffs;
-    int Hc, Wc, nz, levels;
-    int bh[SPIHTB_MAX_LEVELS], bw[SPIHTB_MAX_LEVELS], sh[SPIHTB_MAX_LEVELS], sw[SPIHTB_MAX_LEVELS];
+    uint8_t *dp;  // null without the fused pyramid pass
+    int Hc, Wc, NH, NW, nz, nrect, nrows;
+    int r0[2 * SPIHTB_MAX_LEVELS], r1[2 * SPIHTB_MAX_LEVELS], c0[2 * SPIHTB_MAX_LEVELS], c1[2 * SPIHTB_MAX_LEVELS];
+    int first[2 * SPIHTB_MAX_LEVELS + 1];  // running row count
 };
-__global__ void __launch_bounds__(256) gap_fill_kernel(const GapK p)
+__global__ void __launch_bounds__(256) gap_fill_kernel(const __grid_constant__ GapK p)
 {
+    const int gr = blockIdx.x * 8 + threadIdx.y;
+    if (gr >= p.nrows) return;
+    int q = 0;
+    while (q + 1 < p.nrect && gr >= p.first[q + 1]) ++q;
+    const int r = p.r0[q] + (gr - p.first[q]), c0 = p.c0[q], c1 = p.c1[q];
+    // the cell row this coefficient row opens, when both of its rows lie in the rectangle
+    const bool cell_row = p.dp && !(r & 1) && r + 1 < p.r1[q] && (r >> 1) < p.NH;
     for (int z = blockIdx.y; z < p.nz; z += gridDim.y) {
-    int32_t *cz = p.coeffs + (size_t)z * p.Hc * p.Wc;
-    for (int l = 0; l < p.levels; ++l) {
-        const int gh = p.sh[l] - p.bh[l], gw = p.sw[l] - p.bw[l];
-        const int n1 = gh > 0 ? gh * p.bw[l] : 0;
-        const int n2 = gw > 0 ? p.bh[l] * gw : 0;
-        for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n1 + n2; t += gridDim.x * blockDim.x) {
-            if (t < n1) {
-                const int r = t / p.bw[l], c = t - r * p.bw[l];
-                cz[(size_t)(p.bh[l] + r) * p.Wc + p.sw[l] + c] = 0;
-            } else {
-                const int u = t - n1;
-                const int r = u / gw, c = u - r * gw;
-                cz[(size_t)(p.sh[l] + r) * p.Wc + p.bw[l] + c] = 0;
-            }
+        int32_t *row = p.coeffs + ((size_t)z * p.Hc + r) * p.Wc;
+        for (int c = c0 + threadIdx.x; c < c1; c += 32) row[c] = 0;
+        if (cell_row) {
+            uint8_t *drow = p.dp + ((size_t)z * p.NH + (r >> 1)) * p.NW;
+            for (int b = ((c0 + 1) >> 1) + threadIdx.x; 2 * b + 1 < c1 && b < p.NW; b += 32) drow[b] = 0;
         }
-    }
     }
 }
 
@@ -772,9 +776,12 @@ int launch_forward(spihtb_ctx *ctx, const void *pixels, const XformArgs &x, int3
         return r;
     };
     if (pf) {
-        // gap cells stay 0; per-image maxima start from 0
+        // per-image maxima start from 0.  Every cell byte is written exactly by one of: the epilogue of a
+        // level, gap_fill_kernel (cells inside a gap), pyr_fix_kernel (everything that straddles).  The tests
+        // set SPIHTB_DEBUG_POISON so that a cell none of them reaches cannot pass on a stale value.
         ctx->stage_begin(2);
-        SPIHTB_CUDA_CHECK(cudaMemsetAsync(pf->dp, 0, (size_t)nz * (g.enc_h / 2) * (g.enc_w / 2), ctx->stream));
+        if (getenv("SPIHTB_DEBUG_POISON"))
+            SPIHTB_CUDA_CHECK(cudaMemsetAsync(pf->dp, 0xff, (size_t)nz * (g.enc_h / 2) * (g.enc_w / 2), ctx->stream));
         SPIHTB_CUDA_CHECK(cudaMemsetAsync(pf->maxabs, 0, sizeof(uint32_t) * x.B, ctx->stream));
         ctx->stage_end(2);
     }
@@ -786,21 +793,29 @@ int launch_forward(spihtb_ctx *ctx, const void *pixels, const XformArgs &x, int3
     {
         GapK gk;
         gk.coeffs = coeffs;
+        gk.dp = pf ? pf->dp : nullptr;
         gk.Hc = g.enc_h;
         gk.Wc = g.enc_w;
+        gk.NH = g.enc_h / 2;
+        gk.NW = g.enc_w / 2;
         gk.nz = nz;
-        gk.levels = L;
-        bool any = false;
+        gk.nrect = 0;
+        gk.nrows = 0;
+        auto add = [&](int r0, int r1, int c0, int c1) {
+            if (r0 >= r1 || c0 >= c1) return;
+            const int q = gk.nrect++;
+            gk.r0[q] = r0; gk.r1[q] = r1; gk.c0[q] = c0; gk.c1[q] = c1;
+            gk.first[q] = gk.nrows;
+            gk.nrows += r1 - r0;
+        };
         for (int l = 0; l < L; ++l) {
-            gk.bh[l] = g.band_h[l];
-            gk.bw[l] = g.band_w[l];
-            gk.sh[l] = g.off_h[l];
-            gk.sw[l] = g.off_w[l];
-            any |= (gk.sh[l] > gk.bh[l]) || (gk.sw[l] > gk.bw[l]);
+            add(g.band_h[l], g.off_h[l], g.off_w[l], g.off_w[l] + g.band_w[l]);
+            add(g.off_h[l], g.off_h[l] + g.band_h[l], g.band_w[l], g.off_w[l]);
         }
-        if (any) {
+        gk.first[gk.nrect] = gk.nrows;
+        if (gk.nrect) {
             ctx->stage_begin(1);
-            gap_fill_kernel<<<dim3(8, std::min(nz, 65535)), 256, 0, ctx->stream>>>(gk);
+            gap_fill_kernel<<<dim3((gk.nrows + 7) / 8, std::min(nz, 48)), dim3(32, 8), 0, ctx->stream>>>(gk);
             ctx->launches++;
             ctx->stage_end(1);
         }

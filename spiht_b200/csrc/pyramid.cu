@@ -93,35 +93,87 @@ __device__ __forceinline__ void pyr_up_node(uint8_t *__restrict__ d, uint8_t *__
     d[o] = (uint8_t)max((uint32_t)d[o], m);
 }
 
-// one large ring (ring 2 is a quarter of the node grid): blockDim (32, 8) tiles of nodes; a thread takes the
-// same node of PYR_ZPT planes with all their loads in flight together
-constexpr int PYR_ZPT = 8;
+// 8 / 4 bytes at any alignment from aligned 32-bit words (reads up to 3 bytes past the range: the planes
+// are followed by other planes of the same workspace)
+__device__ __forceinline__ uint2 ld8_any(const uint8_t *p)
+{
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)3);
+    const int sh = 8 * (int)(reinterpret_cast<uintptr_t>(p) & 3);
+    const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+    return make_uint2(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh));
+}
+// per-byte maximum of two words whose bytes are all below 128 (plane numbers are at most 32): the borrow-free
+// subtraction (a | 0x80..) - b leaves bit 7 of a byte set where a >= b.  (The __vmaxu4 intrinsic is emulated
+// on this architecture and several times longer.)
+__device__ __forceinline__ uint32_t bmax4(uint32_t a, uint32_t b)
+{
+    const uint32_t ge = (((a | 0x80808080u) - b) >> 7) & 0x01010101u;
+    const uint32_t m = ge * 0xffu;  // 0xff in the bytes where a >= b
+    return (a & m) | (b & ~m);
+}
+__device__ __forceinline__ uint32_t ld4_any(const uint8_t *p)
+{
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)3);
+    const int sh = 8 * (int)(reinterpret_cast<uintptr_t>(p) & 3);
+    return __funnelshift_r(w[0], w[1], sh);
+}
+
+// one large ring (ring 2 is a quarter of the node grid): blockDim (32, 8); a thread takes four consecutive
+// nodes of a row -- their children are 8 consecutive bytes in each of two rows -- in PYR_ZPT planes with all
+// loads in flight together; byte-wise maxima with the SIMD video instructions
+constexpr int PYR_ZPT = 4;
 __global__ void __launch_bounds__(256) pyr_ring_kernel(int NH, int NW, int RH, int RW, int IH, int IW, int nz,
                                                        uint8_t *__restrict__ dp, uint8_t *__restrict__ lp)
 {
-    const int j = blockIdx.x * 32 + threadIdx.x, i = blockIdx.y * 8 + threadIdx.y;
-    if (i >= RH || j >= RW || (i < IH && j < IW)) return;  // outside / deeper ring (or the self-referential node (0,0))
-    const size_t plane = (size_t)NH * NW, o = (size_t)i * NW + j;
-    const bool r1 = 2 * i + 1 < NH, c1 = 2 * j + 1 < NW;  // 2i < NH and 2j < NW hold for every ring node
-    const size_t c00 = (size_t)(2 * i) * NW + 2 * j;
+    const int j0 = (blockIdx.x * 32 + threadIdx.x) * 4, i = blockIdx.y * 8 + threadIdx.y;
+    if (i >= RH || j0 >= RW) return;
+    // nodes of the quad that belong to this ring: inside [0,RW), outside the deeper rings (and (0,0))
+    uint32_t member = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+        if (j0 + q < RW && !(i < IH && j0 + q < IW)) member |= 1u << q;
+    if (!member) return;
+    const size_t plane = (size_t)NH * NW, o = (size_t)i * NW + j0;
+    const bool r1 = 2 * i + 1 < NH;  // 2i < NH holds for every ring node
+    const size_t c00 = (size_t)(2 * i) * NW + 2 * j0;
+    // child columns 2 j0 .. 2 j0 + 7 that exist
+    const int ncol = min(8, NW - 2 * j0);
+    const uint32_t mlo = ncol >= 4 ? 0xffffffffu : (0xffffffffu >> (8 * (4 - ncol)));
+    const uint32_t mhi = ncol >= 8 ? 0xffffffffu : (ncol <= 4 ? 0u : (0xffffffffu >> (8 * (8 - ncol))));
     for (int z0 = blockIdx.z * PYR_ZPT; z0 < nz; z0 += gridDim.z * PYR_ZPT) {
-        uint32_t own[PYR_ZPT], m[PYR_ZPT];
+        uint2 a[PYR_ZPT], b[PYR_ZPT];
+        uint32_t own[PYR_ZPT];
 #pragma unroll
         for (int q = 0; q < PYR_ZPT; ++q) {
-            own[q] = m[q] = 0;
+            a[q] = b[q] = make_uint2(0u, 0u);
+            own[q] = 0;
             if (z0 + q < nz) {
                 const uint8_t *d = dp + (size_t)(z0 + q) * plane;
-                own[q] = d[o];
-                uint32_t a = d[c00], b = c1 ? d[c00 + 1] : 0u;
-                uint32_t c = r1 ? d[c00 + NW] : 0u, e = (r1 && c1) ? d[c00 + NW + 1] : 0u;
-                m[q] = max(max(a, b), max(c, e));
+                a[q] = ld8_any(d + c00);
+                if (r1) b[q] = ld8_any(d + c00 + NW);
+                own[q] = ld4_any(d + o);
             }
         }
 #pragma unroll
         for (int q = 0; q < PYR_ZPT; ++q) {
             if (z0 + q < nz) {
-                lp[(size_t)(z0 + q) * plane + o] = (uint8_t)m[q];
-                dp[(size_t)(z0 + q) * plane + o] = (uint8_t)max(own[q], m[q]);
+                const uint32_t lo = bmax4(a[q].x, b[q].x) & mlo, hi = bmax4(a[q].y, b[q].y) & mhi;
+                const uint32_t tl = bmax4(lo, lo >> 8), th = bmax4(hi, hi >> 8);  // bytes 0, 2: node maxima
+                const uint32_t m4 = __byte_perm(tl, th, 0x6420);
+                const uint32_t d4 = bmax4(own[q], m4);
+                uint8_t *lq = lp + (size_t)(z0 + q) * plane + o, *dq = dp + (size_t)(z0 + q) * plane + o;
+                if (member == 0xfu && (reinterpret_cast<uintptr_t>(lq) & 3) == 0) {
+                    *reinterpret_cast<uint32_t *>(lq) = m4;
+                    *reinterpret_cast<uint32_t *>(dq) = d4;
+                } else {
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        if (member & (1u << t)) {
+                            lq[t] = (uint8_t)(m4 >> (8 * t));
+                            dq[t] = (uint8_t)(d4 >> (8 * t));
+                        }
+                    }
+                }
             }
         }
     }
@@ -247,7 +299,7 @@ int launch_pyramid(spihtb_ctx *ctx, const int32_t *coeffs, int B, int C, int H, 
             if (RH <= 1 && RW <= 1) break;
             if (t > 2 && (long long)RH * RW <= 65536) break;
             const int IH = (int)((NH + 2 * s - 1) / (2 * s)), IW = (int)((NW + 2 * s - 1) / (2 * s));
-            const dim3 grid((RW + 31) / 32, (RH + 7) / 8, std::min((nz + PYR_ZPT - 1) / PYR_ZPT, 65535));
+            const dim3 grid((RW + 127) / 128, (RH + 7) / 8, std::min((nz + PYR_ZPT - 1) / PYR_ZPT, 65535));
             pyr_ring_kernel<<<grid, dim3(32, 8), 0, st>>>(NH, NW, RH, RW, IH, IW, nz, dp, lp);
             ctx->launches++;
         }
