@@ -113,6 +113,56 @@ def _to_device_pixels(image):
     return torch.from_numpy(np.ascontiguousarray(a)).cuda()
 
 
+_PIPE_CHUNK = 32   # images per host->device copy in the pipelined host path
+
+
+def _encode_host_pipelined(images, g, spiht_settings, budget, level):
+    """Host pixels in, host bytes out, for a large batch: the batch goes to the device in chunks on a copy
+    stream (two device buffers) while the previous chunk is transformed and coded on the current stream, so
+    the PCIe transfer -- by far the longest part of an end-to-end encode -- hides everything else.  Pinned
+    host memory gives a truly asynchronous copy; pageable memory still works (the copy then blocks)."""
+    from . import batch
+    torch = _torch()
+    t = images if isinstance(images, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(images))
+    if t.dtype not in (torch.float32, torch.float64):
+        t = t.to(torch.float64)
+    t = t.contiguous()
+    B, c, h, w = t.shape
+    dev = torch.device("cuda", torch.cuda.current_device())
+    n = _PIPE_CHUNK
+    stride = batch.stream_stride(budget, c, g)
+    bufs = [torch.empty((n, c, h, w), dtype=t.dtype, device=dev) for _ in range(2)]
+    coeffs = torch.empty((n, c, g.enc_h, g.enc_w), dtype=torch.int32, device=dev)
+    streams = torch.empty((B, stride), dtype=torch.uint8, device=dev)
+    main = torch.cuda.current_stream(dev)
+    copy = torch.cuda.Stream(dev)
+    copy.wait_stream(main)
+    done = [None, None]   # per device buffer: event after the chunk that last read it
+    parts = []
+    for i, lo in enumerate(range(0, B, n)):
+        hi = min(B, lo + n)
+        buf = bufs[i & 1][:hi - lo]
+        with torch.cuda.stream(copy):
+            if done[i & 1] is not None:
+                copy.wait_event(done[i & 1])
+            buf.copy_(t[lo:hi], non_blocking=True)
+            ready = torch.cuda.Event()
+            ready.record(copy)
+        main.wait_event(ready)
+        _, nbits, max_n, status, _ = batch.encode_images(buf, g, spiht_settings, budget, out_stride=stride,
+                                                         coeffs=coeffs[:hi - lo], out=streams[lo:hi])
+        parts.append((nbits, max_n, status))
+        done[i & 1] = torch.cuda.Event()
+        done[i & 1].record(main)
+    nbits_h = torch.cat([p[0] for p in parts]).cpu().numpy()
+    max_n_h = torch.cat([p[1] for p in parts]).cpu().numpy()
+    if int(torch.cat([p[2] for p in parts]).max().item()) != 0:
+        raise _lib.SpihtB200Error(_lib.ECAP, "bitstream row too small")
+    nbytes = (nbits_h + 7) // 8
+    rows = streams[:, :int(nbytes.max())].cpu().numpy()
+    return [EncodingResult(rows[b, :int(nbytes[b])].tobytes(), h, w, c, int(max_n_h[b]), level) for b in range(B)]
+
+
 def encode_image(image: np.ndarray, spiht_settings: SpihtSettings = SpihtSettings(), level: Optional[int] = None,
                  max_bits: Optional[int] = None):
     """spiht_wrapper.py:142-189.  Takes the DWT of the image, quantises the
@@ -151,12 +201,15 @@ def encode_images(images, spiht_settings: SpihtSettings = SpihtSettings(), level
     B, c, h, w = images.shape
     _norm_color(spiht_settings.color_model)
     g = _geom(h, w, spiht_settings, level)
-    pixels = _to_device_pixels(images)
-
     if max_bits is None:
         max_bits = _VERY_LARGE
     budget = int(max_bits)
     bound = 8 * int(_lib.lib().spihtb_stream_bound(c, g.enc_h, g.enc_w, g.ll_h, g.ll_w))
+    host_side = not (isinstance(images, torch.Tensor) and images.is_cuda)
+    if host_side and 0 < budget <= bound and B >= 2 * _PIPE_CHUNK:
+        return _encode_host_pipelined(images, g, spiht_settings, budget, level)
+    pixels = _to_device_pixels(images)
+
     if budget == 0 or budget > bound:
         # untruncated: run the transform first, size the rows from the largest coefficient
         coeffs = batch.forward(pixels, g, spiht_settings)
