@@ -68,7 +68,11 @@ __global__ void __launch_bounds__(IV_WARPS * 32) dwt_inv_level_kernel(const InvK
     constexpr int F = Wav<WID>::F;
     constexpr int HF = F / 2;
     constexpr int NOUT = 32 - (HF - 1);
-    constexpr int PD = (HF % 3 == 0) ? 3 : HF;  // prefetch distance in rows; divides HF
+    // prefetch distance in rows and unroll of the streaming loop (a multiple of HF: static window and queue slots)
+    // (6 rows ahead pay off on the latency-bound coarse levels; the float32 output level is issue-bound: 3)
+    constexpr int PD = HF == 3 ? (sizeof(Tout) == 8 ? 6 : 3) : HF;
+    constexpr int UN = PD;
+    static_assert(UN % HF == 0 && UN % PD == 0, "static slots");
     constexpr unsigned FULL = 0xffffffffu;
     long long task = (long long)blockIdx.x * IV_WARPS + (threadIdx.x >> 5);
     if (task >= p.ntasks) return;
@@ -181,12 +185,12 @@ __global__ void __launch_bounds__(IV_WARPS * 32) dwt_inv_level_kernel(const InvK
     Tout *dst = static_cast<Tout *>(p.dst) + (size_t)z * p.oh * p.ow + (size_t)(2 * p0) * p.ow + 2 * q_out;
     const int ow = p.ow;
 
-    const int niter = (npair + HF - 1) / HF;
+    const int niter = (npair + UN - 1) / UN;
     for (int it = 0; it < niter; ++it) {
 #pragma unroll
-        for (int u0 = 0; u0 < HF; ++u0) {
-            const int i = it * HF + u0;  // output row pair of the chunk
-            const int j = u0 + HF - 1;   // stream row completing it (up to a multiple of HF)
+        for (int u0 = 0; u0 < UN; ++u0) {
+            const int i = it * UN + u0;  // output row pair of the chunk (pairs past npair are computed and dropped)
+            const int j = u0 + HF - 1;   // stream row completing it (up to a multiple of UN)
             h_synth(q[j % PD], j % HF);
             load_row(jn++, q[j % PD]);
             // axis -2: stream row (j - u) holds coefficient row p + S/2 - u
@@ -271,7 +275,7 @@ static int launch_inv_level(spihtb_ctx *ctx, InvK k, int nz, bool out_f32)
 {
     constexpr int F = Wav<WID>::F;
     constexpr int NOUT = 32 - (F / 2 - 1);
-    constexpr int RHMAX = 32;  // output row pairs per chunk
+    constexpr int RHMAX = 36;  // output row pairs per chunk (a multiple of the bior2.2 loop unroll)
     const int opw = k.ow / 2, oph = k.oh / 2;
     k.tiles_x = (opw + NOUT - 1) / NOUT;
     k.tiles_y = (oph + RHMAX - 1) / RHMAX;
