@@ -54,6 +54,9 @@ extern "C" {
 /* pixel dtypes */
 #define SPIHTB_F32 0
 #define SPIHTB_F64 1
+/* forward direction only: uint8 pixels as stored on disk, scaled like the reference's loader
+ * (spiht/utils.py:12-20 imload: im / 255 in float64) before the transform */
+#define SPIHTB_U8 2
 
 #define SPIHTB_MAX_LEVELS 24
 
@@ -138,7 +141,7 @@ int spihtb_decode_coeffs(spihtb_ctx *ctx, const uint8_t *dev_in, uint64_t in_str
 /* ---- transform stages, DEVICE buffers ----------------------------------- */
 /* spiht_wrapper.py:158-172: optional RGB->colour (color_models.py:6-13), pywt.wavedec2 (:163),
  * pywt.coeffs_to_array (:165), per-channel scale (:167-170), quantize (:9-11, truncation toward
- * zero of (m_c * x) * q).  ch_scales: host double[C] or NULL.  pixel_dtype: SPIHTB_F32/F64.
+ * zero of (m_c * x) * q).  ch_scales: host double[C] or NULL.  pixel_dtype: SPIHTB_F32/F64/U8.
  * dev_coeffs int32 [B][C][enc_h][enc_w]. */
 int spihtb_forward(spihtb_ctx *ctx, const void *dev_pixels, int32_t pixel_dtype, int32_t B, int32_t C,
                    const spihtb_geom *geom, int32_t color_model, const double *ch_scales, double q,

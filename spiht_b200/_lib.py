@@ -15,7 +15,7 @@ MAX_LEVELS = 24
 WAVELET_IDS = {"bior2.2": 0, "bior4.4": 1, "bior6.8": 2}
 MODE_IDS = {"reflect": 0, "symmetric": 1, "periodization": 2}
 COLOR_NONE, COLOR_IPT = 0, 1
-F32, F64 = 0, 1
+F32, F64, U8 = 0, 1, 2   # U8: forward direction only (pixels / 255 in float64, as utils.imload)
 
 
 class Geom(ctypes.Structure):

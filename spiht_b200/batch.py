@@ -36,12 +36,14 @@ def _settings_args(settings, C):
     return color_id, sc, float(settings.quantization_scale)
 
 
-def _pixel_dtype(t):
+def _pixel_dtype(t, allow_u8=False):
     if t.dtype == torch.float32:
         return _lib.F32
     if t.dtype == torch.float64:
         return _lib.F64
-    raise TypeError(f"pixels must be float32 or float64, got {t.dtype}")
+    if allow_u8 and t.dtype == torch.uint8:
+        return _lib.U8   # image bytes as stored on disk: scaled by 1 / 255 in float64 like utils.imload
+    raise TypeError(f"pixels must be float32 or float64{' or uint8' if allow_u8 else ''}, got {t.dtype}")
 
 
 def _check_cuda(t, name):
@@ -67,7 +69,7 @@ def forward(pixels, geom, settings):
     ctx = _ctx_for(pixels)
     color_id, sc, q = _settings_args(settings, C)
     coeffs = torch.empty((B, C, geom.enc_h, geom.enc_w), dtype=torch.int32, device=pixels.device)
-    _lib.check(_lib.lib().spihtb_forward(ctx.handle, _ptr(pixels), _pixel_dtype(pixels), B, C, ctypes.byref(geom),
+    _lib.check(_lib.lib().spihtb_forward(ctx.handle, _ptr(pixels), _pixel_dtype(pixels, True), B, C, ctypes.byref(geom),
                                          color_id, sc, q, _ptr(coeffs)))
     return coeffs
 
@@ -157,7 +159,7 @@ def encode_images(pixels, geom, settings, max_bits, out_stride=None, coeffs=None
     nbits = torch.empty((B,), dtype=torch.int64, device=pixels.device)
     max_n = torch.empty((B,), dtype=torch.int32, device=pixels.device)
     status = torch.empty((B,), dtype=torch.int32, device=pixels.device)
-    _lib.check(_lib.lib().spihtb_encode_images(ctx.handle, _ptr(pixels), _pixel_dtype(pixels), B, C,
+    _lib.check(_lib.lib().spihtb_encode_images(ctx.handle, _ptr(pixels), _pixel_dtype(pixels, True), B, C,
                                                ctypes.byref(geom), color_id, sc, q, scalar, _ptr(per), _ptr(coeffs),
                                                _ptr(out), out_stride, _ptr(nbits), _ptr(max_n), _ptr(status)))
     return out, nbits, max_n, status, coeffs

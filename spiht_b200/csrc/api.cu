@@ -100,7 +100,7 @@ static int fill_xform(XformArgs *x, int B, int C, const spihtb_geom *g, int colo
         set_error("unknown colour model id %d", color);
         return SPIHTB_EINVAL;
     }
-    if (pixel_dtype != SPIHTB_F32 && pixel_dtype != SPIHTB_F64) {
+    if (pixel_dtype != SPIHTB_F32 && pixel_dtype != SPIHTB_F64 && pixel_dtype != SPIHTB_U8) {
         set_error("unknown pixel dtype %d", pixel_dtype);
         return SPIHTB_EINVAL;
     }
@@ -252,7 +252,7 @@ int spihtb_destroy(spihtb_ctx *ctx)
     if (!ctx) return SPIHTB_OK;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    DevBuf *bufs[] = {&ctx->pyr, &ctx->lists, &ctx->misc, &ctx->tmpa, &ctx->tmpb, &ctx->io, &ctx->io2, &ctx->fix};
+    DevBuf *bufs[] = {&ctx->pyr, &ctx->lists, &ctx->misc, &ctx->tmpa, &ctx->tmpb, &ctx->io, &ctx->io2, &ctx->fix, &ctx->u8lut};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
     for (int s = 0; s < SPIHTB_NSTAGES; ++s)

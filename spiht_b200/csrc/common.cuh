@@ -52,6 +52,7 @@ struct spihtb_ctx {
     spihtb::DevBuf tmpa, tmpb;  // DWT approximation ping-pong (float64)
     spihtb::DevBuf io;       // staging for the host-pointer entry points
     spihtb::DevBuf io2;
+    spihtb::DevBuf u8lut;    // k / 255.0 for uint8 pixels
     spihtb::DevBuf fix;      // rectangles of the pyramid fix-up pass (forward transform with fused base pass)
     std::vector<int32_t> fix_host;  // their host copy: [key (32 ints)] [nrect, total] [rects] [prefix]
     std::vector<uint8_t> host_out;  // spihtb_encode result

@@ -40,6 +40,7 @@ struct FwdK {
     long long ntasks;       // nz * tiles_y * tiles_x
     double scale[8];
     double q;
+    const double *u8lut;    // device table k / 255.0, k = 0 .. 255 (uint8 pixels only)
     // fused pyramid base pass (PYR kernels): dp planes [nz][NH][NW] and the per-image maximum magnitude
     uint8_t *dp;
     uint32_t *maxabs;
@@ -73,7 +74,11 @@ template <typename Tin, int NC>
 __device__ __forceinline__ void lds_frag(uint32_t saddr, Tin (&v)[NC])
 {
     constexpr int BYTES = NC * (int)sizeof(Tin);
-    if constexpr (BYTES == 8) {
+    if constexpr (BYTES == 4) {
+        uint32_t r;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(saddr));
+        memcpy(v, &r, 4);
+    } else if constexpr (BYTES == 8) {
         uint2 r;
         asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(saddr));
         memcpy(v, &r, 8);
@@ -139,6 +144,20 @@ __device__ __forceinline__ void cell_row(CellTrack &ct, uint32_t cm, bool odd, b
     ct.off += odd ? NW : 0;
 }
 
+// pixel -> float64.  uint8 pixels are images as stored on disk; the reference's loader (spiht/utils.py:12-20,
+// imload) scales them with `im / 255` in float64: the 256 quotients come from a table the host fills with the
+// same IEEE division (exact, and no division in the streaming loop).
+template <typename Tin>
+__device__ __forceinline__ double px_f64(Tin v, const double *)
+{
+    return (double)v;
+}
+template <>
+__device__ __forceinline__ double px_f64<uint8_t>(uint8_t v, const double *lut)
+{
+    return lut[v];
+}
+
 template <int WID>
 struct FwdCfg {
     static constexpr int F = Wav<WID>::F;
@@ -169,7 +188,8 @@ struct FwdCfg {
 // (and whose rows are vector-aligned) copies its fragment as one vector; the halo
 // lanes of the edge strips go through the boundary map one element at a time.
 template <typename Tin, int WID, int NP, bool UNIT_M, bool LAST, bool PYR>
-__device__ __forceinline__ void dwt_fwd_task(const FwdK &p, int tx, int ty, int z, uint32_t ring, bool aligned)
+__device__ __forceinline__ void dwt_fwd_task(const FwdK &p, int tx, int ty, int z, uint32_t ring, bool aligned,
+                                             const double *lut)
 {
     constexpr int F = Wav<WID>::F;
     constexpr int HF = F / 2;
@@ -178,8 +198,14 @@ __device__ __forceinline__ void dwt_fwd_task(const FwdK &p, int tx, int ty, int 
     constexpr int HL = (HF - 1) / NP;           // lanes that only feed their neighbours
     constexpr int NOUT = 32 * NP - (HF - 1);
     constexpr int DEPTH = FwdCfg<WID>::DEPTH;
-    constexpr int FRAG = NC * (int)sizeof(Tin);  // bytes of one lane's row fragment
-    constexpr int SLOT = 2 * 32 * FRAG;          // one row pair of the warp
+    // uint8 pixels: cp.async cannot copy single bytes, so a lane that goes element by element (boundary map)
+    // copies the aligned 32-bit word around each pixel into a 4-byte slot and picks the byte when it reads the
+    // row back; rows are 4-byte aligned (the launcher converts other widths to float64 first)
+    constexpr bool U8 = sizeof(Tin) == 1;
+    constexpr int ES = U8 ? 4 : (int)sizeof(Tin);   // ring bytes per element
+    constexpr int VFRAG = NC * (int)sizeof(Tin);    // bytes a lane copies as one vector
+    constexpr int FRAG = NC * ES;                   // ring bytes of one lane's row fragment
+    constexpr int SLOT = 2 * 32 * FRAG;             // one row pair of the warp
     constexpr unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const int src_h = p.src_h, src_w = p.src_w, mode = p.mode;
@@ -191,7 +217,7 @@ __device__ __forceinline__ void dwt_fwd_task(const FwdK &p, int tx, int ty, int 
     const int gr0 = 2 * r0 - (F - 2) + sft;    // first input row of the chunk's window
 
     const Tin *plane = static_cast<const Tin *>(p.src) + (size_t)z * src_h * src_w;
-    const bool lane_vec = aligned && gc >= 0 && gc + NC <= src_w;
+    const bool lane_vec = aligned && VFRAG >= 4 && gc >= 0 && gc + NC <= src_w;
     const bool warp_vec = __all_sync(0xffffffffu, lane_vec);
     int col[NC];
 #pragma unroll
@@ -209,24 +235,25 @@ __device__ __forceinline__ void dwt_fwd_task(const FwdK &p, int tx, int ty, int 
             pb = plane + (size_t)ext_index_slow(gr + 1, src_h, mode) * src_w;
         }
         const uint32_t sa = my + slot_off, sb = sa + 32 * FRAG;
-        constexpr int VB = FRAG >= 16 ? 16 : 8;
+        constexpr int VB = VFRAG >= 16 ? 16 : (VFRAG >= 8 ? 8 : 4);
         if (warp_vec) {  // interior strips: every lane copies its fragment as vectors (no per-lane predicates)
 #pragma unroll
-            for (int o = 0; o < FRAG; o += VB) {
+            for (int o = 0; o < VFRAG; o += VB) {
                 cp_async<VB>(sa + o, reinterpret_cast<const char *>(pa + gc) + o);
                 cp_async<VB>(sb + o, reinterpret_cast<const char *>(pb + gc) + o);
             }
         } else if (lane_vec) {
 #pragma unroll
-            for (int o = 0; o < FRAG; o += VB) {
+            for (int o = 0; o < VFRAG; o += VB) {
                 cp_async<VB>(sa + o, reinterpret_cast<const char *>(pa + gc) + o);
                 cp_async<VB>(sb + o, reinterpret_cast<const char *>(pb + gc) + o);
             }
         } else {
 #pragma unroll
             for (int c = 0; c < NC; ++c) {
-                cp_async<(int)sizeof(Tin)>(sa + c * (int)sizeof(Tin), pa + col[c]);
-                cp_async<(int)sizeof(Tin)>(sb + c * (int)sizeof(Tin), pb + col[c]);
+                const int cc = U8 ? (col[c] & ~3) : col[c];
+                cp_async<ES>(sa + c * ES, pa + cc);
+                cp_async<ES>(sb + c * ES, pb + cc);
             }
         }
         cp_async_commit();
@@ -237,8 +264,30 @@ __device__ __forceinline__ void dwt_fwd_task(const FwdK &p, int tx, int ty, int 
     auto take_pair = [&](uint32_t slot_off, Tin (&a)[NC], Tin (&b)[NC]) {
         cp_async_wait<DEPTH - 1>();
         const uint32_t sa = my + slot_off;
-        lds_frag<Tin, NC>(sa, a);
-        lds_frag<Tin, NC>(sa + 32 * FRAG, b);
+        if constexpr (U8) {
+            if (lane_vec) {  // NP == 2: the lane's four pixels are one word
+                uint32_t wa, wb;
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(wa) : "r"(sa));
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(wb) : "r"(sa + 32 * FRAG));
+#pragma unroll
+                for (int c = 0; c < NC; ++c) {
+                    a[c] = (Tin)((wa >> (8 * (c & 3))) & 0xffu);
+                    b[c] = (Tin)((wb >> (8 * (c & 3))) & 0xffu);
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < NC; ++c) {
+                    uint32_t wa, wb;
+                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(wa) : "r"(sa + c * ES));
+                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(wb) : "r"(sa + 32 * FRAG + c * ES));
+                    a[c] = (Tin)((wa >> (8 * (col[c] & 3))) & 0xffu);
+                    b[c] = (Tin)((wb >> (8 * (col[c] & 3))) & 0xffu);
+                }
+            }
+        } else {
+            lds_frag<Tin, NC>(sa, a);
+            lds_frag<Tin, NC>(sa + 32 * FRAG, b);
+        }
     };
 
     // row pair j of the chunk (local rows 2j, 2j+1) goes through ring slot j % DEPTH; pairs 0 .. HF-2
@@ -254,8 +303,8 @@ __device__ __forceinline__ void dwt_fwd_task(const FwdK &p, int tx, int ty, int 
         take_pair(j * SLOT, a, b);
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
-            w[2 * j][c] = (double)a[c];
-            w[2 * j + 1][c] = (double)b[c];
+            w[2 * j][c] = px_f64<Tin>(a[c], lut);
+            w[2 * j + 1][c] = px_f64<Tin>(b[c], lut);
         }
         fetch_pair(j * SLOT);  // pair j + DEPTH
     }
@@ -330,8 +379,8 @@ __device__ __forceinline__ void dwt_fwd_task(const FwdK &p, int tx, int ty, int 
                 take_pair(slot_off, a, b);
 #pragma unroll
                 for (int c = 0; c < NC; ++c) {
-                    w[(2 * u + F - 2) % F][c] = (double)a[c];
-                    w[(2 * u + F - 1) % F][c] = (double)b[c];
+                    w[(2 * u + F - 2) % F][c] = px_f64<Tin>(a[c], lut);
+                    w[(2 * u + F - 1) % F][c] = px_f64<Tin>(b[c], lut);
                 }
             }
             fetch_pair(slot_off);
@@ -478,8 +527,13 @@ __global__ void __launch_bounds__(FW_WARPS * 32, FwdCfg<WID>::MINB) dwt_fwd_leve
     constexpr int F = Wav<WID>::F;
     constexpr int NOUT = 32 * NP - (F / 2 - 1);
     constexpr int DEPTH = FwdCfg<WID>::DEPTH;
-    constexpr int WARP_RING = DEPTH * 2 * 32 * 2 * NP * (int)sizeof(Tin);
+    constexpr int WARP_RING = DEPTH * 2 * 32 * 2 * NP * (sizeof(Tin) == 1 ? 4 : (int)sizeof(Tin));
     __shared__ __align__(16) unsigned char s_ring[FW_WARPS * WARP_RING];
+    __shared__ double s_lut[sizeof(Tin) == 1 ? 256 : 1];  // k / 255 for uint8 pixels
+    if constexpr (sizeof(Tin) == 1) {
+        for (int k = threadIdx.x; k < 256; k += FW_WARPS * 32) s_lut[k] = p.u8lut[k];
+        __syncthreads();
+    }
     const uint32_t ring = (uint32_t)__cvta_generic_to_shared(s_ring) + (threadIdx.x >> 5) * WARP_RING;
     long long task = (long long)blockIdx.x * FW_WARPS + (threadIdx.x >> 5);
     if (task >= p.ntasks) return;
@@ -490,12 +544,12 @@ __global__ void __launch_bounds__(FW_WARPS * 32, FwdCfg<WID>::MINB) dwt_fwd_leve
     // every row fragment of the strip vector-aligned (warp-uniform)
     const int sft = p.mode == SPIHTB_MODE_PERIODIZATION ? (F / 2 - 1) : 0;
     const int gc_first = 2 * (tx * NOUT - (F / 2 - 1)) + sft;
-    constexpr int VB = 2 * NP * (int)sizeof(Tin) >= 16 ? 16 : 8;  // vector bytes
+    constexpr int VB = 2 * NP * (int)sizeof(Tin) >= 16 ? 16 : (2 * NP * (int)sizeof(Tin) >= 8 ? 8 : 4);  // vector bytes
     const long long base = (long long)reinterpret_cast<uintptr_t>(p.src) +
                            (long long)z * p.src_h * p.src_w * (long long)sizeof(Tin);
     const bool aligned = ((size_t)p.src_w * sizeof(Tin)) % VB == 0 &&
                          (base + (long long)gc_first * (long long)sizeof(Tin)) % VB == 0;
-    dwt_fwd_task<Tin, WID, NP, UNIT_M, LAST, PYR>(p, tx, ty, z, ring, aligned);
+    dwt_fwd_task<Tin, WID, NP, UNIT_M, LAST, PYR>(p, tx, ty, z, ring, aligned, s_lut);
 }
 
 // zero the gaps coeffs_to_array leaves between a level's off-diagonal blocks
@@ -532,6 +586,13 @@ __global__ void __launch_bounds__(256) gap_fill_kernel(const __grid_constant__ G
     }
 }
 
+// uint8 pixels whose rows are not 4-byte aligned: imload's im / 255 as a separate pass
+__global__ void __launch_bounds__(256) u8_to_f64_kernel(const uint8_t *__restrict__ src, double *__restrict__ dst, size_t n)
+{
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x)
+        dst[t] = (double)src[t] / 255.0;
+}
+
 // ---- RGB -> IPT (color_models.py:6-13 -> colour.convert(.., 'RGB', 'IPT')) ----
 // linear sRGB -> XYZ (4-digit IEC matrix) -> LMS -> sign(x)|x|^0.43 -> IPT, float64.
 __device__ __forceinline__ double spow(double a, double e) { return a == 0.0 ? 0.0 : copysign(pow(fabs(a), e), a); }
@@ -544,7 +605,12 @@ __global__ void __launch_bounds__(256) rgb_to_ipt_kernel(const Tin *__restrict__
     for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
         const size_t b = t / plane, o = t - b * plane;
         const Tin *s = src + b * 3 * plane + o;
-        const double R = (double)s[0], G = (double)s[plane], B = (double)s[2 * plane];
+        double R = (double)s[0], G = (double)s[plane], B = (double)s[2 * plane];
+        if (sizeof(Tin) == 1) {  // uint8 pixels: imload's im / 255 (IEEE division, as numpy's)
+            R /= 255.0;
+            G /= 255.0;
+            B /= 255.0;
+        }
         const double X = 0.4124 * R + 0.3576 * G + 0.1805 * B;
         const double Y = 0.2126 * R + 0.7152 * G + 0.0722 * B;
         const double Z = 0.0193 * R + 0.1192 * G + 0.9505 * B;
@@ -717,8 +783,31 @@ int launch_forward(spihtb_ctx *ctx, const void *pixels, const XformArgs &x, int3
     rc = ctx->ensure(ctx->tmpb, ll2 + 256);
     if (rc) return rc;
 
-    const void *src = pixels;
-    bool src_is_f64 = x.pixel_dtype == SPIHTB_F64;
+    const double *u8lut = nullptr;
+    const void *conv = nullptr;  // uint8 pixels converted to float64 up front (unaligned rows)
+    if (x.pixel_dtype == SPIHTB_U8 && x.color != SPIHTB_COLOR_IPT &&
+        (g.w % 4 != 0 || (reinterpret_cast<uintptr_t>(pixels) & 3) != 0)) {
+        const size_t n = (size_t)nz * g.h * g.w;
+        rc = ctx->ensure(ctx->io2, n * sizeof(double) + 256);
+        if (rc) return rc;
+        const unsigned nb = (unsigned)std::min<size_t>((n + 255) / 256, (size_t)ctx->sm_count * 32);
+        u8_to_f64_kernel<<<nb, 256, 0, ctx->stream>>>(static_cast<const uint8_t *>(pixels),
+                                                      static_cast<double *>(ctx->io2.p), n);
+        ctx->launches++;
+        conv = ctx->io2.p;
+    } else if (x.pixel_dtype == SPIHTB_U8 && x.color != SPIHTB_COLOR_IPT) {
+        if (!ctx->u8lut.p) {
+            rc = ctx->ensure(ctx->u8lut, 256 * sizeof(double));
+            if (rc) return rc;
+            double h[256];
+            for (int k = 0; k < 256; ++k) h[k] = (double)k / 255.0;  // utils.py:19  im / 255
+            SPIHTB_CUDA_CHECK(cudaMemcpyAsync(ctx->u8lut.p, h, sizeof(h), cudaMemcpyHostToDevice, ctx->stream));
+            SPIHTB_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));  // h is on the stack
+        }
+        u8lut = static_cast<const double *>(ctx->u8lut.p);
+    }
+    const void *src = conv ? conv : pixels;
+    bool src_is_f64 = x.pixel_dtype == SPIHTB_F64 || conv;
     if (x.color == SPIHTB_COLOR_IPT) {
         if (x.C != 3) {
             set_error("IPT colour model needs 3 channels, got %d", x.C);
@@ -731,6 +820,9 @@ int launch_forward(spihtb_ctx *ctx, const void *pixels, const XformArgs &x, int3
         if (src_is_f64)
             rgb_to_ipt_kernel<double><<<nb, 256, 0, ctx->stream>>>(static_cast<const double *>(pixels),
                                                                    static_cast<double *>(ctx->io2.p), plane, x.B);
+        else if (x.pixel_dtype == SPIHTB_U8)
+            rgb_to_ipt_kernel<uint8_t><<<nb, 256, 0, ctx->stream>>>(static_cast<const uint8_t *>(pixels),
+                                                                    static_cast<double *>(ctx->io2.p), plane, x.B);
         else
             rgb_to_ipt_kernel<float><<<nb, 256, 0, ctx->stream>>>(static_cast<const float *>(pixels),
                                                                   static_cast<double *>(ctx->io2.p), plane, x.B);
@@ -743,8 +835,9 @@ int launch_forward(spihtb_ctx *ctx, const void *pixels, const XformArgs &x, int3
     // so that a group's float64 approximation planes stay in L2 for the next level, was measured slower
     // on B200: the short launches leave the SMs idle at every kernel boundary.)
     auto run_level = [&](int l, int z0, int nzg) -> int {
-        const bool in_f64 = l > 0 || x.pixel_dtype == SPIHTB_F64 || x.color == SPIHTB_COLOR_IPT;
-        const size_t esz = in_f64 ? sizeof(double) : sizeof(float);
+        const bool in_f64 = l > 0 || x.pixel_dtype == SPIHTB_F64 || x.color == SPIHTB_COLOR_IPT || conv;
+        const bool in_u8 = !in_f64 && x.pixel_dtype == SPIHTB_U8;
+        const size_t esz = in_f64 ? sizeof(double) : (in_u8 ? 1 : sizeof(float));
         FwdK k;
         const void *lsrc = l == 0 ? src : (((l - 1) & 1) ? ctx->tmpb.p : ctx->tmpa.p);
         k.src_h = g.in_h[l];
@@ -770,8 +863,10 @@ int launch_forward(spihtb_ctx *ctx, const void *pixels, const XformArgs &x, int3
         k.NW = g.enc_w / 2;
         const int st = l == 0 ? 0 : 1;
         ctx->stage_begin(st);
+        k.u8lut = u8lut;
         const int r = in_f64 ? launch_level_w<double>(ctx, g.wavelet, k, nzg)
-                             : launch_level_w<float>(ctx, g.wavelet, k, nzg);
+                             : (in_u8 ? launch_level_w<uint8_t>(ctx, g.wavelet, k, nzg)
+                                      : launch_level_w<float>(ctx, g.wavelet, k, nzg));
         ctx->stage_end(st);
         return r;
     };

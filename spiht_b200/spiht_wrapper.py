@@ -100,15 +100,17 @@ def _torch():
 
 
 def _to_device_pixels(image):
-    """numpy / torch image batch -> contiguous CUDA tensor, float32 kept, everything else float64"""
+    """numpy / torch image batch -> contiguous CUDA tensor; float32 and uint8 kept, everything else float64.
+    uint8 is image data as stored on disk: the library scales it by 1 / 255 in float64, exactly what the
+    reference's loader does (utils.py:12-20), so encode_image(raw_uint8) == encode_image(imload-style floats)."""
     torch = _torch()
     if isinstance(image, torch.Tensor):
         t = image
-        if t.dtype not in (torch.float32, torch.float64):
+        if t.dtype not in (torch.float32, torch.float64, torch.uint8):
             t = t.to(torch.float64)
         return t.cuda().contiguous()
     a = np.asarray(image)
-    if a.dtype != np.float32:
+    if a.dtype not in (np.float32, np.uint8):
         a = a.astype(np.float64)
     return torch.from_numpy(np.ascontiguousarray(a)).cuda()
 
@@ -124,7 +126,7 @@ def _encode_host_pipelined(images, g, spiht_settings, budget, level):
     from . import batch
     torch = _torch()
     t = images if isinstance(images, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(images))
-    if t.dtype not in (torch.float32, torch.float64):
+    if t.dtype not in (torch.float32, torch.float64, torch.uint8):
         t = t.to(torch.float64)
     t = t.contiguous()
     B, c, h, w = t.shape

@@ -237,3 +237,31 @@ def test_host_batch_pipelined_equals_device_batch(torch_cuda):
         assert a == b
     # numpy input (pageable memory) takes the same path
     assert spiht.encode_images(imgs[:B], st, max_bits=mb) == oneshot
+
+
+@pytest.mark.parametrize("shape,kw", [
+    ((3, 64, 96), dict()),
+    ((3, 128, 256), dict(mode="periodization")),
+    ((1, 70, 68), dict()),                                        # edge strips and boundary rows only
+    ((3, 67, 131), dict()),                                       # rows not 4-byte aligned: converted up front
+    ((2, 128, 96), dict(wavelet="bior4.4", mode="symmetric")),   # one column pair per lane
+    ((1, 320, 320), dict(wavelet="bior6.8")),
+    ((3, 64, 64), dict(quantization_scale=1.0, color_model="IPT", per_channel_quant_scales=[50.0, 15.0, 15.0])),
+])
+def test_uint8_pixels_equal_imload_floats(torch_cuda, shape, kw):
+    """uint8 pixels go through the library's own 1/255 scaling (utils.py:12-20, imload: im / 255 in float64):
+    coefficient arrays and streams equal those of the float64 image bit for bit"""
+    import spiht_b200 as spiht
+    from spiht_b200 import _lib, batch
+    torch = torch_cuda
+    c, h, w = shape
+    rng = np.random.default_rng(5)
+    u8 = np.clip(np.round(synth_image(c, h, w, 9) * 255 + rng.normal(0, 2, (c, h, w))), 0, 255).astype(np.uint8)
+    f64 = u8 / 255                       # the reference's imload
+    st = spiht.SpihtSettings(**kw)
+    g = _lib.plan(h, w, kw.get("wavelet", "bior2.2"), kw.get("mode", "reflect"), None)
+    ca = batch.forward(torch.from_numpy(u8[None]).cuda(), g, st)
+    cb = batch.forward(torch.from_numpy(f64[None]).cuda(), g, st)
+    assert torch.equal(ca, cb)
+    mb = h * w // 2
+    assert spiht.encode_image(u8, st, max_bits=mb) == spiht.encode_image(f64, st, max_bits=mb)
