@@ -252,7 +252,7 @@ int spihtb_destroy(spihtb_ctx *ctx)
     if (!ctx) return SPIHTB_OK;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    DevBuf *bufs[] = {&ctx->pyr, &ctx->lists, &ctx->misc, &ctx->tmpa, &ctx->tmpb, &ctx->io, &ctx->io2, &ctx->fix, &ctx->u8lut};
+    DevBuf *bufs[] = {&ctx->pyr, &ctx->lists, &ctx->misc, &ctx->tmpa, &ctx->tmpb, &ctx->io, &ctx->io2, &ctx->fix, &ctx->u8lut, &ctx->blk};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
     for (int s = 0; s < SPIHTB_NSTAGES; ++s)
@@ -606,11 +606,35 @@ int spihtb_decode_images(spihtb_ctx *ctx, const uint8_t *dev_in, uint64_t in_str
         set_error("null pointer");
         return SPIHTB_EINVAL;
     }
-    int rc = spihtb_decode_coeffs(ctx, dev_in, in_stride, dev_nbytes, dev_n, B, C, geom->enc_h, geom->enc_w,
-                                  geom->ll_h, geom->ll_w, dev_coeffs_scratch);
+    if (!ctx || !dev_in || !dev_nbytes || !dev_n || !dev_pixels_out || B <= 0) {
+        set_error("null pointer or empty batch");
+        return SPIHTB_EINVAL;
+    }
+    const int c = C, h = geom->enc_h, w = geom->enc_w;
+    int rc = check_coder_geom(c, h, w, geom->ll_h, geom->ll_w);
     if (rc) return rc;
-    return spihtb_inverse(ctx, dev_coeffs_scratch, B, C, geom, color_model, ch_scales, q, dev_pixels_out,
-                          pixel_dtype);
+    XformArgs x;
+    rc = fill_xform(&x, B, C, geom, color_model, ch_scales, q, pixel_dtype);
+    if (rc) return rc;
+    SPIHTB_CUDA_CHECK(cudaSetDevice(ctx->device));
+    // the decoder marks the 64x64 blocks of the array it writes into; the inverse transform skips the detail
+    // bands of tasks with no marked block (at low rates the finest levels hold no coefficient at all)
+    const size_t nblk = (size_t)B * C * ((h + 63) / 64) * ((w + 63) / 64);
+    rc = ctx->ensure(ctx->blk, nblk + 256);
+    if (rc) return rc;
+    SPIHTB_CUDA_CHECK(cudaMemsetAsync(ctx->blk.p, 0, nblk, ctx->stream));
+    DecArgs a;
+    a.in = dev_in;
+    a.in_stride = in_stride;
+    a.nbytes = dev_nbytes;
+    a.n = dev_n;
+    a.B = B; a.C = c; a.H = h; a.W = w; a.ll_h = geom->ll_h; a.ll_w = geom->ll_w;
+    a.out = dev_coeffs_scratch;
+    a.blk = static_cast<uint8_t *>(ctx->blk.p);
+    rc = launch_decode(ctx, a);
+    if (rc) return rc;
+    x.blk = a.blk;
+    return launch_inverse(ctx, dev_coeffs_scratch, x, dev_pixels_out);
 }
 
 }  // extern "C"

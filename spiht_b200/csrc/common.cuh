@@ -53,6 +53,7 @@ struct spihtb_ctx {
     spihtb::DevBuf io;       // staging for the host-pointer entry points
     spihtb::DevBuf io2;
     spihtb::DevBuf u8lut;    // k / 255.0 for uint8 pixels
+    spihtb::DevBuf blk;      // marks of the 64x64 blocks the decoder wrote into (spihtb_decode_images)
     spihtb::DevBuf fix;      // rectangles of the pyramid fix-up pass (forward transform with fused base pass)
     std::vector<int32_t> fix_host;  // their host copy: [key (32 ints)] [nrect, total] [rects] [prefix]
     std::vector<uint8_t> host_out;  // spihtb_encode result

@@ -23,6 +23,7 @@
 // waverec2 drops the approximation's trailing row/column when it is one
 // longer than the detail band (odd sizes); the strips simply never read it.
 #include <algorithm>
+#include <type_traits>
 
 #include "common.cuh"
 #include "kernels.cuh"
@@ -45,6 +46,11 @@ struct InvK {
     long long ntasks;
     double rscale[8];  // 1 / m_c
     double rq;         // 1 / q
+    // optional marks of the 64x64 blocks of the coefficient array that hold a non-zero coefficient
+    // ([nz][BH][BW] bytes, written by the SPIHT decoder): a task none of whose detail blocks is marked reads no
+    // detail band and skips their half of the arithmetic (at low rates the finest bands are empty)
+    const uint8_t *blk;
+    int BH, BW;
 };
 
 template <typename Tout>
@@ -105,6 +111,31 @@ __global__ void __launch_bounds__(IV_WARPS * 32) dwt_inv_level_kernel(const InvK
     const double *a_aa = LLQ ? nullptr : p.src_a + (size_t)z * p.a_h * p.a_w + kc;
     const int a_w = p.a_w;
 
+    // ---- are the three detail bands zero over everything this task reads?
+    bool dz = false;
+    if (p.blk) {
+        // band rows / columns of the task (clamped like the loads; a wrapped range counts as the whole band)
+        int ra = p0 + S2 - (HF - 1), rb = ra + npair + HF - 1;
+        int ca = q0 + S2 - (HF - 1), cb = ca + 31;
+        if (per && (ra < 0 || rb >= bh)) { ra = 0; rb = bh - 1; }
+        if (per && (ca < 0 || cb >= bw)) { ca = 0; cb = bw - 1; }
+        ra = max(ra, 0); rb = min(rb, bh - 1);
+        ca = max(ca, 0); cb = min(cb, bw - 1);
+        const uint8_t *bz = p.blk + (size_t)z * p.BH * p.BW;
+        bool any = false;
+#pragma unroll
+        for (int band = 0; band < 3; ++band) {  // ad (rows 0.., cols sw..), da (rows sh.., cols 0..), dd
+            const int ro = band == 0 ? 0 : p.sh, co = band == 1 ? 0 : p.sw;
+            const int br0 = (ro + ra) >> 6, br1 = (ro + rb) >> 6, bc0 = (co + ca) >> 6, bc1 = (co + cb) >> 6;
+            const int nbc = bc1 - bc0 + 1, nb = (br1 - br0 + 1) * nbc;
+            for (int t = lane; t < nb; t += 32) any = any || bz[(size_t)(br0 + t / nbc) * p.BW + bc0 + t % nbc] != 0;
+        }
+        dz = !__any_sync(FULL, any);
+    }
+
+    // the streaming part, compiled twice: with and without the detail bands (warp-uniform choice)
+    auto stream = [&](auto dzc) {
+    constexpr bool DZ = decltype(dzc)::value;
     struct Raw {
         int32_t ad, da, dd, aaq;
         double aa;
@@ -120,9 +151,13 @@ __global__ void __launch_bounds__(IV_WARPS * 32) dwt_inv_level_kernel(const InvK
             row = min(row, bh - 1);
         }
         const size_t o = (size_t)row * Wc;
-        r.ad = __ldg(c_ad + o);
-        r.da = __ldg(c_da + o);
-        r.dd = __ldg(c_dd + o);
+        if constexpr (!DZ) {
+            r.ad = __ldg(c_ad + o);
+            r.da = __ldg(c_da + o);
+            r.dd = __ldg(c_dd + o);
+        } else {
+            r.ad = r.da = r.dd = 0;
+        }
         if (LLQ)
             r.aaq = __ldg(c_aa + o);
         else
@@ -141,21 +176,18 @@ __global__ void __launch_bounds__(IV_WARPS * 32) dwt_inv_level_kernel(const InvK
         for (int u = 0; u < HF; ++u) {
             const int d = HF - 1 - u;  // lane j + d holds column q + S/2 - u
             const double vaa = d ? __shfl_down_sync(FULL, aa, d) : aa;
+            if (Wav<WID>::rec_lo(2 * u) != 0.0) le = fma(Wav<WID>::rec_lo(2 * u), vaa, le);
+            if (Wav<WID>::rec_lo(2 * u + 1) != 0.0) lo = fma(Wav<WID>::rec_lo(2 * u + 1), vaa, lo);
+            if constexpr (DZ) continue;  // all three detail bands are zero over this task
             const double vad = d ? __shfl_down_sync(FULL, ad, d) : ad;
             const double vda = d ? __shfl_down_sync(FULL, da, d) : da;
             const double vdd = d ? __shfl_down_sync(FULL, dd, d) : dd;
-            if (Wav<WID>::rec_lo(2 * u) != 0.0) {
-                le = fma(Wav<WID>::rec_lo(2 * u), vaa, le);
-                he = fma(Wav<WID>::rec_lo(2 * u), vda, he);
-            }
+            if (Wav<WID>::rec_lo(2 * u) != 0.0) he = fma(Wav<WID>::rec_lo(2 * u), vda, he);
             if (wav_rec_hi<WID>(2 * u) != 0.0) {
                 le = fma(wav_rec_hi<WID>(2 * u), vad, le);
                 he = fma(wav_rec_hi<WID>(2 * u), vdd, he);
             }
-            if (Wav<WID>::rec_lo(2 * u + 1) != 0.0) {
-                lo = fma(Wav<WID>::rec_lo(2 * u + 1), vaa, lo);
-                ho = fma(Wav<WID>::rec_lo(2 * u + 1), vda, ho);
-            }
+            if (Wav<WID>::rec_lo(2 * u + 1) != 0.0) ho = fma(Wav<WID>::rec_lo(2 * u + 1), vda, ho);
             if (wav_rec_hi<WID>(2 * u + 1) != 0.0) {
                 lo = fma(wav_rec_hi<WID>(2 * u + 1), vad, lo);
                 ho = fma(wav_rec_hi<WID>(2 * u + 1), vdd, ho);
@@ -202,7 +234,7 @@ __global__ void __launch_bounds__(IV_WARPS * 32) dwt_inv_level_kernel(const InvK
                     e0 = fma(Wav<WID>::rec_lo(2 * u), xlo[slot][0], e0);
                     e1 = fma(Wav<WID>::rec_lo(2 * u), xlo[slot][1], e1);
                 }
-                if (wav_rec_hi<WID>(2 * u) != 0.0) {
+                if (wav_rec_hi<WID>(2 * u) != 0.0 && !DZ) {
                     e0 = fma(wav_rec_hi<WID>(2 * u), xhi[slot][0], e0);
                     e1 = fma(wav_rec_hi<WID>(2 * u), xhi[slot][1], e1);
                 }
@@ -210,7 +242,7 @@ __global__ void __launch_bounds__(IV_WARPS * 32) dwt_inv_level_kernel(const InvK
                     o0 = fma(Wav<WID>::rec_lo(2 * u + 1), xlo[slot][0], o0);
                     o1 = fma(Wav<WID>::rec_lo(2 * u + 1), xlo[slot][1], o1);
                 }
-                if (wav_rec_hi<WID>(2 * u + 1) != 0.0) {
+                if (wav_rec_hi<WID>(2 * u + 1) != 0.0 && !DZ) {
                     o0 = fma(wav_rec_hi<WID>(2 * u + 1), xhi[slot][0], o0);
                     o1 = fma(wav_rec_hi<WID>(2 * u + 1), xhi[slot][1], o1);
                 }
@@ -222,6 +254,11 @@ __global__ void __launch_bounds__(IV_WARPS * 32) dwt_inv_level_kernel(const InvK
             dst += 2 * (size_t)ow;
         }
     }
+    };
+    if (dz)
+        stream(std::true_type{});
+    else
+        stream(std::false_type{});
 }
 
 // ---- IPT -> RGB (colour.convert(.., 'IPT', 'RGB')): numpy-inverted IPT matrices,
@@ -360,6 +397,9 @@ int launch_inverse(spihtb_ctx *ctx, const int32_t *coeffs, const XformArgs &x, v
         k.C = x.C;
         for (int c = 0; c < 8; ++c) k.rscale[c] = 1.0 / x.scale[c];
         k.rq = 1.0 / x.q;
+        k.blk = x.blk;
+        k.BH = (g.enc_h + 63) / 64;
+        k.BW = (g.enc_w + 63) / 64;
         bool out_f32 = false;
         if (l == 0) {
             k.dst = color ? ctx->io2.p : pixels_out;

@@ -47,6 +47,9 @@ struct DecArgs {
     const int32_t *n;        // [B]
     int B, C, H, W, ll_h, ll_w;
     int32_t *out;  // [B][C][H][W]
+    // optional [B*C][ceil(H/64)][ceil(W/64)] bytes, zeroed by the caller: the decoder marks every 64x64 block
+    // of the array it writes a coefficient into (the inverse transform skips the detail bands of unmarked blocks)
+    uint8_t *blk = nullptr;
 };
 int launch_decode(spihtb_ctx *ctx, const DecArgs &a);
 
@@ -58,6 +61,7 @@ struct XformArgs {
     double scale[8];  // per-channel multipliers m_c (1.0 when none)
     double q;
     int pixel_dtype;
+    const uint8_t *blk = nullptr;  // inverse only: block marks of the coefficient array (see DecArgs), or null
 };
 // Pyramid base pass fused into the forward transform: dp planes [B*C][enc_h/2][enc_w/2] and maxabs [B]
 // are complete when launch_forward returns (stream order).

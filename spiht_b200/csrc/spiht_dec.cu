@@ -57,6 +57,8 @@ struct DecK {
     int B, C, H, W, ll_h, ll_w;
     KeyFmt kf;
     int32_t *out;
+    uint8_t *blk;  // optional block marks [B*C][BH][BW] (64x64 blocks of the array holding a coefficient)
+    int BH, BW;
     uint32_t *lip, *lsp, *lis;  // lip: 2 buffers per slot; lis: 3 buffers per slot
     size_t pix_cap, lis_cap;
     unsigned int *counter;
@@ -141,7 +143,8 @@ __device__ __forceinline__ void refine_cell(int32_t *cell, int n, uint32_t bit)
     *cell = x >= 0 ? (int32_t)mag : -(int32_t)mag;
 }
 
-// One thread: apply queued writes in list order.
+// One thread: apply queued writes in list order.  (Cells in a duplicated subtree; their blocks are marked by
+// the caller's mark() at queueing time.)
 __device__ void apply_queue(const uint2 *dq, uint32_t cnt, const KeyFmt &kf, int32_t *rec, uint32_t H, uint32_t W,
                             int n)
 {
@@ -191,6 +194,63 @@ __device__ __forceinline__ uint32_t lip_state_scan(uint32_t fn, uint32_t s_in, u
     // state entering this lane = exclusive prefix within the warp applied to the warp's entry state
     const uint32_t prev = __shfl_up_sync(0xffffffffu, inc, 1);
     return lane == 0 ? s_mine : ((prev >> s_mine) & 1u);
+}
+
+// ---- the serial walk over the LIS records of one round (one thread).  Out of line so that its register
+// allocation does not depend on the rest of the kernel (which runs at the 64-register cap): the loop is pure
+// instruction latency, and a spilled value in it costs more than the call.
+// a_sw: staged stream words (MSB-first, zero from the end of the stream on), q: table address of the round's first
+// bit (s_lp + pos mod 32; the table is 32-byte aligned, so q mod 32 is the shift of the stream window), a_x: per-entry
+// child-length bytes to fill, a_t: set-type words (MSB-first), cnt: entries of the round.  Returns the bits consumed
+// (every entry one, every fired A set its child bits).
+__device__ __noinline__ uint32_t lis_walk(uint32_t a_sw, uint32_t q, uint32_t a_x, uint32_t a_t, uint32_t cnt)
+{
+    const uint32_t a_swe = a_sw + (DEC_PLW - 1) * 4;  // last staged word
+    const uint32_t a_x31 = a_x + 31u;
+    const uint32_t q0 = q;
+    uint32_t r0 = lds_u32(a_sw), r1 = lds_u32(a_sw + 4), r2 = lds_u32(a_sw + 8);
+    a_sw += 12;
+    uint32_t t0 = lds_u32(a_t), t1 = lds_u32(a_t + 4), t2 = lds_u32(a_t + 8);
+    a_t += 12;
+    uint32_t e = 0;                                 // entries consumed in this round
+    uint32_t nextq = (q & ~31u) + 32, nexte = 32;   // where the windows run out of their first word
+#pragma unroll 1
+    while (e < cnt) {
+        const uint32_t w0 = __funnelshift_l(r1, r0, q);
+        const uint32_t tt = __funnelshift_l(t1, t0, e);
+        const uint32_t m = w0 & tt & 0xffffff00u;
+        uint32_t hb;
+        asm("bfind.u32 %0, %1;" : "=r"(hb) : "r"(m));  // 31 - distance of the fired set
+        const uint32_t at = q - hb;                     // table address of the set, minus 31
+        const uint32_t len = lds_u8(at + 31u);
+        const uint32_t e1 = e - hb + 32u;
+        if (__builtin_expect(m != 0, 1)) {
+            sts_u8(a_x31 + e - hb, len);
+            e = e1;
+            q = at + len + 32u;
+        } else {  // no fired A set within the next 24 entries
+            const uint32_t sh = min(24u, cnt - e);
+            e += sh;
+            q += sh;
+        }
+        if (__builtin_expect(q >= nextq || e >= nexte, 0)) {
+            if (q >= nextq) {
+                nextq += 32;
+                r0 = r1;
+                r1 = r2;
+                r2 = lds_u32(min(a_sw, a_swe));
+                a_sw += 4;
+            }
+            if (e >= nexte) {
+                nexte += 32;
+                t0 = t1;
+                t1 = t2;
+                t2 = lds_u32(a_t);
+                a_t += 4;
+            }
+        }
+    }
+    return q - q0;
 }
 
 __global__ void __launch_bounds__(DEC_NT, 2) spiht_decode_kernel(const DecK p)
@@ -490,67 +550,15 @@ __global__ void __launch_bounds__(DEC_NT, 2) spiht_decode_kernel(const DecK p)
                             // of the stream window and the funnel shift wraps it), the entry index e is the
                             // shift of the set-type window, and both word rotations and the step without a
                             // fired set sit behind one rarely taken branch.
-                            uint32_t a_sw = (uint32_t)__cvta_generic_to_shared(s_sw);
-                            uint32_t q = (uint32_t)__cvta_generic_to_shared(s_lp) + (uint32_t)(pos & 31);
-                            uint32_t a_x31 = (uint32_t)__cvta_generic_to_shared(s_x) + 31u;
-                            uint32_t a_t = (uint32_t)__cvta_generic_to_shared(s_tmask);
-                            uint32_t a_swe = a_sw + (DEC_PLW - 1) * 4;  // last staged word
-                            const uint32_t q0 = q;
-                            // keep the addresses in registers (the compiler would otherwise rebuild them
-                            // from a special register inside the loop)
-                            asm volatile("" : "+r"(a_sw), "+r"(q), "+r"(a_x31), "+r"(a_t), "+r"(a_swe));
-                            uint32_t r0 = lds_u32(a_sw), r1 = lds_u32(a_sw + 4), r2 = lds_u32(a_sw + 8);
-                            a_sw += 12;
-                            uint32_t t0 = lds_u32(a_t), t1 = lds_u32(a_t + 4), t2 = lds_u32(a_t + 8);
-                            a_t += 12;
-                            uint32_t e = 0;                         // entries consumed in this round
-                            uint32_t nextq = (q & ~31u) + 32, nexte = 32;  // where the windows run out of their first word
-                            uint32_t n_it = 0, n_ev = 0;
-#pragma unroll 1
-                            while (e < cnt) {
-                                const uint32_t w0 = __funnelshift_l(r1, r0, q);
-                                const uint32_t tt = __funnelshift_l(t1, t0, e);
-                                const uint32_t m = w0 & tt & 0xffffff00u;
-                                uint32_t hb;
-                                asm("bfind.u32 %0, %1;" : "=r"(hb) : "r"(m));  // 31 - distance of the fired set
-                                const uint32_t at = q - hb;                     // table address of the set, minus 31
-                                const uint32_t len = lds_u8(at + 31u);
-                                const uint32_t e1 = e - hb + 32u;
-                                if (__builtin_expect(m != 0, 1)) {
-                                    sts_u8(a_x31 + e - hb, len);
-                                    e = e1;
-                                    q = at + len + 32u;
-                                    DEC_CHAIN_CNT(n_ev);
-                                } else {  // no fired A set within the next 24 entries
-                                    const uint32_t sh = min(24u, cnt - e);
-                                    e += sh;
-                                    q += sh;
-                                }
-                                DEC_CHAIN_CNT(n_it);
-                                if (__builtin_expect(q >= nextq || e >= nexte, 0)) {
-                                    if (q >= nextq) {
-                                        nextq += 32;
-                                        r0 = r1;
-                                        r1 = r2;
-                                        r2 = lds_u32(min(a_sw, a_swe));
-                                        a_sw += 4;
-                                    }
-                                    if (e >= nexte) {
-                                        nexte += 32;
-                                        t0 = t1;
-                                        t1 = t2;
-                                        t2 = lds_u32(a_t);
-                                        a_t += 4;
-                                    }
-                                }
-                            }
+                            const uint32_t used = lis_walk((uint32_t)__cvta_generic_to_shared(s_sw),
+                                                           (uint32_t)__cvta_generic_to_shared(s_lp) + (uint32_t)(pos & 31),
+                                                           (uint32_t)__cvta_generic_to_shared(s_x),
+                                                           (uint32_t)__cvta_generic_to_shared(s_tmask), cnt);
                             // bits consumed: every entry one, every fired A set its child bits
-                            s_chain_p = pos + (q - q0);
+                            s_chain_p = pos + used;
                             s_na = 0;
                             if (b == 0) {
                                 g_dec_prof[2] += (unsigned long long)(clock64() - _tc);
-                                g_dec_prof[9] += n_it;
-                                g_dec_prof[10] += n_ev;
                                 g_dec_prof[11] += 1;
                             }
                         }
@@ -731,6 +739,25 @@ __global__ void __launch_bounds__(DEC_NT, 2) spiht_decode_kernel(const DecK p)
             if (n == 0) break;
         }
         __syncthreads();
+        // every coefficient that became non-zero is in the LSP: mark the 64x64 blocks of the array they lie in
+        // (benign race: every writer stores 1)
+        if (p.blk) {
+            uint8_t *blkb = p.blk + (size_t)b * C * p.BH * p.BW;
+            constexpr int MU = 8;  // keys in flight per thread (the loop is pure load latency otherwise)
+            for (uint32_t e0 = tid; e0 < lsp_len; e0 += DEC_NT * MU) {
+                uint32_t key[MU];
+#pragma unroll
+                for (int u = 0; u < MU; ++u) key[u] = e0 + u * DEC_NT < lsp_len ? lsp[e0 + u * DEC_NT] : 0xffffffffu;
+#pragma unroll
+                for (int u = 0; u < MU; ++u) {
+                    if (e0 + u * DEC_NT < lsp_len) {
+                        uint32_t k, i, j;
+                        key_unpack(kf, key[u], k, i, j);
+                        blkb[((size_t)k * p.BH + (i >> 6)) * p.BW + (j >> 6)] = 1;
+                    }
+                }
+            }
+        }
         if (tid == 0 && b == 0) g_dec_prof[5] += (unsigned long long)(clock64() - _timg);
     }
 }
@@ -761,6 +788,9 @@ int launch_decode(spihtb_ctx *ctx, const DecArgs &a)
     k.n = a.n;
     k.B = a.B; k.C = a.C; k.H = a.H; k.W = a.W; k.ll_h = a.ll_h; k.ll_w = a.ll_w;
     k.out = a.out;
+    k.blk = a.blk;
+    k.BH = (a.H + 63) / 64;
+    k.BW = (a.W + 63) / 64;
 
     int occ = 1;
     SPIHTB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, spiht_decode_kernel, DEC_NT, 0));
