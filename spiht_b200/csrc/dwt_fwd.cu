@@ -335,37 +335,44 @@ __device__ __forceinline__ void dwt_fwd_task(const FwdK &p, int tx, int ty, int 
     if (ok0 && ok_prev) fl |= SP_PAIR_PREV;
     if (ok0 && !ok_prev) fl |= SP_V0_ALONE;
     if (ok1 && !ok_next) fl |= SP_V1_ALONE;
-    const uint32_t k0m = ok0 ? ~0u : 0u, k1m = ok1 ? ~0u : 0u, kpm = ok_prev ? ~0u : 0u;
+    // The high-pass column filter of every supported wavelet ends one pair earlier than the low-pass one (the
+    // taps at pair offset HF-1 are zero), so the last column of the lane *before* the first storing lane is
+    // already correct in the two bands that start at column sw: a cell of those bands that straddles two strips
+    // is completed by the right-hand strip, and the fix-up pass needs none of their interior columns.
+    constexpr bool HI_SHORT = wav_dec_hi<WID>(2 * (HF - 1)) == 0.0 && wav_dec_hi<WID>(2 * (HF - 1) + 1) == 0.0;
+    const bool ok_prev_hi = HI_SHORT ? (lane >= 1 && lane >= HL && kf - 1 >= 0 && kf - 1 < p.bw) : ok_prev;
+    const uint32_t k0m = ok0 ? ~0u : 0u, k1m = ok1 ? ~0u : 0u, kpm = ok_prev ? ~0u : 0u,
+                   kpm_hi = ok_prev_hi ? ~0u : 0u;
     // fused pyramid base pass: one cell tracker per detail band (band rows from ro, columns from co)
     CellTrack ct_ad, ct_da, ct_dd;
     uint32_t mx = 0;
     const int pyrNW = p.NW;
     uint8_t *dpz = PYR ? p.dp + (size_t)z * p.NH * p.NW : nullptr;
     bool wr_lo, wr_hi;  // lane's cell complete in this strip: bands starting at column 0 / at column sw
-    auto cell_init = [&](CellTrack &ct, int ro, int co, bool &wr) {
+    auto cell_init = [&](CellTrack &ct, int ro, int co, bool &wr, bool okp) {
         const int c = co + kf, a = ro + r0;
         ct.prev = 0;
         ct.off = (a >> 1) * p.NW + (c >> 1);
         if (NP == 2)
-            wr = (c & 1) ? (ok0 && ok_prev) : (ok0 && ok1);
+            wr = (c & 1) ? (ok0 && okp) : (ok0 && ok1);
         else
-            wr = (c & 1) && ok0 && ok_prev;
+            wr = (c & 1) && ok0 && okp;
     };
-    cell_init(ct_ad, 0, p.sw, wr_hi);
-    cell_init(ct_da, p.sh, 0, wr_lo);
-    cell_init(ct_dd, p.sh, p.sw, wr_hi);
+    cell_init(ct_ad, 0, p.sw, wr_hi, ok_prev_hi);
+    cell_init(ct_da, p.sh, 0, wr_lo, ok_prev);
+    cell_init(ct_dd, p.sh, p.sw, wr_hi, ok_prev_hi);
     const int par_ad = r0 & 1, par_lo = (p.sh + r0) & 1;  // parity of the chunk's first row in the array
     const bool codd_hi = ((p.sw + kf) & 1) != 0, codd_lo = (kf & 1) != 0;  // first column odd (warp-uniform for NP == 2)
     // cell maximum of one band row and the running maximum of everything stored
-    auto cell_max = [&](int32_t v0, int32_t v1, int32_t up, bool codd) -> uint32_t {
+    auto cell_max = [&](int32_t v0, int32_t v1, int32_t up, bool codd, uint32_t kp) -> uint32_t {
         const uint32_t m0 = absu(v0) & k0m;
         if (NP == 2) {
             const uint32_t t = max(m0, absu(v1) & k1m);
             mx = max(mx, t);
-            return codd ? max(absu(up) & kpm, m0) : t;
+            return codd ? max(absu(up) & kp, m0) : t;
         }
         mx = max(mx, m0);
-        return max(absu(up) & kpm, m0);
+        return max(absu(up) & kp, m0);
     };
 
     // the loop body is unrolled over HF rows so that the window slots are static
@@ -501,9 +508,9 @@ __device__ __forceinline__ void dwt_fwd_task(const FwdK &p, int tx, int ty, int 
                 if constexpr (PYR) {
                     const bool not_first = i > 0;
                     const bool odd_ad = ((i ^ par_ad) & 1) != 0, odd_lo = ((i ^ par_lo) & 1) != 0;
-                    cell_row(ct_ad, cell_max(q_ad[0], q_ad[NP - 1], u_ad, codd_hi), odd_ad, wr_hi && not_first, dpz, pyrNW);
-                    cell_row(ct_da, cell_max(q_da[0], q_da[NP - 1], u_da, codd_lo), odd_lo, wr_lo && not_first, dpz, pyrNW);
-                    cell_row(ct_dd, cell_max(q_dd[0], q_dd[NP - 1], u_dd, codd_hi), odd_lo, wr_hi && not_first, dpz, pyrNW);
+                    cell_row(ct_ad, cell_max(q_ad[0], q_ad[NP - 1], u_ad, codd_hi, kpm_hi), odd_ad, wr_hi && not_first, dpz, pyrNW);
+                    cell_row(ct_da, cell_max(q_da[0], q_da[NP - 1], u_da, codd_lo, kpm), odd_lo, wr_lo && not_first, dpz, pyrNW);
+                    cell_row(ct_dd, cell_max(q_dd[0], q_dd[NP - 1], u_dd, codd_hi, kpm_hi), odd_lo, wr_hi && not_first, dpz, pyrNW);
                     if (!ll_scratch) {
                         mx = max(mx, absu(q_aa[0]) & k0m);
                         if (NP == 2) mx = max(mx, absu(q_aa[NP - 1]) & k1m);
@@ -702,10 +709,15 @@ static void fix_rects_level(std::vector<FixRect> &out, int bh, int bw, int sh, i
             if (first & 1) add(first >> 1, (first >> 1) + 1, b0, b1);
             if (!(last & 1)) add(last >> 1, (last >> 1) + 1, b0, b1);
         }
+        // (the bands that start at column sw complete their strip-straddling cells themselves when the
+        // high-pass filter is one pair shorter, see HI_SHORT in dwt_fwd_task: only the band's own edges remain)
+        constexpr int HF = Wav<WID>::F / 2;
+        constexpr bool HI_SHORT = wav_dec_hi<WID>(2 * (HF - 1)) == 0.0 && wav_dec_hi<WID>(2 * (HF - 1) + 1) == 0.0;
+        const bool self = HI_SHORT && co != 0;
         for (int tx = 0; tx < tiles_x; ++tx) {
             const int first = co + tx * NOUT, last = co + std::min((tx + 1) * NOUT, bw) - 1;
-            if (first & 1) add(a0, a1, first >> 1, (first >> 1) + 1);
-            if (!(last & 1)) add(a0, a1, last >> 1, (last >> 1) + 1);
+            if ((first & 1) && !(self && tx > 0)) add(a0, a1, first >> 1, (first >> 1) + 1);
+            if (!(last & 1) && !(self && tx + 1 < tiles_x)) add(a0, a1, last >> 1, (last >> 1) + 1);
         }
     }
 }
