@@ -243,6 +243,9 @@ int spihtb_create(int device, spihtb_ctx **out)
     SPIHTB_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
     c->sm_count = sms > 0 ? sms : 148;
     c->stream = nullptr;
+    SPIHTB_CUDA_CHECK(cudaStreamCreateWithFlags(&c->aux, cudaStreamNonBlocking));
+    SPIHTB_CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    SPIHTB_CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     *out = c;
     return SPIHTB_OK;
 }
@@ -252,6 +255,12 @@ int spihtb_destroy(spihtb_ctx *ctx)
     if (!ctx) return SPIHTB_OK;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->aux) {
+        cudaStreamSynchronize(ctx->aux);
+        cudaStreamDestroy(ctx->aux);
+        cudaEventDestroy(ctx->ev_fork);
+        cudaEventDestroy(ctx->ev_join);
+    }
     DevBuf *bufs[] = {&ctx->pyr, &ctx->lists, &ctx->misc, &ctx->tmpa, &ctx->tmpb, &ctx->io, &ctx->io2, &ctx->fix, &ctx->u8lut, &ctx->blk};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);

@@ -44,6 +44,10 @@ struct spihtb_ctx {
     int device = 0;
     int sm_count = 148;
     cudaStream_t stream = nullptr;
+    // side stream for work that is independent of the main chain of a call (the gap fill of the forward
+    // transform runs beside the first DWT level); fork / join events
+    cudaStream_t aux = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int64_t launches = 0;
     // grow-only device workspaces
     spihtb::DevBuf pyr;      // DP / LP planes + LL-root planes + per-image max

@@ -892,11 +892,9 @@ int launch_forward(spihtb_ctx *ctx, const void *pixels, const XformArgs &x, int3
         SPIHTB_CUDA_CHECK(cudaMemsetAsync(pf->maxabs, 0, sizeof(uint32_t) * x.B, ctx->stream));
         ctx->stage_end(2);
     }
-    for (int l = 0; l < L; ++l) {
-        rc = run_level(l, 0, nz);
-        if (rc) return rc;
-    }
-    (void)src_is_f64;
+    rc = run_level(0, 0, nz);
+    if (rc) return rc;
+    bool gap_forked = false;
     {
         GapK gk;
         gk.coeffs = coeffs;
@@ -921,12 +919,22 @@ int launch_forward(spihtb_ctx *ctx, const void *pixels, const XformArgs &x, int3
         }
         gk.first[gk.nrect] = gk.nrows;
         if (gk.nrect) {
-            ctx->stage_begin(1);
-            gap_fill_kernel<<<dim3((gk.nrows + 7) / 8, std::min(nz, 48)), dim3(32, 8), 0, ctx->stream>>>(gk);
+            // independent of every DWT level (disjoint parts of the array and of the cell planes): it runs on the
+            // side stream, beside the levels after the first (which leave bandwidth unused), and is joined before the fix-up pass / the end of the call
+            SPIHTB_CUDA_CHECK(cudaEventRecord(ctx->ev_fork, ctx->stream));
+            SPIHTB_CUDA_CHECK(cudaStreamWaitEvent(ctx->aux, ctx->ev_fork, 0));
+            gap_fill_kernel<<<dim3((gk.nrows + 7) / 8, std::min(nz, 48)), dim3(32, 8), 0, ctx->aux>>>(gk);
             ctx->launches++;
-            ctx->stage_end(1);
+            SPIHTB_CUDA_CHECK(cudaEventRecord(ctx->ev_join, ctx->aux));
+            gap_forked = true;
         }
     }
+    for (int l = 1; l < L; ++l) {
+        rc = run_level(l, 0, nz);
+        if (rc) return rc;
+    }
+    (void)src_is_f64;
+    if (gap_forked) SPIHTB_CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));  // join the gap fill
     SPIHTB_CUDA_CHECK(cudaGetLastError());
     if (pf) {
         const FixRect *rects;
