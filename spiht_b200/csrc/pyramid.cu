@@ -118,6 +118,55 @@ __device__ __forceinline__ uint32_t ld4_any(const uint8_t *p)
     return __funnelshift_r(w[0], w[1], sh);
 }
 
+// One quad = four consecutive nodes (i, j0 .. j0+3) of a ring in one plane.  quad_load gathers their eight child
+// bytes in each of two rows and their own four bytes; quad_store writes lp = max over the children and
+// dp = max(dp, lp) for the nodes of the quad that belong to the ring (`member`).
+struct Quad {
+    uint2 a, b;
+    uint32_t own;
+};
+__device__ __forceinline__ uint32_t quad_members(int i, int j0, int RW, int IH, int IW)
+{
+    uint32_t member = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+        if (j0 + q < RW && !(i < IH && j0 + q < IW)) member |= 1u << q;  // outside the deeper rings (and (0,0))
+    return member;
+}
+__device__ __forceinline__ Quad quad_load(const uint8_t *d, int NH, int NW, int i, int j0)
+{
+    Quad q;
+    const size_t c00 = (size_t)(2 * i) * NW + 2 * j0;
+    q.a = ld8_any(d + c00);
+    q.b = 2 * i + 1 < NH ? ld8_any(d + c00 + NW) : make_uint2(0u, 0u);  // 2i < NH holds for every ring node
+    q.own = ld4_any(d + (size_t)i * NW + j0);
+    return q;
+}
+__device__ __forceinline__ void quad_store(const Quad &q, uint8_t *d, uint8_t *l, int NW, int i, int j0, uint32_t member)
+{
+    // child columns 2 j0 .. 2 j0 + 7 that exist
+    const int ncol = min(8, NW - 2 * j0);
+    const uint32_t mlo = ncol >= 4 ? 0xffffffffu : (0xffffffffu >> (8 * (4 - ncol)));
+    const uint32_t mhi = ncol >= 8 ? 0xffffffffu : (ncol <= 4 ? 0u : (0xffffffffu >> (8 * (8 - ncol))));
+    const uint32_t lo = bmax4(q.a.x, q.b.x) & mlo, hi = bmax4(q.a.y, q.b.y) & mhi;
+    const uint32_t tl = bmax4(lo, lo >> 8), th = bmax4(hi, hi >> 8);  // bytes 0, 2: node maxima
+    const uint32_t m4 = __byte_perm(tl, th, 0x6420);
+    const uint32_t d4 = bmax4(q.own, m4);
+    uint8_t *lq = l + (size_t)i * NW + j0, *dq = d + (size_t)i * NW + j0;
+    if (member == 0xfu && (reinterpret_cast<uintptr_t>(lq) & 3) == 0) {
+        *reinterpret_cast<uint32_t *>(lq) = m4;
+        *reinterpret_cast<uint32_t *>(dq) = d4;
+    } else {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            if (member & (1u << t)) {
+                lq[t] = (uint8_t)(m4 >> (8 * t));
+                dq[t] = (uint8_t)(d4 >> (8 * t));
+            }
+        }
+    }
+}
+
 // one large ring (ring 2 is a quarter of the node grid): blockDim (32, 8); a thread takes four consecutive
 // nodes of a row -- their children are 8 consecutive bytes in each of two rows -- in PYR_ZPT planes with all
 // loads in flight together; byte-wise maxima with the SIMD video instructions
@@ -127,55 +176,18 @@ __global__ void __launch_bounds__(256) pyr_ring_kernel(int NH, int NW, int RH, i
 {
     const int j0 = (blockIdx.x * 32 + threadIdx.x) * 4, i = blockIdx.y * 8 + threadIdx.y;
     if (i >= RH || j0 >= RW) return;
-    // nodes of the quad that belong to this ring: inside [0,RW), outside the deeper rings (and (0,0))
-    uint32_t member = 0;
-#pragma unroll
-    for (int q = 0; q < 4; ++q)
-        if (j0 + q < RW && !(i < IH && j0 + q < IW)) member |= 1u << q;
+    const uint32_t member = quad_members(i, j0, RW, IH, IW);
     if (!member) return;
-    const size_t plane = (size_t)NH * NW, o = (size_t)i * NW + j0;
-    const bool r1 = 2 * i + 1 < NH;  // 2i < NH holds for every ring node
-    const size_t c00 = (size_t)(2 * i) * NW + 2 * j0;
-    // child columns 2 j0 .. 2 j0 + 7 that exist
-    const int ncol = min(8, NW - 2 * j0);
-    const uint32_t mlo = ncol >= 4 ? 0xffffffffu : (0xffffffffu >> (8 * (4 - ncol)));
-    const uint32_t mhi = ncol >= 8 ? 0xffffffffu : (ncol <= 4 ? 0u : (0xffffffffu >> (8 * (8 - ncol))));
+    const size_t plane = (size_t)NH * NW;
     for (int z0 = blockIdx.z * PYR_ZPT; z0 < nz; z0 += gridDim.z * PYR_ZPT) {
-        uint2 a[PYR_ZPT], b[PYR_ZPT];
-        uint32_t own[PYR_ZPT];
+        Quad q[PYR_ZPT];
 #pragma unroll
-        for (int q = 0; q < PYR_ZPT; ++q) {
-            a[q] = b[q] = make_uint2(0u, 0u);
-            own[q] = 0;
-            if (z0 + q < nz) {
-                const uint8_t *d = dp + (size_t)(z0 + q) * plane;
-                a[q] = ld8_any(d + c00);
-                if (r1) b[q] = ld8_any(d + c00 + NW);
-                own[q] = ld4_any(d + o);
-            }
-        }
+        for (int u = 0; u < PYR_ZPT; ++u)
+            if (z0 + u < nz) q[u] = quad_load(dp + (size_t)(z0 + u) * plane, NH, NW, i, j0);
 #pragma unroll
-        for (int q = 0; q < PYR_ZPT; ++q) {
-            if (z0 + q < nz) {
-                const uint32_t lo = bmax4(a[q].x, b[q].x) & mlo, hi = bmax4(a[q].y, b[q].y) & mhi;
-                const uint32_t tl = bmax4(lo, lo >> 8), th = bmax4(hi, hi >> 8);  // bytes 0, 2: node maxima
-                const uint32_t m4 = __byte_perm(tl, th, 0x6420);
-                const uint32_t d4 = bmax4(own[q], m4);
-                uint8_t *lq = lp + (size_t)(z0 + q) * plane + o, *dq = dp + (size_t)(z0 + q) * plane + o;
-                if (member == 0xfu && (reinterpret_cast<uintptr_t>(lq) & 3) == 0) {
-                    *reinterpret_cast<uint32_t *>(lq) = m4;
-                    *reinterpret_cast<uint32_t *>(dq) = d4;
-                } else {
-#pragma unroll
-                    for (int t = 0; t < 4; ++t) {
-                        if (member & (1u << t)) {
-                            lq[t] = (uint8_t)(m4 >> (8 * t));
-                            dq[t] = (uint8_t)(d4 >> (8 * t));
-                        }
-                    }
-                }
-            }
-        }
+        for (int u = 0; u < PYR_ZPT; ++u)
+            if (z0 + u < nz)
+                quad_store(q[u], dp + (size_t)(z0 + u) * plane, lp + (size_t)(z0 + u) * plane, NW, i, j0, member);
     }
 }
 
@@ -194,10 +206,23 @@ __global__ void __launch_bounds__(256) pyr_rest_kernel(const int32_t *__restrict
         const int RH = (int)((NH + s - 1) / s), RW = (int)((NW + s - 1) / s);
         if (RH <= 1 && RW <= 1) break;
         const int IH = (int)((NH + 2 * s - 1) / (2 * s)), IW = (int)((NW + 2 * s - 1) / (2 * s));
-        for (int r = threadIdx.x; r < RH * RW; r += blockDim.x) {
-            const int i = r / RW, j = r % RW;
-            if (i < IH && j < IW) continue;
-            pyr_up_node(d, l, NH, NW, i, j);
+        // four nodes per thread and step, two steps in flight (the chain of rings is latency-bound)
+        const int qpr = (RW + 3) / 4, nq = RH * qpr;
+        for (int r = threadIdx.x; r < nq; r += 2 * blockDim.x) {
+            Quad q[2];
+            int qi[2], qj[2];
+            uint32_t mem[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int rr = r + u * blockDim.x;
+                qi[u] = rr / qpr;
+                qj[u] = 4 * (rr - qi[u] * qpr);
+                mem[u] = rr < nq ? quad_members(qi[u], qj[u], RW, IH, IW) : 0u;
+                if (mem[u]) q[u] = quad_load(d, NH, NW, qi[u], qj[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+                if (mem[u]) quad_store(q[u], d, l, NW, qi[u], qj[u], mem[u]);
         }
         __syncthreads();  // the next ring reads this ring's dp
     }
