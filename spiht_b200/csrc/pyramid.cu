@@ -80,19 +80,6 @@ __global__ void __launch_bounds__(256) pyr_base_kernel(const int32_t *__restrict
 // ---- ring t >= 2: nodes whose deepest child chain has length t ------------
 // node (i,j) of ring [0,RH) x [0,RW) minus the deeper rings [0,IH) x [0,IW):
 //   lp = max dp over its four child nodes, dp = max(dp, lp)
-__device__ __forceinline__ void pyr_up_node(uint8_t *__restrict__ d, uint8_t *__restrict__ l, int NH, int NW, int i, int j)
-{
-    uint32_t m = 0;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const int ci = 2 * i + (q >> 1), cj = 2 * j + (q & 1);
-        if (ci < NH && cj < NW) m = max(m, (uint32_t)d[(size_t)ci * NW + cj]);
-    }
-    const size_t o = (size_t)i * NW + j;
-    l[o] = (uint8_t)m;
-    d[o] = (uint8_t)max((uint32_t)d[o], m);
-}
-
 // 8 / 4 bytes at any alignment from aligned 32-bit words (reads up to 3 bytes past the range: the planes
 // are followed by other planes of the same workspace)
 __device__ __forceinline__ uint2 ld8_any(const uint8_t *p)
@@ -169,7 +156,7 @@ __device__ __forceinline__ void quad_store(const Quad &q, uint8_t *d, uint8_t *l
 
 // one large ring (ring 2 is a quarter of the node grid): blockDim (32, 8); a thread takes four consecutive
 // nodes of a row -- their children are 8 consecutive bytes in each of two rows -- in PYR_ZPT planes with all
-// loads in flight together; byte-wise maxima with the SIMD video instructions
+// loads in flight together; byte-wise maxima by SWAR arithmetic (bmax4)
 constexpr int PYR_ZPT = 4;
 __global__ void __launch_bounds__(256) pyr_ring_kernel(int NH, int NW, int RH, int RW, int IH, int IW, int nz,
                                                        uint8_t *__restrict__ dp, uint8_t *__restrict__ lp)
