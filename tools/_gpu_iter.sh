@@ -1,2 +1,6 @@
-timeout 1000 compute-sanitizer --tool memcheck --print-limit 20 --error-exitcode 9 python -m pytest tests/test_gpu_fused_pyramid.py "tests/test_gpu_transform.py::test_uint8_pixels_equal_imload_floats" "tests/test_gpu_transform.py::test_encode_image_decode_image_parity" tests/test_gpu_spiht.py::test_random_shapes_truncations tests/test_gpu_spiht.py::test_kat3_odd_dims -x -q -m gpu > gpurun_out/memcheck_1.log 2>&1
-echo "exit $?"; grep -c "Invalid\|out of bounds\|Error" gpurun_out/memcheck_1.log; tail -15 gpurun_out/memcheck_1.log | cut -c1-200
+python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu_13.log 2>&1; tail -2 gpurun_out/pytest_gpu_13.log
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+python bench.py > gpurun_out/bench_23.log 2>&1; tail -1 gpurun_out/bench_23.log | cut -c1-200
+ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file gpurun_out/launches_r1e.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --e2e-steps 1 > gpurun_out/ncu_launch_e.log 2>&1
+ncu --set full --clock-control none -k regex:"dwt_fwd_level_kernel|pyr_|gap_fill|spiht_encode_kernel" -c 12 -o /tmp/prof_enc_final -f python tools/profile_step.py --batch 256 --steps 1 > gpurun_out/ncu_final2.log 2>&1; tail -1 gpurun_out/ncu_final2.log
+python tools/ncu_summary.py /tmp/prof_enc_final.ncu-rep > gpurun_out/r01_kernels_b256_encode.md; wc -l gpurun_out/r01_kernels_b256_encode.md
