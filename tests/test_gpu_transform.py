@@ -265,3 +265,32 @@ def test_uint8_pixels_equal_imload_floats(torch_cuda, shape, kw):
     assert torch.equal(ca, cb)
     mb = h * w // 2
     assert spiht.encode_image(u8, st, max_bits=mb) == spiht.encode_image(f64, st, max_bits=mb)
+
+
+@pytest.mark.parametrize("shape,kw", [
+    ((3, 256, 384), dict()),
+    ((1, 301, 263), dict()),
+    ((3, 256, 256), dict(mode="periodization")),
+    ((2, 200, 328), dict(wavelet="bior4.4", mode="symmetric")),
+    ((1, 320, 333), dict(wavelet="bior6.8")),
+])
+@pytest.mark.parametrize("bpp", [0.05, 0.3, 1.0, 3.0])
+def test_decode_images_sparse_inverse_equals_full_inverse(torch_cuda, shape, kw, bpp):
+    """spihtb_decode_images lets the inverse transform skip the detail bands of tasks whose 64x64 blocks hold no
+    decoded coefficient; the pixels must equal those of the full inverse over the same decoded array (from almost
+    empty arrays at 0.05 bpp to dense ones at 3 bpp, so that tasks of both kinds sit side by side)"""
+    import spiht_b200 as spiht
+    from spiht_b200 import _lib, batch
+    torch = torch_cuda
+    c, h, w = shape
+    px = torch.from_numpy(np.stack([synth_image(c, h, w, 40 + s) for s in range(2)])).cuda()
+    st = spiht.SpihtSettings(**kw)
+    g = _lib.plan(h, w, kw.get("wavelet", "bior2.2"), kw.get("mode", "reflect"), None)
+    mb = int(h * w * bpp)
+    s, nbits, max_n, _, _ = batch.encode_images(px, g, st, mb)
+    nbytes = (nbits + 7) // 8
+    fast, coeffs = batch.decode_images(s, nbytes, max_n, c, g, st, dtype=torch.float64)
+    rec = batch.decode_coeffs(s, nbytes, max_n, c, g.enc_h, g.enc_w, g.ll_h, g.ll_w)
+    assert torch.equal(rec, coeffs)
+    full = batch.inverse(rec, g, st, dtype=torch.float64)
+    assert torch.equal(fast, full)
