@@ -140,7 +140,13 @@ __device__ __forceinline__ void cell_row(CellTrack &ct, uint32_t cm, bool odd, b
 {
     const uint32_t m = max(ct.prev, cm);
     ct.prev = cm;
-    if (odd && wr) dpz[ct.off] = (uint8_t)plane1(m);
+    // one predicated byte store (as inline PTX: left to itself the compiler branches around the store and its
+    // address arithmetic three times per row, and the branches cost more than the few instructions they skip)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.global.u8 [%0], %1;\n\t}"
+        :
+        : "l"(dpz + ct.off), "r"(plane1(m)), "r"((uint32_t)(odd && wr))
+        : "memory");
     ct.off += odd ? NW : 0;
 }
 
