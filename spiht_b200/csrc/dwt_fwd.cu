@@ -26,6 +26,9 @@
 namespace spihtb {
 
 constexpr int FW_WARPS = 4;  // warps (= independent tasks) per CTA
+// output rows per task at most (launch_level and fix_rects_level must agree): long chunks amortise the window
+// fill on the small levels, shorter ones balance the big first level better (measured)
+static inline int fw_rhmax(int bh) { return bh >= 384 ? 64 : 96; }
 
 struct FwdK {
     const void *src;        // [nz][src_h][src_w] planes of Tin
@@ -236,7 +239,7 @@ __device__ __forceinline__ void dwt_fwd_task(const FwdK &p, int tx, int ty, int 
     asm volatile("" : "+r"(my));  // keep the shared address in a register (not rebuilt from special registers)
     auto fetch_pair = [&](uint32_t slot_off) {
         const Tin *pa = runp, *pb = runp + src_w;
-        if (gr < 0 || gr + 1 >= src_h) {  // rare (warp-uniform): boundary rows go through the extension map
+        if ((uint32_t)gr > (uint32_t)(src_h - 2)) {  // gr < 0 or gr + 1 >= src_h; rare (warp-uniform): boundary rows go through the extension map
             pa = plane + (size_t)ext_index_slow(gr, src_h, mode) * src_w;
             pb = plane + (size_t)ext_index_slow(gr + 1, src_h, mode) * src_w;
         }
@@ -642,7 +645,7 @@ static int launch_level(spihtb_ctx *ctx, FwdK k, int nz)
 {
     constexpr int NP = FwdCfg<WID>::NP;
     constexpr int NOUT = FwdCfg<WID>::NOUT;
-    constexpr int RHMAX = 64;
+    const int RHMAX = fw_rhmax(k.bh);
     k.tiles_x = (k.bw + NOUT - 1) / NOUT;
     // balanced row chunks (no nearly empty tail chunk)
     k.tiles_y = (k.bh + RHMAX - 1) / RHMAX;
@@ -695,7 +698,7 @@ template <int WID>
 static void fix_rects_level(std::vector<FixRect> &out, int bh, int bw, int sh, int sw, int NH, int NW)
 {
     constexpr int NOUT = FwdCfg<WID>::NOUT;
-    constexpr int RHMAX = 64;
+    const int RHMAX = fw_rhmax(bh);
     const int tiles_x = (bw + NOUT - 1) / NOUT, tiles_y = (bh + RHMAX - 1) / RHMAX;
     const int RH = (bh + tiles_y - 1) / tiles_y;
     auto add = [&](int a0, int a1, int b0, int b1) {
