@@ -28,7 +28,7 @@ namespace spihtb {
 constexpr int FW_WARPS = 4;  // warps (= independent tasks) per CTA
 // output rows per task at most (launch_level and fix_rects_level must agree): long chunks amortise the window
 // fill on the small levels, shorter ones balance the big first level better (measured)
-static inline int fw_rhmax(int bh) { return bh >= 384 ? 64 : 96; }
+static inline int fw_rhmax(int bh) { return bh >= 384 ? 80 : 96; }
 
 struct FwdK {
     const void *src;        // [nz][src_h][src_w] planes of Tin
