@@ -312,8 +312,10 @@ static int launch_inv_level(spihtb_ctx *ctx, InvK k, int nz, bool out_f32)
 {
     constexpr int F = Wav<WID>::F;
     constexpr int NOUT = 32 - (F / 2 - 1);
-    constexpr int RHMAX = 36;  // output row pairs per chunk (a multiple of the bior2.2 loop unroll)
     const int opw = k.ow / 2, oph = k.oh / 2;
+    // output row pairs per chunk (multiples of the bior2.2 loop unroll): long chunks amortise the window fill on
+    // the coarse levels, shorter ones balance the big finest level better (measured)
+    const int RHMAX = oph >= 384 ? 60 : 96;
     k.tiles_x = (opw + NOUT - 1) / NOUT;
     k.tiles_y = (oph + RHMAX - 1) / RHMAX;
     k.RH = (oph + k.tiles_y - 1) / k.tiles_y;
