@@ -121,22 +121,23 @@ def _cpu_worker(args):
     img = img.astype(np.float32).astype(np.float64)
     max_bits = int(size * size * bpp)
     t0 = time.perf_counter()
-    arr, ll_h, ll_w = wrapper_ref.forward_coeffs(img, wavelet, mode)
+    arr, ll_h, ll_w = wrapper_ref.forward_coeffs(img, wavelet, mode, fast=True)   # compiled transform (oracle/dwt_fast.c)
     t1 = time.perf_counter()
     data, max_n = spiht_oracle.encode(arr, ll_h, ll_w, max_bits)
     t2 = time.perf_counter()
     rec = spiht_oracle.decode(data, max_n, 3, arr.shape[1], arr.shape[2], ll_h, ll_w)
     t3 = time.perf_counter()
-    wrapper_ref.inverse_coeffs(rec, size, size, wavelet, mode)
+    wrapper_ref.inverse_coeffs(rec, size, size, wavelet, mode, fast=True)
     t4 = time.perf_counter()
     return (t1 - t0, t2 - t1, t3 - t2, t4 - t3)
 
 
 def cpu_reference_sample(size, bpp, wavelet, mode, n_images, cores, seed=4242):
-    """the oracle (C restatement of the Rust coder + float64 numpy DWT) on n_images images, one image per
+    """the oracle (C restatements of the Rust coder and of the PyWavelets transform, float64) on n_images images, one image per
     process over `cores` processes.  Returns (encode MP/s, decode MP/s, detail dict)."""
-    from oracle import spiht_oracle
+    from oracle import dwt_fast, spiht_oracle
     spiht_oracle.build()
+    dwt_fast.lib()
     jobs = [(i, size, bpp, wavelet, mode, seed) for i in range(n_images)]
     with mp.get_context("spawn").Pool(cores) as pool:
         pool.map(_cpu_worker, [(0, 64, bpp, wavelet, mode, seed)] * cores)   # warm the workers (imports, build)
@@ -186,7 +187,7 @@ def run_reference(args):
         "decode": {"value": round(statistics.mean(dvals), 3), "unit": "MP/s"},
         "cpu_baseline": {"value": round(value, 3), "unit": "MP/s", "cores": cores, "kind": "port",
                          "sample": f"{n_images} images of the workload per step, one image per process; "
-                                   "oracle/spiht_ref.c (restated Rust coder) + float64 numpy DWT",
+                                   "oracle/spiht_ref.c (restated Rust coder) + oracle/dwt_fast.c (restated PyWavelets transform, float64)",
                          "detail": detail},
         "e2e": {"value": round(value, 3), "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -419,7 +420,7 @@ def run_b200(args):
         line["cpu_baseline"] = {"value": round(enc_mps, 3), "unit": "MP/s", "cores": cores, "kind": "port",
                                 "decode_value": round(dec_mps, 3),
                                 "sample": f"{n_images} images of the workload, one image per process; "
-                                          "oracle/spiht_ref.c (restated Rust coder) + float64 numpy DWT",
+                                          "oracle/spiht_ref.c (restated Rust coder) + oracle/dwt_fast.c (restated PyWavelets transform, float64)",
                                 "detail": detail}
     print(json.dumps(line), flush=True)
     if use_dist:

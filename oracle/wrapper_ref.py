@@ -19,12 +19,17 @@ def dequantize(arr, q_scale=10.0):        # spiht_wrapper.py:13-14
 
 
 def forward_coeffs(image, wavelet="bior2.2", mode="reflect", level=None, quantization_scale=50.0,
-                   color_model=None, per_channel_quant_scales=None, return_float=False):
-    """spiht_wrapper.py:158-172 -> (int32 coeffs [c,Hc,Wc], ll_h, ll_w)"""
+                   color_model=None, per_channel_quant_scales=None, return_float=False, fast=False):
+    """spiht_wrapper.py:158-172 -> (int32 coeffs [c,Hc,Wc], ll_h, ll_w).  fast: the transform in compiled C
+    (oracle/dwt_fast.c, for the timed CPU baseline) instead of the numpy checker."""
     image = np.asarray(image, np.float64)
     if color_model is not None:
         image = ipt_ref.convert(image, "RGB", color_model)
-    coeffs = dwt_ref.wavedec2(image, wavelet, mode, level)
+    if fast:
+        from . import dwt_fast
+        coeffs = dwt_fast.wavedec2(image, wavelet, mode, level)
+    else:
+        coeffs = dwt_ref.wavedec2(image, wavelet, mode, level)
     ll_h, ll_w = coeffs[0].shape[1], coeffs[0].shape[2]
     arr = dwt_ref.coeffs_to_array(coeffs)
     if per_channel_quant_scales is not None:
@@ -50,14 +55,18 @@ def encode_image(image, wavelet="bior2.2", mode="reflect", level=None, quantizat
 
 
 def inverse_coeffs(rec_arr, h, w, wavelet="bior2.2", mode="reflect", level=None, quantization_scale=50.0,
-                   color_model=None, per_channel_quant_scales=None):
-    """spiht_wrapper.py:259-281"""
+                   color_model=None, per_channel_quant_scales=None, fast=False):
+    """spiht_wrapper.py:259-281.  fast: see forward_coeffs."""
     slices, _, _ = dwt_ref.get_slices_and_h_w(h, w, wavelet, mode, level)
     rec_arr = np.asarray(rec_arr, np.float64)
     if per_channel_quant_scales is not None:
         rec_arr = rec_arr / np.array(per_channel_quant_scales)[:, None, None]
     rec_arr = dequantize(rec_arr, quantization_scale)
-    img = dwt_ref.waverec2(dwt_ref.array_to_coeffs(rec_arr, slices), wavelet, mode)
+    if fast:
+        from . import dwt_fast
+        img = dwt_fast.waverec2(dwt_ref.array_to_coeffs(rec_arr, slices), wavelet, mode)
+    else:
+        img = dwt_ref.waverec2(dwt_ref.array_to_coeffs(rec_arr, slices), wavelet, mode)
     if color_model is not None:
         img = ipt_ref.convert(img, color_model, "RGB")
     return img

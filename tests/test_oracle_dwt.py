@@ -78,3 +78,30 @@ def test_wrapper_ref_roundtrip():
     rec_full = wrapper_ref.decode_image(wrapper_ref.encode_image(img))
     mse_full = np.mean((rec_full - img) ** 2)
     assert mse_full < 1e-3 and mse_full < mse1 < 0.05
+
+
+@pytest.mark.parametrize("shape,wavelet,mode,level", [
+    ((3, 64, 96), "bior2.2", "reflect", None),
+    ((1, 67, 131), "bior2.2", "reflect", 3),
+    ((2, 70, 70), "bior2.2", "symmetric", None),
+    ((3, 128, 64), "bior2.2", "periodization", None),
+    ((1, 131, 66), "bior4.4", "periodization", 2),
+    ((2, 128, 96), "bior4.4", "symmetric", None),
+    ((1, 200, 168), "bior6.8", "reflect", 2),
+])
+def test_compiled_transform_of_the_cpu_baseline_matches_the_checker(shape, wavelet, mode, level):
+    """oracle/dwt_fast.c (timed by bench.py's CPU legs) == oracle/dwt_ref.py (the checker) to rounding"""
+    from oracle import dwt_fast, dwt_ref, wrapper_ref
+    rng = np.random.default_rng(11)
+    x = rng.normal(size=shape)
+    a = dwt_ref.wavedec2(x, wavelet, mode, level)
+    b = dwt_fast.wavedec2(x, wavelet, mode, level)
+    assert len(a) == len(b)
+    assert np.abs(a[0] - b[0]).max() <= 1e-12
+    for ta, tb in zip(a[1:], b[1:]):
+        for u, v in zip(ta, tb):
+            assert u.shape == v.shape and np.abs(u - v).max() <= 1e-12
+    assert np.abs(dwt_ref.waverec2(a, wavelet, mode) - dwt_fast.waverec2(a, wavelet, mode)).max() <= 1e-12
+    c1, lh, lw = wrapper_ref.forward_coeffs(x, wavelet, mode, level)
+    c2, lh2, lw2 = wrapper_ref.forward_coeffs(x, wavelet, mode, level, fast=True)
+    assert (lh, lw) == (lh2, lw2) and c1.shape == c2.shape and np.abs(c1 - c2).max() <= 1
