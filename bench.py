@@ -163,7 +163,7 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    n_images = args.cpu_images or 2 * cores
+    n_images = args.cpu_images or 4 * cores
     workload = workload_name(args)
     vals, dvals = [], []
     t_all = time.perf_counter()
@@ -415,7 +415,7 @@ def run_b200(args):
                           "ms_per_step": round(dec_ms_max / args.steps, 4), "psnr_db": round(psnr, 2)}
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        n_images = args.cpu_images or 2 * cores
+        n_images = args.cpu_images or 4 * cores
         enc_mps, dec_mps, detail = cpu_reference_sample(S, args.bpp, args.wavelet, args.mode, n_images, cores)
         line["cpu_baseline"] = {"value": round(enc_mps, 3), "unit": "MP/s", "cores": cores, "kind": "port",
                                 "decode_value": round(dec_mps, 3),
