@@ -145,3 +145,31 @@ def test_config5_periodization_mixed_sizes(T, oracle, bpp):
     recs = spiht.decode_images(encs, st)
     ps = [_psnr(r[:, :im.shape[1], :im.shape[2]], im) for r, im in zip(recs, imgs)]
     assert min(ps) > 15
+
+
+def test_repeated_runs_are_bit_identical(T):
+    """the coder's passes are scans and compactions over many warps, the forward transform forks a side stream and
+    the decoder marks blocks with plain stores: repeated runs over the same batch must give the same bytes, the same
+    decoded coefficients and the same pixels every time (a race would show up as a difference)"""
+    torch = T
+    import spiht_b200 as spiht
+    from spiht_b200 import _lib, batch
+    from spiht_b200.utils import synthetic_images
+    B, S = 24, 256
+    px = synthetic_images(B, 3, S, S, seed=77)
+    st = spiht.SpihtSettings()
+    g = _lib.plan(S, S, "bior2.2", "reflect", None)
+    mb = int(S * S * 0.8)
+    ref = None
+    for it in range(12):
+        s, nbits, max_n, _, coeffs = batch.encode_images(px, g, st, mb)
+        nbytes = (nbits + 7) // 8
+        out, rec = batch.decode_images(s, nbytes, max_n, 3, g, st, dtype=torch.float32)
+        nb = int(nbytes.min())   # every image hits the budget: rows are written up to ceil(max_bits / 8) bytes
+        assert int(nbytes.max()) == nb
+        cur = (s[:, :nb].clone(), nbits.clone(), max_n.clone(), coeffs.clone(), rec.clone(), out.clone())
+        if ref is None:
+            ref = cur
+        else:
+            for a, b in zip(ref, cur):
+                assert torch.equal(a, b), f"run {it} differs from run 0"
