@@ -76,9 +76,7 @@ __global__ void __launch_bounds__(IV_WARPS * 32) dwt_inv_level_kernel(const InvK
     constexpr int NOUT = 32 - (HF - 1);
     // prefetch distance in rows and unroll of the streaming loop (a multiple of HF: static window and queue slots)
     // (6 rows ahead pay off on the latency-bound coarse levels; the float32 output level is issue-bound: 3)
-    constexpr int PD = HF == 3 ? (sizeof(Tout) == 8 ? 6 : 3) : HF;
-    constexpr int UN = PD;
-    static_assert(UN % HF == 0 && UN % PD == 0, "static slots");
+    constexpr int PD_FULL = HF == 3 ? (sizeof(Tout) == 8 ? 6 : 3) : HF;
     constexpr unsigned FULL = 0xffffffffu;
     long long task = (long long)blockIdx.x * IV_WARPS + (threadIdx.x >> 5);
     if (task >= p.ntasks) return;
@@ -136,6 +134,11 @@ __global__ void __launch_bounds__(IV_WARPS * 32) dwt_inv_level_kernel(const InvK
     // the streaming part, compiled twice: with and without the detail bands (warp-uniform choice)
     auto stream = [&](auto dzc) {
     constexpr bool DZ = decltype(dzc)::value;
+    // (without the detail bands a row costs one load and two registers: 12 rows ahead on the float32 output level, 6
+    // on the float64 ones -- measured)
+    constexpr int PD = (DZ && HF == 3) ? (sizeof(Tout) == 4 ? 12 : 6) : PD_FULL;
+    constexpr int UN = PD;
+    static_assert(UN % HF == 0 && UN % PD == 0, "static slots");
     struct Raw {
         int32_t ad, da, dd, aaq;
         double aa;
