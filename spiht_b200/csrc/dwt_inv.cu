@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(IV_WARPS * 32) dwt_inv_level_kernel(const InvK
     constexpr int NOUT = 32 - (HF - 1);
     // prefetch distance in rows and unroll of the streaming loop (a multiple of HF: static window and queue slots)
     // (6 rows ahead pay off on the latency-bound coarse levels; the float32 output level is issue-bound: 3)
-    constexpr int PD_FULL = HF == 3 ? (sizeof(Tout) == 8 ? 6 : 3) : HF;
+    constexpr int PD_FULL = HF == 3 ? (sizeof(Tout) == 8 ? 9 : 3) : HF;
     constexpr unsigned FULL = 0xffffffffu;
     long long task = (long long)blockIdx.x * IV_WARPS + (threadIdx.x >> 5);
     if (task >= p.ntasks) return;
