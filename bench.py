@@ -242,17 +242,24 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # clocks are sampled from the start of the warm-up to the end of the timed region: the GPU is under the
-    # same load throughout, and the timed region alone (K steps of a few ms) is shorter than one nvidia-smi
-    # period.  Warm-up runs at least W >= 3 steps and at least ~0.8 s so that several samples land under load.
+    # Warm-up: exactly max(W, 3) steps on every rank (every step posts a collective when N > 1, so the count
+    # must never depend on a per-rank clock).  nvidia-smi needs ~0.8 s under load to return a few samples and
+    # the timed region alone (K steps of a few ms) is shorter than one sampling period, so the warm-up is
+    # followed by untimed "soak" steps whose number rank 0 decides from its own clock and broadcasts.
     clocks = ClockSampler(local_rank)
     clocks.start()
+    n_warm = max(args.warmup, 3)
     t_warm = time.perf_counter()
-    n_warm = 0
-    while n_warm < max(args.warmup, 3) or (time.perf_counter() - t_warm < 0.8 and n_warm < 400):
+    for _ in range(n_warm):
         res = step()
         torch.cuda.synchronize()
-        n_warm += 1
+    per_step = (time.perf_counter() - t_warm) / n_warm
+    n_soak = torch.tensor([min(400, max(0, int(0.8 / max(per_step, 1e-4)) - n_warm))], dtype=torch.int64, device=dev)
+    if use_dist:
+        dist.broadcast(n_soak, src=0)
+    n_soak = int(n_soak.item())
+    for _ in range(n_soak):
+        res = step()
     barrier()
 
     # ---- timed region: K steps, CUDA events on the launching stream, stage timers on
@@ -381,7 +388,7 @@ def run_b200(args):
 
     line = {
         "metric": "encode megapixels/sec at %.3g bpp" % args.bpp, "value": round(value, 1), "unit": "MP/s",
-        "n_gpus": world, "steps": args.steps, "warmup": n_warm, "ms_per_step": round(ms_per_step, 4),
+        "n_gpus": world, "steps": args.steps, "warmup": n_warm, "soak_steps": n_soak, "ms_per_step": round(ms_per_step, 4),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64/int32",
         "data": "synthetic",
         "config": {"workload": workload_name(args), "global_batch": world * B, "max_bits": max_bits,

@@ -85,7 +85,9 @@ int spihtb_version(void);
 const char *spihtb_last_error(void);
 int spihtb_create(int device, spihtb_ctx **ctx);
 int spihtb_destroy(spihtb_ctx *ctx);
-/* run subsequent calls on `cuda_stream` (a cudaStream_t; NULL = legacy default stream) */
+/* run subsequent calls on `cuda_stream` (a cudaStream_t; NULL = legacy default stream).  A context owns one
+ * set of workspaces, so its calls are serialised: when the stream changes, the new stream first waits (event)
+ * for everything this context queued on the old one.  For concurrent calls use one context per stream. */
 int spihtb_set_stream(spihtb_ctx *ctx, void *cuda_stream);
 int spihtb_sync(spihtb_ctx *ctx);
 /* number of kernels this context has launched so far (bench.py `gpu_launches`) */
@@ -138,6 +140,11 @@ int spihtb_decode_coeffs(spihtb_ctx *ctx, const uint8_t *dev_in, uint64_t in_str
                          const int32_t *dev_n, int32_t B, int32_t c, int32_t h, int32_t w,
                          int32_t ll_h, int32_t ll_w, int32_t *dev_coeffs_out);
 
+/* Largest magnitude per image of a coefficient batch: dev_out uint32[B] = max |x| over the per_image int32 values
+ * of image b.  (encoder_decoder.rs:165 takes the same maximum; the host uses it to size the stream rows of an
+ * untruncated encode, spiht_wrapper.py:174-176 max_bits=None.)  B <= 65535. */
+int spihtb_max_abs(spihtb_ctx *ctx, const int32_t *dev_coeffs, int32_t B, uint64_t per_image, uint32_t *dev_out);
+
 /* ---- transform stages, DEVICE buffers ----------------------------------- */
 /* spiht_wrapper.py:158-172: optional RGB->colour (color_models.py:6-13), pywt.wavedec2 (:163),
  * pywt.coeffs_to_array (:165), per-channel scale (:167-170), quantize (:9-11, truncation toward
@@ -151,6 +158,14 @@ int spihtb_forward(spihtb_ctx *ctx, const void *dev_pixels, int32_t pixel_dtype,
 int spihtb_inverse(spihtb_ctx *ctx, const int32_t *dev_coeffs, int32_t B, int32_t C, const spihtb_geom *geom,
                    int32_t color_model, const double *ch_scales, double q,
                    void *dev_pixels_out, int32_t pixel_dtype);
+
+/* spiht/color_models.py:6-13  convert(im, src, dest) for the one colour model on the accelerated path:
+ * planar images [B][3][plane].  src_model / dst_model are SPIHTB_COLOR_NONE (= RGB) or SPIHTB_COLOR_IPT.
+ * RGB -> IPT: dev_in is in_dtype (F32 / F64 / U8), dev_out float64.  IPT -> RGB: dev_in float64 (in_dtype
+ * must be SPIHTB_F64), dev_out is out_dtype (F32 / F64).  Same models: a copy with conversion to out_dtype is
+ * not offered -- the call fails with SPIHTB_EINVAL. */
+int spihtb_convert_color(spihtb_ctx *ctx, const void *dev_in, int32_t in_dtype, int32_t B, uint64_t plane,
+                         int32_t src_model, int32_t dst_model, void *dev_out, int32_t out_dtype);
 
 /* ---- fused image path, DEVICE buffers ----------------------------------- */
 /* encode_image (spiht_wrapper.py:142-189) over a batch: forward + encode_coeffs.

@@ -7,8 +7,11 @@ absent from this image, so the published transform is restated: linear sRGB
 -> CIE XYZ with the 4-digit IEC 61966-2-1 matrix (no CCTF decoding, no
 chromatic adaptation), then Ebner & Fairchild (1998) IPT:
     LMS = M_xyz2lms . XYZ ; LMS' = sign(LMS) |LMS|^0.43 ; IPT = M_lms2ipt . LMS'
-The way back uses numpy-inverted IPT matrices and the hard-coded 4-digit
-XYZ -> sRGB matrix, which is not the exact inverse of the forward one.
+The way back uses numpy-inverted matrices throughout: colour-science 0.4.4
+defines MATRIX_XYZ_TO_sRGB = np.linalg.inv(MATRIX_sRGB_TO_XYZ)
+(colour/models/rgb/datasets/srgb.py; releases before 0.4 hard-coded the rounded
+4-digit inverse, which is not an exact inverse), so RGB -> IPT -> RGB is the
+identity to rounding.
 
 PARITY UNPINNED: the reference has no test on colour values.
 """
@@ -17,9 +20,7 @@ import numpy as np
 M_RGB_TO_XYZ = np.array([[0.4124, 0.3576, 0.1805],
                          [0.2126, 0.7152, 0.0722],
                          [0.0193, 0.1192, 0.9505]])
-M_XYZ_TO_RGB = np.array([[3.2406, -1.5372, -0.4986],
-                         [-0.9689, 1.8758, 0.0415],
-                         [0.0557, -0.2040, 1.0570]])
+M_XYZ_TO_RGB = np.linalg.inv(M_RGB_TO_XYZ)
 M_XYZ_TO_LMS = np.array([[0.4002, 0.7075, -0.0807],
                          [-0.2280, 1.1500, 0.0612],
                          [0.0000, 0.0000, 0.9184]])

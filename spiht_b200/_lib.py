@@ -48,7 +48,7 @@ EXPORTS = (
     "spihtb_sync", "spihtb_launch_count", "spihtb_plan", "spihtb_encode", "spihtb_decode",
     "spihtb_encode_coeffs", "spihtb_decode_coeffs", "spihtb_forward", "spihtb_inverse",
     "spihtb_encode_images", "spihtb_decode_images", "spihtb_stream_bound",
-    "spihtb_profile_enable", "spihtb_profile_read",
+    "spihtb_profile_enable", "spihtb_profile_read", "spihtb_max_abs", "spihtb_convert_color",
 )
 
 
@@ -88,6 +88,8 @@ def lib():
         L.spihtb_encode_images.argtypes = [vp, vp, i32, i32, i32, P(Geom), i32, P(dbl), dbl, u64, vp, vp,
                                            vp, u64, vp, vp, vp]
         L.spihtb_decode_images.argtypes = [vp, vp, u64, vp, vp, i32, i32, P(Geom), i32, P(dbl), dbl, vp, vp, i32]
+        L.spihtb_max_abs.argtypes = [vp, vp, i32, u64, vp]
+        L.spihtb_convert_color.argtypes = [vp, vp, i32, i32, u64, i32, i32, vp, i32]
         L.spihtb_stream_bound.argtypes = [i32, i32, i32, i32, i32]
         L.spihtb_stream_bound.restype = u64
         L.spihtb_profile_enable.argtypes = [vp, ctypes.c_int]

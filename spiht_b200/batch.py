@@ -88,6 +88,18 @@ def inverse(coeffs, geom, settings, dtype=torch.float64):
     return out
 
 
+def max_abs(coeffs):
+    """spihtb_max_abs: per-image maximum magnitude of an int32 [B,...] coefficient batch -> int64 [B] (CUDA)"""
+    _check_cuda(coeffs, "coeffs")
+    if coeffs.dtype != torch.int32:
+        raise TypeError("coeffs must be int32")
+    B = coeffs.shape[0]
+    ctx = _ctx_for(coeffs)
+    out = torch.empty((B,), dtype=torch.int32, device=coeffs.device)   # uint32 bit patterns, all < 2^31
+    _lib.check(_lib.lib().spihtb_max_abs(ctx.handle, _ptr(coeffs), B, coeffs[0].numel(), _ptr(out)))
+    return out.to(torch.int64) & 0xffffffff
+
+
 def _max_bits_args(max_bits, B, device):
     if isinstance(max_bits, torch.Tensor):
         mb = max_bits.to(device=device, dtype=torch.int64).contiguous()

@@ -43,7 +43,9 @@ static int check_coder_geom(int c, int h, int w, int ll_h, int ll_w)
         set_error("assertion failed: ll_h > 1 && ll_w > 1 (got %d, %d)", ll_h, ll_w);
         return SPIHTB_ELL;
     }
-    if (2LL * ll_h + (ll_h & 1) > h || 2LL * ll_w + (ll_w & 1) > w) {
+    // lowest offspring row of an LL root: 2 ll_h - 1 (ll_h even) or 2 ll_h - 2 (ll_h odd: the last odd root is
+    // ll_h - 2, the even root ll_h - 1 has its block at rows ll_h - 1, ll_h)
+    if (2LL * ll_h - (ll_h & 1) > h || 2LL * ll_w - (ll_w & 1) > w) {
         set_error("LL band %dx%d too large for a %dx%d array: root offspring out of bounds", ll_h, ll_w, h, w);
         return SPIHTB_EGEOM;
     }
@@ -246,6 +248,7 @@ int spihtb_create(int device, spihtb_ctx **out)
     SPIHTB_CUDA_CHECK(cudaStreamCreateWithFlags(&c->aux, cudaStreamNonBlocking));
     SPIHTB_CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     SPIHTB_CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+    SPIHTB_CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_order, cudaEventDisableTiming));
     *out = c;
     return SPIHTB_OK;
 }
@@ -260,6 +263,7 @@ int spihtb_destroy(spihtb_ctx *ctx)
         cudaStreamDestroy(ctx->aux);
         cudaEventDestroy(ctx->ev_fork);
         cudaEventDestroy(ctx->ev_join);
+        cudaEventDestroy(ctx->ev_order);
     }
     DevBuf *bufs[] = {&ctx->pyr, &ctx->lists, &ctx->misc, &ctx->tmpa, &ctx->tmpb, &ctx->io, &ctx->io2, &ctx->fix, &ctx->u8lut, &ctx->blk};
     for (DevBuf *b : bufs)
@@ -280,7 +284,15 @@ int spihtb_set_stream(spihtb_ctx *ctx, void *cuda_stream)
         set_error("ctx is null");
         return SPIHTB_EINVAL;
     }
-    ctx->stream = static_cast<cudaStream_t>(cuda_stream);
+    cudaStream_t ns = static_cast<cudaStream_t>(cuda_stream);
+    if (ns != ctx->stream) {
+        // The workspaces (pyramid planes, lists, scratch, work counters) are shared by every call on this context:
+        // work already queued on the old stream must finish before anything queued on the new one touches them.
+        SPIHTB_CUDA_CHECK(cudaSetDevice(ctx->device));
+        SPIHTB_CUDA_CHECK(cudaEventRecord(ctx->ev_order, ctx->stream));
+        SPIHTB_CUDA_CHECK(cudaStreamWaitEvent(ns, ctx->ev_order, 0));
+        ctx->stream = ns;
+    }
     return SPIHTB_OK;
 }
 
@@ -409,6 +421,16 @@ int spihtb_encode_coeffs(spihtb_ctx *ctx, const int32_t *dev_coeffs, int32_t B, 
     if (rc) return rc;
     return encode_with_pyramid(ctx, dev_coeffs, B, c, h, w, ll_h, ll_w, pb, false, max_bits, dev_max_bits, dev_out,
                                out_stride, dev_nbits, dev_max_n, dev_status);
+}
+
+int spihtb_max_abs(spihtb_ctx *ctx, const int32_t *dev_coeffs, int32_t B, uint64_t per_image, uint32_t *dev_out)
+{
+    if (!ctx || !dev_coeffs || !dev_out || B <= 0 || B > 65535 || per_image == 0) {
+        set_error("null pointer, empty batch or more than 65535 images");
+        return SPIHTB_EINVAL;
+    }
+    SPIHTB_CUDA_CHECK(cudaSetDevice(ctx->device));
+    return launch_max_abs(ctx, dev_coeffs, B, (size_t)per_image, dev_out);
 }
 
 int spihtb_decode_coeffs(spihtb_ctx *ctx, const uint8_t *dev_in, uint64_t in_stride, const uint64_t *dev_nbytes,
@@ -573,6 +595,32 @@ int spihtb_inverse(spihtb_ctx *ctx, const int32_t *dev_coeffs, int32_t B, int32_
     if (rc) return rc;
     SPIHTB_CUDA_CHECK(cudaSetDevice(ctx->device));
     return launch_inverse(ctx, dev_coeffs, x, dev_pixels_out);
+}
+
+int spihtb_convert_color(spihtb_ctx *ctx, const void *dev_in, int32_t in_dtype, int32_t B, uint64_t plane,
+                         int32_t src_model, int32_t dst_model, void *dev_out, int32_t out_dtype)
+{
+    if (!ctx || !dev_in || !dev_out || B <= 0 || plane == 0) {
+        set_error("null pointer or empty batch");
+        return SPIHTB_EINVAL;
+    }
+    SPIHTB_CUDA_CHECK(cudaSetDevice(ctx->device));
+    if (src_model == SPIHTB_COLOR_NONE && dst_model == SPIHTB_COLOR_IPT) {
+        if ((in_dtype != SPIHTB_F32 && in_dtype != SPIHTB_F64 && in_dtype != SPIHTB_U8) || out_dtype != SPIHTB_F64) {
+            set_error("RGB -> IPT takes float32 / float64 / uint8 pixels and writes float64");
+            return SPIHTB_EINVAL;
+        }
+        return launch_rgb_to_ipt(ctx, dev_in, in_dtype, static_cast<double *>(dev_out), (size_t)plane, B);
+    }
+    if (src_model == SPIHTB_COLOR_IPT && dst_model == SPIHTB_COLOR_NONE) {
+        if (in_dtype != SPIHTB_F64 || (out_dtype != SPIHTB_F32 && out_dtype != SPIHTB_F64)) {
+            set_error("IPT -> RGB takes float64 and writes float32 / float64");
+            return SPIHTB_EINVAL;
+        }
+        return launch_ipt_to_rgb(ctx, static_cast<const double *>(dev_in), dev_out, out_dtype, (size_t)plane, B);
+    }
+    set_error("unsupported colour conversion %d -> %d (RGB <-> IPT only)", src_model, dst_model);
+    return SPIHTB_EINVAL;
 }
 
 int spihtb_encode_images(spihtb_ctx *ctx, const void *dev_pixels, int32_t pixel_dtype, int32_t B, int32_t C,

@@ -48,6 +48,7 @@ struct spihtb_ctx {
     // transform runs beside the first DWT level); fork / join events
     cudaStream_t aux = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_order = nullptr;  // orders the shared workspaces across a change of stream (spihtb_set_stream)
     int64_t launches = 0;
     // grow-only device workspaces
     spihtb::DevBuf pyr;      // DP / LP planes + LL-root planes + per-image max

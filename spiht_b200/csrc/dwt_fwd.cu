@@ -609,37 +609,6 @@ __global__ void __launch_bounds__(256) u8_to_f64_kernel(const uint8_t *__restric
         dst[t] = (double)src[t] / 255.0;
 }
 
-// ---- RGB -> IPT (color_models.py:6-13 -> colour.convert(.., 'RGB', 'IPT')) ----
-// linear sRGB -> XYZ (4-digit IEC matrix) -> LMS -> sign(x)|x|^0.43 -> IPT, float64.
-__device__ __forceinline__ double spow(double a, double e) { return a == 0.0 ? 0.0 : copysign(pow(fabs(a), e), a); }
-
-template <typename Tin>
-__global__ void __launch_bounds__(256) rgb_to_ipt_kernel(const Tin *__restrict__ src, double *__restrict__ dst,
-                                                         size_t plane, size_t nimg)
-{
-    const size_t total = plane * nimg;
-    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
-        const size_t b = t / plane, o = t - b * plane;
-        const Tin *s = src + b * 3 * plane + o;
-        double R = (double)s[0], G = (double)s[plane], B = (double)s[2 * plane];
-        if (sizeof(Tin) == 1) {  // uint8 pixels: imload's im / 255 (IEEE division, as numpy's)
-            R /= 255.0;
-            G /= 255.0;
-            B /= 255.0;
-        }
-        const double X = 0.4124 * R + 0.3576 * G + 0.1805 * B;
-        const double Y = 0.2126 * R + 0.7152 * G + 0.0722 * B;
-        const double Z = 0.0193 * R + 0.1192 * G + 0.9505 * B;
-        const double L = spow(0.4002 * X + 0.7075 * Y + -0.0807 * Z, 0.43);
-        const double M = spow(-0.2280 * X + 1.1500 * Y + 0.0612 * Z, 0.43);
-        const double S = spow(0.0 * X + 0.0 * Y + 0.9184 * Z, 0.43);
-        double *d = dst + b * 3 * plane + o;
-        d[0] = 0.4000 * L + 0.4000 * M + 0.2000 * S;
-        d[plane] = 4.4550 * L + -4.8510 * M + 0.3960 * S;
-        d[2 * plane] = 0.8056 * L + 0.3572 * M + -1.1628 * S;
-    }
-}
-
 template <typename Tin, int WID>
 static int launch_level(spihtb_ctx *ctx, FwdK k, int nz)
 {
@@ -837,17 +806,9 @@ int launch_forward(spihtb_ctx *ctx, const void *pixels, const XformArgs &x, int3
         const size_t plane = (size_t)g.h * g.w;
         rc = ctx->ensure(ctx->io2, (size_t)nz * plane * sizeof(double) + 256);
         if (rc) return rc;
-        const unsigned nb = (unsigned)std::min<size_t>((plane * x.B + 255) / 256, (size_t)ctx->sm_count * 32);
-        if (src_is_f64)
-            rgb_to_ipt_kernel<double><<<nb, 256, 0, ctx->stream>>>(static_cast<const double *>(pixels),
-                                                                   static_cast<double *>(ctx->io2.p), plane, x.B);
-        else if (x.pixel_dtype == SPIHTB_U8)
-            rgb_to_ipt_kernel<uint8_t><<<nb, 256, 0, ctx->stream>>>(static_cast<const uint8_t *>(pixels),
-                                                                    static_cast<double *>(ctx->io2.p), plane, x.B);
-        else
-            rgb_to_ipt_kernel<float><<<nb, 256, 0, ctx->stream>>>(static_cast<const float *>(pixels),
-                                                                  static_cast<double *>(ctx->io2.p), plane, x.B);
-        ctx->launches++;
+        rc = launch_rgb_to_ipt(ctx, pixels, src_is_f64 ? SPIHTB_F64 : x.pixel_dtype, static_cast<double *>(ctx->io2.p),
+                               plane, x.B);
+        if (rc) return rc;
         src = ctx->io2.p;
         src_is_f64 = true;
     }

@@ -264,52 +264,6 @@ __global__ void __launch_bounds__(IV_WARPS * 32) dwt_inv_level_kernel(const InvK
         stream(std::false_type{});
 }
 
-// ---- IPT -> RGB (colour.convert(.., 'IPT', 'RGB')): numpy-inverted IPT matrices,
-// exponent 1/0.43, then the hard-coded 4-digit XYZ -> sRGB matrix ----
-struct IptInv {
-    double ipt2lms[9];  // inv(M_LMS'->IPT)
-    double lms2xyz[9];  // inv(M_XYZ->LMS)
-};
-__device__ __forceinline__ double spow_inv(double a, double e) { return a == 0.0 ? 0.0 : copysign(pow(fabs(a), e), a); }
-
-template <typename Tout>
-__global__ void __launch_bounds__(256) ipt_to_rgb_kernel(const double *__restrict__ src, Tout *__restrict__ dst,
-                                                         size_t plane, size_t nimg, const IptInv mi)
-{
-    const size_t total = plane * nimg;
-    const double e = 1.0 / 0.43;
-    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
-        const size_t b = t / plane, o = t - b * plane;
-        const double *s = src + b * 3 * plane + o;
-        const double I = s[0], P = s[plane], T = s[2 * plane];
-        const double L = spow_inv(mi.ipt2lms[0] * I + mi.ipt2lms[1] * P + mi.ipt2lms[2] * T, e);
-        const double M = spow_inv(mi.ipt2lms[3] * I + mi.ipt2lms[4] * P + mi.ipt2lms[5] * T, e);
-        const double Sv = spow_inv(mi.ipt2lms[6] * I + mi.ipt2lms[7] * P + mi.ipt2lms[8] * T, e);
-        const double X = mi.lms2xyz[0] * L + mi.lms2xyz[1] * M + mi.lms2xyz[2] * Sv;
-        const double Y = mi.lms2xyz[3] * L + mi.lms2xyz[4] * M + mi.lms2xyz[5] * Sv;
-        const double Z = mi.lms2xyz[6] * L + mi.lms2xyz[7] * M + mi.lms2xyz[8] * Sv;
-        Tout *d = dst + b * 3 * plane + o;
-        d[0] = (Tout)(3.2406 * X + -1.5372 * Y + -0.4986 * Z);
-        d[plane] = (Tout)(-0.9689 * X + 1.8758 * Y + 0.0415 * Z);
-        d[2 * plane] = (Tout)(0.0557 * X + -0.2040 * Y + 1.0570 * Z);
-    }
-}
-
-static void inv3(const double a[9], double r[9])
-{
-    const double det = a[0] * (a[4] * a[8] - a[5] * a[7]) - a[1] * (a[3] * a[8] - a[5] * a[6]) +
-                       a[2] * (a[3] * a[7] - a[4] * a[6]);
-    r[0] = (a[4] * a[8] - a[5] * a[7]) / det;
-    r[1] = (a[2] * a[7] - a[1] * a[8]) / det;
-    r[2] = (a[1] * a[5] - a[2] * a[4]) / det;
-    r[3] = (a[5] * a[6] - a[3] * a[8]) / det;
-    r[4] = (a[0] * a[8] - a[2] * a[6]) / det;
-    r[5] = (a[2] * a[3] - a[0] * a[5]) / det;
-    r[6] = (a[3] * a[7] - a[4] * a[6]) / det;
-    r[7] = (a[1] * a[6] - a[0] * a[7]) / det;
-    r[8] = (a[0] * a[4] - a[1] * a[3]) / det;
-}
-
 template <int WID>
 static int launch_inv_level(spihtb_ctx *ctx, InvK k, int nz, bool out_f32)
 {
@@ -424,19 +378,8 @@ int launch_inverse(spihtb_ctx *ctx, const int32_t *coeffs, const XformArgs &x, v
         a_w = k.ow;
     }
     if (color) {
-        IptInv mi;
-        const double lms2ipt[9] = {0.4000, 0.4000, 0.2000, 4.4550, -4.8510, 0.3960, 0.8056, 0.3572, -1.1628};
-        const double xyz2lms[9] = {0.4002, 0.7075, -0.0807, -0.2280, 1.1500, 0.0612, 0.0, 0.0, 0.9184};
-        inv3(lms2ipt, mi.ipt2lms);
-        inv3(xyz2lms, mi.lms2xyz);
-        const unsigned nb = (unsigned)std::min<size_t>((img * x.B + 255) / 256, (size_t)ctx->sm_count * 32);
-        if (x.pixel_dtype == SPIHTB_F32)
-            ipt_to_rgb_kernel<float><<<nb, 256, 0, ctx->stream>>>(static_cast<const double *>(ctx->io2.p),
-                                                                  static_cast<float *>(pixels_out), img, x.B, mi);
-        else
-            ipt_to_rgb_kernel<double><<<nb, 256, 0, ctx->stream>>>(static_cast<const double *>(ctx->io2.p),
-                                                                   static_cast<double *>(pixels_out), img, x.B, mi);
-        ctx->launches++;
+        rc = launch_ipt_to_rgb(ctx, static_cast<const double *>(ctx->io2.p), pixels_out, x.pixel_dtype, img, x.B);
+        if (rc) return rc;
     }
     ctx->stage_end(7);
     SPIHTB_CUDA_CHECK(cudaGetLastError());

@@ -16,6 +16,13 @@ struct FixRect {
 int launch_pyr_fix(spihtb_ctx *ctx, const int32_t *coeffs, int nz, int H, int W, uint8_t *dp, const FixRect *dev_rects,
                    const uint32_t *dev_prefix, int nrect, uint32_t total);
 
+// out[b] = max |x| over image b's per_image coefficients
+int launch_max_abs(spihtb_ctx *ctx, const int32_t *coeffs, int B, size_t per_image, uint32_t *out);
+
+// ---- color.cu: stand-alone RGB <-> IPT passes over planar [B][3][plane] images
+int launch_rgb_to_ipt(spihtb_ctx *ctx, const void *src, int src_dtype, double *dst, size_t plane, int B);
+int launch_ipt_to_rgb(spihtb_ctx *ctx, const double *src, void *dst, int dst_dtype, size_t plane, int B);
+
 // ---- spiht_enc.cu
 struct EncArgs {
     const int32_t *coeffs;  // [B][C][H][W]

@@ -323,4 +323,36 @@ int launch_pyramid(spihtb_ctx *ctx, const int32_t *coeffs, int B, int C, int H, 
     return SPIHTB_OK;
 }
 
+// ---- per-image maximum magnitude of a coefficient batch (spihtb_max_abs): sizes the stream rows of an
+// untruncated encode.  gridDim.y = images; blocks of an image stride over its coefficients.
+__global__ void __launch_bounds__(256) max_abs_kernel(const int32_t *__restrict__ coeffs, size_t per_image,
+                                                      uint32_t *__restrict__ out)
+{
+    __shared__ uint32_t s_max[8];
+    const int32_t *p = coeffs + (size_t)blockIdx.y * per_image;
+    uint32_t m = 0;
+    for (size_t t = (size_t)blockIdx.x * 256 + threadIdx.x; t < per_image; t += (size_t)gridDim.x * 256)
+        m = max(m, absu(__ldg(p + t)));
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, d));
+    if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) t = max(t, s_max[q]);
+        if (t) atomicMax(out + blockIdx.y, t);
+    }
+}
+
+int launch_max_abs(spihtb_ctx *ctx, const int32_t *coeffs, int B, size_t per_image, uint32_t *out)
+{
+    SPIHTB_CUDA_CHECK(cudaMemsetAsync(out, 0, sizeof(uint32_t) * (size_t)B, ctx->stream));
+    const unsigned gx = (unsigned)std::min<size_t>((per_image + 256 * 8 - 1) / (256 * 8), 1024);
+    max_abs_kernel<<<dim3(gx ? gx : 1, (unsigned)B), 256, 0, ctx->stream>>>(coeffs, per_image, out);
+    ctx->launches++;
+    SPIHTB_CUDA_CHECK(cudaGetLastError());
+    return SPIHTB_OK;
+}
+
 }  // namespace spihtb

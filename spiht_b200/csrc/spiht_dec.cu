@@ -64,22 +64,31 @@ struct DecK {
     unsigned int *counter;
 };
 
-// per-phase cycle counters of image 0's CTA (tools/dec_phases.py); compiled in, costs a few clock reads per pass
+// per-phase cycle counters of image 0's CTA (tools/dec_phases.py): debug builds only (-DSPIHTB_PROF); release
+// builds compile them out and do not export spihtb_debug_dec_prof
+#ifdef SPIHTB_PROF
 __device__ unsigned long long g_dec_prof[16];
 #define DEC_PROF_T0() const long long _t0 = clock64()
 #define DEC_PROF_ADD(slot)                                                        \
     do {                                                                          \
         if (tid == 0 && b == 0) g_dec_prof[slot] += (unsigned long long)(clock64() - _t0); \
     } while (0)
-#ifdef SPIHTB_DEC_CHAIN_COUNTS
-#define DEC_CHAIN_CNT(x) ((x) += 1)
-#else
-#define DEC_CHAIN_CNT(x) ((void)0)
-#endif
 #define DEC_PROF_CNT(slot, v)                                  \
     do {                                                       \
         if (tid == 0 && b == 0) g_dec_prof[slot] += (v);       \
     } while (0)
+#define DEC_PROF_MARK(name) const long long name = clock64()
+#define DEC_PROF_SINCE(slot, name)                                                        \
+    do {                                                                                  \
+        if (tid == 0 && b == 0) g_dec_prof[slot] += (unsigned long long)(clock64() - name); \
+    } while (0)
+#else
+#define DEC_PROF_T0() do { } while (0)
+#define DEC_PROF_ADD(slot) do { } while (0)
+#define DEC_PROF_CNT(slot, v) do { } while (0)
+#define DEC_PROF_MARK(name) do { } while (0)
+#define DEC_PROF_SINCE(slot, name) do { } while (0)
+#endif
 
 __device__ __forceinline__ uint32_t lds_u8(uint32_t addr)
 {
@@ -338,7 +347,7 @@ __global__ void __launch_bounds__(DEC_NT, 2) spiht_decode_kernel(const DecK p)
         __syncthreads();
 
         uint64_t pos = 0;  // uniform: next unread bit
-        const long long _timg = clock64();
+        DEC_PROF_MARK(_timg);
         for (; pos < limit; --n) {
             const int32_t basev = n == 0 ? 1 : (int32_t)((1u << (n - 1)) + (1u << n));
             const uint32_t lsp_len0 = lsp_len;
@@ -535,7 +544,7 @@ __global__ void __launch_bounds__(DEC_NT, 2) spiht_decode_kernel(const DecK p)
                         DEC_PROF_ADD(1);
                         // ---- chain: one thread jumps from fired A set to fired A set
                         if (tid == 0) {
-                            const long long _tc = clock64();
+                            DEC_PROF_MARK(_tc);
                             // Everything is kept MSB-first so that the next fired A set is one
                             // count-leading-zeros away.  r0, r1 (r2 prefetched): stream words, sS = consumed
                             // bits of r0; t0, t1 (t2): set-type words, sT likewise; all from shared memory
@@ -557,10 +566,8 @@ __global__ void __launch_bounds__(DEC_NT, 2) spiht_decode_kernel(const DecK p)
                             // bits consumed: every entry one, every fired A set its child bits
                             s_chain_p = pos + used;
                             s_na = 0;
-                            if (b == 0) {
-                                g_dec_prof[2] += (unsigned long long)(clock64() - _tc);
-                                g_dec_prof[11] += 1;
-                            }
+                            DEC_PROF_SINCE(2, _tc);
+                            DEC_PROF_CNT(11, 1);
                         }
                         __syncthreads();
                         const uint64_t p_base = pos;
@@ -579,7 +586,7 @@ __global__ void __launch_bounds__(DEC_NT, 2) spiht_decode_kernel(const DecK p)
                             if (tid < DEC_CH / 32) s_grp[tid] = (uint32_t)ex;
                         }
                         __syncthreads();
-                        const long long _tb = clock64();
+                        DEC_PROF_MARK(_tb);
                         // ---- every entry: its own bit, then the fired sets' records
                         for (uint32_t eb = 0; eb < cnt; eb += DEC_NT) {
                             const uint32_t e = eb + tid;
@@ -684,10 +691,8 @@ __global__ void __launch_bounds__(DEC_NT, 2) spiht_decode_kernel(const DecK p)
                             }
                         }
                         __syncthreads();  // s_x / s_tmask / s_grp are rewritten by the next round
-                        if (tid == 0 && b == 0) {
-                            g_dec_prof[3] += (unsigned long long)(clock64() - _tb);
-                            g_dec_prof[12] += (cnt + DEC_NT - 1) / DEC_NT;
-                        }
+                        DEC_PROF_SINCE(3, _tb);
+                        DEC_PROF_CNT(12, (cnt + DEC_NT - 1) / DEC_NT);
                         if (pos >= limit) ended = true;
                     }
                     uint32_t *old = cur;
@@ -758,10 +763,11 @@ __global__ void __launch_bounds__(DEC_NT, 2) spiht_decode_kernel(const DecK p)
                 }
             }
         }
-        if (tid == 0 && b == 0) g_dec_prof[5] += (unsigned long long)(clock64() - _timg);
+        DEC_PROF_SINCE(5, _timg);
     }
 }
 
+#ifdef SPIHTB_PROF
 // debug: read and clear the phase counters (tools/dec_phases.py)
 extern "C" int spihtb_debug_dec_prof(unsigned long long *out16)
 {
@@ -770,6 +776,7 @@ extern "C" int spihtb_debug_dec_prof(unsigned long long *out16)
     if (cudaMemcpyToSymbol(g_dec_prof, z, sizeof(z)) != cudaSuccess) return SPIHTB_ECUDA;
     return SPIHTB_OK;
 }
+#endif
 
 int launch_decode(spihtb_ctx *ctx, const DecArgs &a)
 {

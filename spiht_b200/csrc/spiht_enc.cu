@@ -114,6 +114,9 @@ __device__ __forceinline__ void bw_flush(uint32_t *ring, uint32_t *outrow, uint6
     wflushed = wend;
 }
 
+// Phase cycle counters of image 0's CTA: debug builds only (-DSPIHTB_PROF, python -m spiht_b200.build -DSPIHTB_PROF).
+// Release builds compile them out entirely; the symbols below are not part of the C ABI.
+#ifdef SPIHTB_PROF
 __device__ unsigned long long g_enc_prof[16];
 extern "C" int spihtb_debug_enc_prof(unsigned long long *out16)
 {
@@ -123,17 +126,12 @@ extern "C" int spihtb_debug_enc_prof(unsigned long long *out16)
     return SPIHTB_OK;
 }
 #define ENC_T0() const long long _t0 = clock64(); [[maybe_unused]] long long _tl = _t0
-// lap timer (debug builds only): cycles since the previous lap of this chunk into g_enc_prof[slot]
-#ifdef SPIHTB_ENC_LAPS
 #define ENC_LAP(slot)                                                   \
     do {                                                                \
         const long long _n = clock64();                                 \
         if (tid == 0 && b == 0) g_enc_prof[slot] += (unsigned long long)(_n - _tl); \
         _tl = _n;                                                       \
     } while (0)
-#else
-#define ENC_LAP(slot) do { } while (0)
-#endif
 #define ENC_ADD(slot, cnt)                                                              \
     do {                                                                                \
         if (tid == 0 && b == 0) {                                                       \
@@ -141,6 +139,18 @@ extern "C" int spihtb_debug_enc_prof(unsigned long long *out16)
             g_enc_prof[slot + 8] += (cnt);                                              \
         }                                                                               \
     } while (0)
+#define ENC_IMG_T0() const long long _timg = clock64()
+#define ENC_IMG_ADD()                                                                        \
+    do {                                                                                     \
+        if (b == 0) g_enc_prof[3] += (unsigned long long)(clock64() - _timg);                \
+    } while (0)
+#else
+#define ENC_T0() do { } while (0)
+#define ENC_LAP(slot) do { } while (0)
+#define ENC_ADD(slot, cnt) do { } while (0)
+#define ENC_IMG_T0() do { } while (0)
+#define ENC_IMG_ADD() do { } while (0)
+#endif
 
 __global__ void __launch_bounds__(ENC_NT, 2) spiht_encode_kernel(const EncK p)
 {
@@ -186,7 +196,7 @@ __global__ void __launch_bounds__(ENC_NT, 2) spiht_encode_kernel(const EncK p)
 
         for (int i = tid; i < ENC_RING; i += ENC_NT) s_ring[i] = 0;
         uint64_t wflushed = 0, bitpos = 0;
-        const long long _timg = clock64();
+        ENC_IMG_T0();
 
         // ---- list initialisation (encoder_decoder.rs:170-190): i, j, channel innermost
         const uint32_t T0 = ll_h * ll_w * C;
@@ -494,7 +504,7 @@ __global__ void __launch_bounds__(ENC_NT, 2) spiht_encode_kernel(const EncK p)
             p.nbits[b] = end;
             p.max_n[b] = max_n;
             if (p.status) p.status[b] = (bitpos >= limit && want > cap_bits) ? 1 : 0;
-            if (b == 0) g_enc_prof[3] += (unsigned long long)(clock64() - _timg);
+            ENC_IMG_ADD();
         }
         __syncthreads();
     }

@@ -179,11 +179,19 @@ def encode_image(image: np.ndarray, spiht_settings: SpihtSettings = SpihtSetting
 
 
 def encode_images(images, spiht_settings: SpihtSettings = SpihtSettings(), level: Optional[int] = None,
-                  max_bits: Optional[int] = None) -> List[EncodingResult]:
+                  max_bits=None) -> List[EncodingResult]:
     """Batched encode_image.  images: array/tensor (B,C,H,W), or a sequence of
-    (C,H,W) images (shapes may differ; equal shapes are encoded together)."""
+    (C,H,W) images (shapes may differ; equal shapes are encoded together).
+    max_bits: None (no limit), one budget for every image, or a sequence with one budget per image."""
     from . import batch
     torch = _torch()
+    per_image = None
+    if max_bits is not None and not np.isscalar(max_bits):
+        per_image = [int(m) for m in max_bits]
+        if len(per_image) != len(images):
+            raise ValueError("max_bits must be a scalar or have one entry per image")
+        if any(m <= 0 for m in per_image):
+            raise ValueError("per-image max_bits must be positive")
     if isinstance(images, (list, tuple)):
         for im in images:
             if im.ndim != 3:
@@ -195,7 +203,8 @@ def encode_images(images, spiht_settings: SpihtSettings = SpihtSettings(), level
         for _, idxs in groups.items():
             ims = [images[i] for i in idxs]
             stack = torch.stack(ims) if isinstance(ims[0], torch.Tensor) else np.stack(ims)
-            for i, r in zip(idxs, encode_images(stack, spiht_settings, level, max_bits)):
+            mb = max_bits if per_image is None else [per_image[i] for i in idxs]
+            for i, r in zip(idxs, encode_images(stack, spiht_settings, level, mb)):
                 results[i] = r
         return results  # type: ignore[return-value]
     if images.ndim != 4:
@@ -205,21 +214,29 @@ def encode_images(images, spiht_settings: SpihtSettings = SpihtSettings(), level
     g = _geom(h, w, spiht_settings, level)
     if max_bits is None:
         max_bits = _VERY_LARGE
-    budget = int(max_bits)
     bound = 8 * int(_lib.lib().spihtb_stream_bound(c, g.enc_h, g.enc_w, g.ll_h, g.ll_w))
-    host_side = not (isinstance(images, torch.Tensor) and images.is_cuda)
-    if host_side and 0 < budget <= bound and B >= 2 * _PIPE_CHUNK:
-        return _encode_host_pipelined(images, g, spiht_settings, budget, level)
-    pixels = _to_device_pixels(images)
-
-    if budget == 0 or budget > bound:
-        # untruncated: run the transform first, size the rows from the largest coefficient
-        coeffs = batch.forward(pixels, g, spiht_settings)
-        planes = int(coeffs.abs().max().item()).bit_length() + 1
-        stride = (bound // 31 * min(planes + 1, 31) // 8 + 64) // 8 * 8
-        streams, nbits, max_n, status = batch.encode_coeffs(coeffs, g.ll_h, g.ll_w, budget, out_stride=stride)
+    if per_image is not None:
+        # one budget per image (device array); rows sized for the largest, never beyond the full-encode bound
+        pixels = _to_device_pixels(images)
+        budgets = torch.tensor([min(m, bound) for m in per_image], dtype=torch.int64, device=pixels.device)
+        stride = batch.stream_stride(min(max(per_image), bound), c, g)
+        streams, nbits, max_n, status, _ = batch.encode_images(pixels, g, spiht_settings, budgets, out_stride=stride)
+        if max(per_image) >= bound:
+            status = torch.zeros_like(status)      # a budget at the bound cannot truncate
     else:
-        streams, nbits, max_n, status, _ = batch.encode_images(pixels, g, spiht_settings, budget)
+        budget = int(max_bits)
+        host_side = not (isinstance(images, torch.Tensor) and images.is_cuda)
+        if host_side and 0 < budget <= bound and B >= 2 * _PIPE_CHUNK:
+            return _encode_host_pipelined(images, g, spiht_settings, budget, level)
+        pixels = _to_device_pixels(images)
+        if budget == 0 or budget > bound:
+            # untruncated: run the transform first, size the rows from the largest coefficient
+            coeffs = batch.forward(pixels, g, spiht_settings)
+            planes = int(batch.max_abs(coeffs).cpu().numpy().max()).bit_length() + 1
+            stride = (bound // 31 * min(planes + 1, 31) // 8 + 64) // 8 * 8
+            streams, nbits, max_n, status = batch.encode_coeffs(coeffs, g.ll_h, g.ll_w, budget, out_stride=stride)
+        else:
+            streams, nbits, max_n, status, _ = batch.encode_images(pixels, g, spiht_settings, budget)
     nbits_h = nbits.cpu().numpy()
     max_n_h = max_n.cpu().numpy()
     if int(status.max().item()) != 0:

@@ -34,3 +34,16 @@ def oracle():
     from oracle import spiht_oracle
     spiht_oracle.lib()
     return spiht_oracle
+
+
+def record_count(name, **values):
+    """append a measured parity figure (e.g. quantised-coefficient mismatches against the float64 oracle) to
+    gpurun_out/parity_counts.jsonl, so that a GPU run leaves the numbers behind (copied to profiles/)"""
+    import json
+    out = os.path.join(ROOT, "gpurun_out")
+    try:
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, "parity_counts.jsonl"), "a") as f:
+            f.write(json.dumps(dict(name=name, **values)) + "\n")
+    except OSError:
+        pass

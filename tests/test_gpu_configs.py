@@ -96,6 +96,9 @@ def test_config3_2048_ipt_tenth_bpp(T, oracle):
     of, _, _ = wrapper_ref.forward_coeffs(px[0].cpu().numpy().astype(np.float64), return_float=True, **kw)
     n_bad = _mismatches(coeffs[0].cpu().numpy(), of)
     print("config 3: quantised coefficient mismatches vs float64 oracle:", n_bad, "of", of.size)
+    from conftest import record_count
+    record_count("config3_2048_ipt_quantised_mismatches", mismatches=int(n_bad), coefficients=int(of.size),
+                 max_abs_err_before_truncation=float(np.abs(coeffs[0].cpu().numpy() - of).max()))
     assert n_bad <= 1e-5 * of.size
     out, _ = batch.decode_images(s, (nbits + 7) // 8, max_n, 3, g, st, dtype=T.float32)
     assert _psnr(out[0, :, :2048, :2048].cpu().numpy(), px[0].cpu().numpy()) > 18
@@ -145,6 +148,32 @@ def test_config5_periodization_mixed_sizes(T, oracle, bpp):
     recs = spiht.decode_images(encs, st)
     ps = [_psnr(r[:, :im.shape[1], :im.shape[2]], im) for r, im in zip(recs, imgs)]
     assert min(ps) > 15
+
+
+@pytest.mark.parametrize("mode", ["reflect", "periodization"])
+def test_config5_one_mixed_size_call(T, oracle, mode):
+    """configs[4] as the config names it: ONE encode_images([...]) call over a mixed-size batch (512 .. 2048 px,
+    two images per size so that equal shapes really are batched), every stream and every decoded image against
+    the oracle; then one decode_images call over the mixed results"""
+    import spiht_b200 as spiht
+    from conftest import synth_image
+    from oracle import wrapper_ref
+    st = spiht.SpihtSettings(mode=mode)
+    sizes = [512, 1024, 512, 2048, 1024, 768]
+    imgs = [synth_image(3, n, n, 150 + i).astype(np.float32) for i, n in enumerate(sizes)]
+    bpps = [0.075, 0.1, 0.5, 1.0, 0.1, 0.5]
+    budgets = [int(n * n * b) for n, b in zip(sizes, bpps)]       # one budget per image, as the config's bpp sweep
+    encs = spiht.encode_images(imgs, st, None, budgets)
+    assert [(e.h, e.w) for e in encs] == [(n, n) for n in sizes]
+    assert [len(e.encoded_bytes) for e in encs] == [(m + 7) // 8 for m in budgets]
+    refs = [wrapper_ref.encode_image(im.astype(np.float64), mode=mode, max_bits=m) for im, m in zip(imgs, budgets)]
+    for e, r in zip(encs, refs):
+        assert e.max_n == r["max_n"] and e.encoded_bytes == r["encoded_bytes"]
+    recs = spiht.decode_images(encs, st)
+    for rec, r, im in zip(recs, refs, imgs):
+        want = wrapper_ref.decode_image(r, mode=mode)
+        assert rec.shape == want.shape and np.abs(rec - want).max() < 1e-9
+        assert _psnr(rec[:, :im.shape[1], :im.shape[2]], im) > 15
 
 
 def test_repeated_runs_are_bit_identical(T):

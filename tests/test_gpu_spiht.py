@@ -163,6 +163,32 @@ def test_odd_ll_unaligned_budgets(rs, oracle):
             assert np.array_equal(rec, ref), (c, h, w, llh, llw, mb, int((rec != ref).sum()))
 
 
+def test_tight_odd_ll_geometry_is_accepted(rs, oracle):
+    """h == 2 ll_h (and 2 ll_h - 1) with odd ll_h: every one-level decomposition with an odd band.  The lowest
+    LL-root offspring row is 2 ll_h - 2 there, so the reference accepts these shapes."""
+    rng = np.random.default_rng(31)
+    for (c, h, w, llh, llw) in [(1, 22, 22, 11, 11), (2, 21, 22, 11, 11), (3, 106, 106, 53, 53), (1, 21, 25, 11, 13)]:
+        x = rng.normal(0, 30, (c, h, w)).astype(np.int32)
+        for mb in (10 ** 9, 1500, 333):
+            want, want_n = oracle.encode(x, llh, llw, mb)
+            got, got_n = rs.encode(x, llh, llw, mb)
+            assert got_n == want_n
+            assert_stream_equal(got, want, f"tight odd ll {(c, h, w, llh, llw)} mb={mb}")
+            assert np.array_equal(rs.decode(got, got_n, c, h, w, llh, llw),
+                                  oracle.decode(want, want_n, c, h, w, llh, llw))
+    # 18x18 and 17x17 images at default settings: level 1, ll = 11 (the shapes ADVICE names)
+    import spiht_b200 as spiht
+    from oracle import wrapper_ref
+    for n in (18, 17, 101, 102):
+        img = synth_image(3, n, n, n)
+        lvl = None if n < 30 else 1
+        enc = spiht.encode_image(img, spiht.SpihtSettings(), level=lvl)
+        ref = wrapper_ref.encode_image(img, level=lvl)
+        assert enc.max_n == ref["max_n"] and enc.encoded_bytes == ref["encoded_bytes"], n
+        rec = spiht.decode_image(enc, spiht.SpihtSettings())
+        assert np.abs(rec - wrapper_ref.decode_image(ref)).max() < 1e-9
+
+
 @pytest.mark.parametrize("shape,wavelet,mode", [((3, 96, 80), "bior2.2", "reflect"),
                                                 ((3, 256, 384), "bior2.2", "reflect"),
                                                 ((1, 130, 70), "bior4.4", "symmetric"),

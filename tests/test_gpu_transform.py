@@ -105,6 +105,8 @@ def test_forward_ipt(torch_cuda):
     got = batch.forward(torch.from_numpy(img[None]).cuda(), g, st)[0].cpu().numpy()
     n_bad = _check_quantised(got, of, "IPT")
     print("IPT quantised mismatches:", n_bad, "of", got.size)
+    from conftest import record_count
+    record_count("forward_ipt_128x160_quantised_mismatches", mismatches=int(n_bad), coefficients=int(got.size))
 
 
 @pytest.mark.parametrize("shape,wavelet,mode,level", CASES)

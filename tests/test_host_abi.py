@@ -105,3 +105,30 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src.replace("the CPU oracle", ""), f
+
+
+def test_release_library_exports_no_debug_symbols():
+    """the phase counters (-DSPIHTB_PROF) are not part of the product library"""
+    import subprocess
+    from spiht_b200 import build
+    out = subprocess.run(["nm", "-D", "--defined-only", build.LIB_PATH], capture_output=True, text=True).stdout
+    names = {ln.split()[-1] for ln in out.splitlines() if " T " in ln and ln.split()[-1].startswith("spihtb_")}
+    from spiht_b200 import _lib
+    assert names == set(_lib.EXPORTS), names ^ set(_lib.EXPORTS)
+
+
+def test_spiht_alias_package_matches_reference_imports():
+    """the import lines of the reference's scripts (encode_decode.py:10-14, make_gif.py, demonstrate.py,
+    spiht/tests/*.py) resolve against the `spiht` alias package"""
+    import spiht
+    from spiht import encode_image, decode_image, EncodingResult, SpihtSettings, ENCODER_DECODER_VERSION  # noqa: F401
+    from spiht import encode, decode  # noqa: F401
+    from spiht.spiht_wrapper import SpihtSettings as S2, get_slices_and_h_w, decode_rec_array, decode_from_rec_arr  # noqa: F401
+    from spiht.utils import imload, bytes_to_bits  # noqa: F401
+    from spiht.color_models import convert  # noqa: F401
+    import spiht.spiht as spiht_rs
+    import spiht_b200
+    assert S2 is spiht_b200.SpihtSettings and spiht.spiht_wrapper is spiht_b200.spiht_wrapper
+    assert spiht_rs.encode is spiht_b200.encode and hasattr(spiht_rs, "decode_with_metadata")
+    with pytest.raises(ValueError):
+        convert(np.zeros((3, 4, 4)), "RGB", "CIE Lab")     # color_models.py:7-10

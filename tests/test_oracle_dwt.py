@@ -62,7 +62,7 @@ def test_ipt_roundtrip_close():
     x = np.random.default_rng(2).random((3, 16, 16))
     y = ipt_ref.convert(x, "RGB", "IPT")
     z = ipt_ref.convert(y, "IPT", "RGB")
-    assert np.abs(z - x).max() < 2e-4      # the 4-digit sRGB matrices are not exact inverses
+    assert np.abs(z - x).max() < 1e-12     # every matrix of the way back is the float64 inverse of the forward one
     with pytest.raises(ValueError):
         ipt_ref.convert(x, "RGB", "CIE Lab")
 
@@ -105,3 +105,55 @@ def test_compiled_transform_of_the_cpu_baseline_matches_the_checker(shape, wavel
     c1, lh, lw = wrapper_ref.forward_coeffs(x, wavelet, mode, level)
     c2, lh2, lw2 = wrapper_ref.forward_coeffs(x, wavelet, mode, level, fast=True)
     assert (lh, lw) == (lh2, lw2) and c1.shape == c2.shape and np.abs(c1 - c2).max() <= 1
+
+
+# ---- independent derivations of the recalled filter tables -------------------------------------------------
+# oracle/dwt_ref.py restates PyWavelets' bior tables from memory.  bior2.2 and bior4.4 are the CDF 5/3 and 9/7
+# pairs of JPEG 2000, whose *lifting* factorisations (ITU-T T.800 Annex F constants; Daubechies & Sweldens
+# 1998) share nothing with those tables: running the lifting steps must reproduce dwt_axis on interior samples
+# up to the sqrt(2) normalisation.  Alignment of the PyWavelets convention out[k] = sum_j f[j] x[2k+1-j]:
+# 5/3: lo[k] = sqrt(2) s[k-1], hi[k] = -d[k-1] / sqrt(2);  9/7: lo[k] = zeta s[k-2], hi[k] = -d[k-2] / zeta.
+def _lift53(x):
+    e, o = x[0::2].copy(), x[1::2].copy()
+    o -= 0.5 * (e + np.roll(e, -1))          # d[n] = x[2n+1] - (x[2n] + x[2n+2]) / 2
+    e += 0.25 * (np.roll(o, 1) + o)          # s[n] = x[2n] + (d[n-1] + d[n]) / 4
+    return 2 ** 0.5 * e, o / 2 ** 0.5
+
+
+def _lift97(x):
+    alpha, beta, gamma, delta = -1.586134342059924, -0.052980118572961, 0.882911075530934, 0.443506852043971
+    zeta = 1.149604398860241                  # = sqrt(2) / K, K = 1.230174104914001 (T.800 Table F.4)
+    e, o = x[0::2].copy(), x[1::2].copy()
+    o += alpha * (e + np.roll(e, -1))
+    e += beta * (np.roll(o, 1) + o)
+    o += gamma * (e + np.roll(e, -1))
+    e += delta * (np.roll(o, 1) + o)
+    return zeta * e, o / zeta
+
+
+@pytest.mark.parametrize("name,lift,shift,tol", [("bior2.2", _lift53, 1, 1e-14), ("bior4.4", _lift97, 2, 1e-11)])
+@pytest.mark.parametrize("mode", ["reflect", "symmetric"])
+def test_lifting_factorisation_reproduces_the_filter_bank(name, lift, shift, tol, mode):
+    rng = np.random.default_rng(5)
+    x = rng.normal(size=128)
+    lo, hi = d.dwt_axis(x[None], d.Wavelet(name), mode, -1)
+    s, dd = lift(x)
+    idx = np.arange(8, len(s) - 8)            # interior: away from the boundary extension and the lifting's wrap
+    assert np.abs(lo[0][idx + shift] - s[idx]).max() < tol
+    assert np.abs(hi[0][idx + shift] + dd[idx]).max() < tol
+
+
+@pytest.mark.parametrize("name,nr,nd", [("bior2.2", 2, 2), ("bior4.4", 4, 4), ("bior6.8", 6, 8)])
+def test_filter_tables_have_the_vanishing_moments_their_name_states(name, nr, nd):
+    """biorNr.Nd: dec_lo has Nd zeros at z = -1 and rec_lo has Nr (so that the decomposition / reconstruction
+    wavelets have Nd / Nr vanishing moments) -- and not one more.  Together with perfect reconstruction,
+    symmetry and the tap counts this determines the pair; it uses no PyWavelets-specific knowledge."""
+    wv = d.Wavelet(name)
+    for f, nz in ((wv.dec_lo, nd), (wv.rec_lo, nr)):
+        k = np.arange(len(f), dtype=np.float64)
+        k -= k[np.abs(f) > 0].mean()          # centre: keeps the high moments well conditioned
+        alt = (-1.0) ** np.arange(len(f))
+        moms = [abs(np.sum(alt * k ** p * f)) for p in range(nz + 1)]
+        assert max(moms[:nz]) < 1e-9, moms
+        assert moms[nz] > 1e-2, moms
+        assert np.allclose(f[np.abs(f) > 0], f[np.abs(f) > 0][::-1], atol=0, rtol=0)   # exactly symmetric
