@@ -93,8 +93,13 @@ int spihtb_sync(spihtb_ctx *ctx);
 /* number of kernels this context has launched so far (bench.py `gpu_launches`) */
 int64_t spihtb_launch_count(spihtb_ctx *ctx);
 
+/* which forward-transform path the last spihtb_forward / spihtb_encode_images call on this context took:
+ * 12 = levels 1 and 2 fused in one kernel (TMA-staged tiles, dwt_fwd2.cu), 1 = one kernel per level.  bench.py
+ * uses it to credit the dominant kernel with the right algorithmic bytes. */
+int spihtb_forward_path(spihtb_ctx *ctx);
+
 /* ---- stage timers (CUDA events on the context's stream; used by bench.py for the roofline) ----
- * Stages: 0 forward DWT level 1, 1 forward remaining levels (+ colour, gap fill), 2 pyramid base pass (with
+ * Stages: 0 forward DWT level 1 (levels 1+2 when spihtb_forward_path() == 12), 1 forward remaining levels (+ colour, gap fill), 2 pyramid base pass (with
  * spihtb_encode_images: zero fill + fix-up of the cells the fused epilogue leaves open), 3 pyramid upper rings + LL roots, 4 SPIHT encode kernel, 5 SPIHT decode (zero fill + kernel),
  * 6 inverse DWT coarse levels, 7 inverse DWT finest level (+ colour). */
 #define SPIHTB_NSTAGES 8

@@ -48,7 +48,7 @@ EXPORTS = (
     "spihtb_sync", "spihtb_launch_count", "spihtb_plan", "spihtb_encode", "spihtb_decode",
     "spihtb_encode_coeffs", "spihtb_decode_coeffs", "spihtb_forward", "spihtb_inverse",
     "spihtb_encode_images", "spihtb_decode_images", "spihtb_stream_bound",
-    "spihtb_profile_enable", "spihtb_profile_read", "spihtb_max_abs", "spihtb_convert_color",
+    "spihtb_profile_enable", "spihtb_profile_read", "spihtb_max_abs", "spihtb_convert_color", "spihtb_forward_path",
 )
 
 
@@ -78,6 +78,7 @@ def lib():
         L.spihtb_sync.argtypes = [vp]
         L.spihtb_launch_count.argtypes = [vp]
         L.spihtb_launch_count.restype = ctypes.c_int64
+        L.spihtb_forward_path.argtypes = [vp]
         L.spihtb_plan.argtypes = [i32, i32, i32, i32, i32, P(Geom)]
         L.spihtb_encode.argtypes = [vp, vp, i32, i32, i32, i32, i32, u64, P(vp), P(u64), P(i32)]
         L.spihtb_decode.argtypes = [vp, ctypes.c_char_p, u64, i32, i32, i32, i32, i32, i32, vp]
@@ -137,6 +138,10 @@ class Context:
 
     def launch_count(self):
         return int(lib().spihtb_launch_count(self._h))
+
+    def forward_path(self):
+        """12 when the last forward transform ran levels 1+2 in the fused TMA kernel, else 1"""
+        return int(lib().spihtb_forward_path(self._h))
 
     STAGES = ("dwt_fwd_level1", "dwt_fwd_rest", "pyramid_base", "pyramid_rest", "spiht_encode", "spiht_decode",
               "dwt_inv_coarse", "dwt_inv_level1")

@@ -308,6 +308,7 @@ int spihtb_sync(spihtb_ctx *ctx)
 }
 
 int64_t spihtb_launch_count(spihtb_ctx *ctx) { return ctx ? ctx->launches : 0; }
+int spihtb_forward_path(spihtb_ctx *ctx) { return ctx && ctx->last_forward_fused12 ? 12 : 1; }
 
 int spihtb_plan(int32_t h, int32_t w, int32_t wavelet, int32_t mode, int32_t level, spihtb_geom *g)
 {

@@ -663,11 +663,13 @@ static int launch_level_w(spihtb_ctx *ctx, int wid, const FwdK &k, int nz)
 // recomputes a cell from the finished array).  Per level and detail band (rows from `ro`, columns from
 // `co`): the cell row of a chunk's first row when that row is odd and of its last row when that is even;
 // the cell column of a strip's first column when odd and of its last column when even; and the LL block.
+// whole: the level was written by the fused two-level kernel (dwt_fwd2.cu), which completes every cell inside a
+// band itself: only the band's own edges remain.
 template <int WID>
-static void fix_rects_level(std::vector<FixRect> &out, int bh, int bw, int sh, int sw, int NH, int NW)
+static void fix_rects_level(std::vector<FixRect> &out, int bh, int bw, int sh, int sw, int NH, int NW, bool whole)
 {
-    constexpr int NOUT = FwdCfg<WID>::NOUT;
-    const int RHMAX = fw_rhmax(bh);
+    const int NOUT = whole ? bw : FwdCfg<WID>::NOUT;
+    const int RHMAX = whole ? bh : fw_rhmax(bh);
     const int tiles_x = (bw + NOUT - 1) / NOUT, tiles_y = (bh + RHMAX - 1) / RHMAX;
     const int RH = (bh + tiles_y - 1) / tiles_y;
     auto add = [&](int a0, int a1, int b0, int b1) {
@@ -700,8 +702,8 @@ static void fix_rects_level(std::vector<FixRect> &out, int bh, int bw, int sh, i
     }
 }
 
-static int upload_fix_rects(spihtb_ctx *ctx, const spihtb_geom &g, const FixRect **rects, const uint32_t **prefix,
-                            int *nrect, uint32_t *total)
+static int upload_fix_rects(spihtb_ctx *ctx, const spihtb_geom &g, bool fused12, const FixRect **rects,
+                            const uint32_t **prefix, int *nrect, uint32_t *total)
 {
     // key: everything the rectangle list depends on
     int32_t key[32] = {0};
@@ -710,6 +712,7 @@ static int upload_fix_rects(spihtb_ctx *ctx, const spihtb_geom &g, const FixRect
         key[6 + 4 * l] = g.band_h[l]; key[7 + 4 * l] = g.band_w[l];
         key[8 + 4 * l] = g.off_h[l]; key[9 + 4 * l] = g.off_w[l];
     }
+    key[30] = fused12 ? 1 : 0;
     key[31] = 0x5eed;
     std::vector<int32_t> &h = ctx->fix_host;
     const bool hit = h.size() >= 34 && memcmp(h.data(), key, sizeof(key)) == 0 && ctx->fix.p;
@@ -719,13 +722,16 @@ static int upload_fix_rects(spihtb_ctx *ctx, const spihtb_geom &g, const FixRect
         for (int l = 0; l < g.levels; ++l) {
             switch (g.wavelet) {
                 case SPIHTB_WAVELET_BIOR22:
-                    fix_rects_level<SPIHTB_WAVELET_BIOR22>(r, g.band_h[l], g.band_w[l], g.off_h[l], g.off_w[l], NH, NW);
+                    fix_rects_level<SPIHTB_WAVELET_BIOR22>(r, g.band_h[l], g.band_w[l], g.off_h[l], g.off_w[l], NH, NW,
+                                                             fused12 && l < 2);
                     break;
                 case SPIHTB_WAVELET_BIOR44:
-                    fix_rects_level<SPIHTB_WAVELET_BIOR44>(r, g.band_h[l], g.band_w[l], g.off_h[l], g.off_w[l], NH, NW);
+                    fix_rects_level<SPIHTB_WAVELET_BIOR44>(r, g.band_h[l], g.band_w[l], g.off_h[l], g.off_w[l], NH, NW,
+                                                             fused12 && l < 2);
                     break;
                 default:
-                    fix_rects_level<SPIHTB_WAVELET_BIOR68>(r, g.band_h[l], g.band_w[l], g.off_h[l], g.off_w[l], NH, NW);
+                    fix_rects_level<SPIHTB_WAVELET_BIOR68>(r, g.band_h[l], g.band_w[l], g.off_h[l], g.off_w[l], NH, NW,
+                                                             fused12 && l < 2);
                     break;
             }
         }
@@ -768,9 +774,7 @@ int launch_forward(spihtb_ctx *ctx, const void *pixels, const XformArgs &x, int3
     // scratch: two float64 approximation planes (level 1 output is the largest)
     const size_t ll1 = (size_t)nz * g.band_h[0] * g.band_w[0] * sizeof(double);
     const size_t ll2 = L > 1 ? (size_t)nz * g.band_h[1] * g.band_w[1] * sizeof(double) : 0;
-    int rc = ctx->ensure(ctx->tmpa, ll1 + 256);
-    if (rc) return rc;
-    rc = ctx->ensure(ctx->tmpb, ll2 + 256);
+    int rc = ctx->ensure(ctx->tmpb, ll2 + 256);
     if (rc) return rc;
 
     const double *u8lut = nullptr;
@@ -862,8 +866,27 @@ int launch_forward(spihtb_ctx *ctx, const void *pixels, const XformArgs &x, int3
         SPIHTB_CUDA_CHECK(cudaMemsetAsync(pf->maxabs, 0, sizeof(uint32_t) * x.B, ctx->stream));
         ctx->stage_end(2);
     }
-    rc = run_level(0, 0, nz);
-    if (rc) return rc;
+    // levels 1 and 2 in one kernel (TMA-staged tiles, the level-1 approximation stays in shared memory) when the
+    // geometry allows it; otherwise level by level through the float64 scratch planes
+    bool fused12 = false;
+    {
+        const bool in_f64 = x.pixel_dtype == SPIHTB_F64 || x.color == SPIHTB_COLOR_IPT || conv;
+        const int sdt = in_f64 ? SPIHTB_F64 : x.pixel_dtype;
+        ctx->stage_begin(0);
+        rc = launch_forward_fused12(ctx, src, sdt, x, coeffs, static_cast<double *>(ctx->tmpb.p), pf, u8lut, &fused12);
+        ctx->stage_end(0);
+        if (rc) return rc;
+    }
+    ctx->last_forward_fused12 = fused12;
+    if (fused12) {  // level 3 writes its approximation to the first scratch plane
+        rc = ctx->ensure(ctx->tmpa, (size_t)nz * g.band_h[2] * g.band_w[2] * sizeof(double) + 256);
+        if (rc) return rc;
+    } else {
+        rc = ctx->ensure(ctx->tmpa, ll1 + 256);
+        if (rc) return rc;
+        rc = run_level(0, 0, nz);
+        if (rc) return rc;
+    }
     bool gap_forked = false;
     {
         GapK gk;
@@ -899,7 +922,7 @@ int launch_forward(spihtb_ctx *ctx, const void *pixels, const XformArgs &x, int3
             gap_forked = true;
         }
     }
-    for (int l = 1; l < L; ++l) {
+    for (int l = fused12 ? 2 : 1; l < L; ++l) {
         rc = run_level(l, 0, nz);
         if (rc) return rc;
     }
@@ -911,7 +934,7 @@ int launch_forward(spihtb_ctx *ctx, const void *pixels, const XformArgs &x, int3
         const uint32_t *prefix;
         int nrect;
         uint32_t total;
-        rc = upload_fix_rects(ctx, g, &rects, &prefix, &nrect, &total);
+        rc = upload_fix_rects(ctx, g, fused12, &rects, &prefix, &nrect, &total);
         if (rc) return rc;
         ctx->stage_begin(2);
         rc = launch_pyr_fix(ctx, coeffs, nz, g.enc_h, g.enc_w, pf->dp, rects, prefix, nrect, total);

@@ -1,0 +1,733 @@
+// Forward transform, levels 1 and 2 fused in one kernel with TMA-staged input tiles.
+//
+// The level-by-level kernel (dwt_fwd.cu) writes the float64 level-1 approximation to HBM and reads it back
+// for level 2: 13.2 MB per 1024^2 RGB image of traffic that carries no algorithmic byte.  Here a CTA owns a
+// column strip of one (image, channel) plane and streams down its rows; both levels are computed from one
+// pass over the pixels and the level-1 approximation never leaves shared memory.
+//
+//   input     TMA (cp.async.bulk.tensor, one 1-row box per plane row, mbarrier completion) into a ring of
+//             stages of 8 rows; boundary rows are ordinary row coordinates (the extension map is applied to
+//             the coordinate), boundary columns are read through a per-thread column map
+//   V1        a thread owns one input column: register window of F rows, row filter -> (lo, hi) rows in smem
+//   H1        a thread owns one level-1 output column of the lo or the hi row: column filter from smem pairs;
+//             aa -> ring of level-1 approximation rows (smem, float64); ad / da / dd quantised -> int32 tile
+//   OUT1      tile rows -> coefficient array as aligned 16-byte stores; 2x2 cells of the tile -> pyramid bytes
+//   V2 / H2 / OUT2   the same one level down, from the ring; aa2 -> float64 scratch for level 3
+//
+// Arithmetic (tap order, fma accumulation, (m x) q truncation) is identical to dwt_fwd.cu, so both paths give
+// bit-identical coefficient arrays (tests/test_gpu_fused12.py).
+//
+// Index conventions, one axis (F taps, sft = F/2 - 1 in periodization mode, else 0):
+//   out[k] = sum_j f[j] x_ext[2k + 1 + sft - j]            window [2k + sft - (F-2), 2k + sft + 1]
+// Columns of a strip: level-2 outputs m in [M0 - 1, M1) (column M0 - 1 only completes the first pyramid cell);
+// level-1 "virtual" columns kv = KV0 + c1, KV0 = 2 (M0-1) + sft - (F-2), c1 in [0, nk), nk = 2 (M1-M0+1) + F-2;
+// input virtual columns xv = XV0 + t, XV0 = 2 KV0 + sft - (F-2), t in [0, cw), cw = 2 nk + F-2.  Level-1 output
+// c1 reads input pairs c1 .. c1+F/2-1.  Rows likewise (level-2 rows [R0 - 1, R1) of a row chunk).
+// In periodization mode virtual level-1 columns / rows ARE the band (periodic); in the other modes level 2
+// extends the level-1 band by its own boundary rule, so virtual index v is read at ext_index(v, band length).
+#include <cuda.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+#include "kernels.cuh"
+#include "wavelets.cuh"
+
+namespace spihtb {
+
+constexpr int F2_NT = 256;   // threads per CTA
+constexpr int F2_CW = 256;   // columns of TMA box A (= most input columns a strip can use)
+constexpr int F2_CWB = 64;   // columns of TMA box B (columns the boundary map takes from the far side of the plane)
+constexpr int F2_NST = 3;    // input stages in flight
+constexpr int F2_SR = 8;     // input rows per stage
+constexpr int F2_SB = 4;     // level-1 rows per step
+constexpr int F2_TW1 = 128;  // ints per level-1 tile row
+constexpr int F2_TW2 = 72;   // ints per level-2 tile row
+constexpr int F2_NKP = 128;  // padded level-1 columns
+
+template <int WID>
+struct F2Cfg {
+    static constexpr int F = Wav<WID>::F;
+    static constexpr int HF = F / 2;
+    static constexpr int FILL1 = (F - 2 + F2_SR - 1) / F2_SR;  // input stages before the first level-1 row
+    static constexpr int FILL2 = (F - 2) / F2_SB;              // V2 steps before the first level-2 row
+    static constexpr int LAGS = (F - 5 + 3) / 4;               // steps V2 runs behind the level-1 rows it reads
+    // level-1 approximation rows kept in smem: at the top of a plane V2 reads rows 1 .. F (mirrored) while H1 is
+    // already up to 4 (LAGS + ceil(F / 4)) + 3 rows further
+    static constexpr int RING = F == 6 ? 16 : (F == 10 ? 32 : 64);
+    static constexpr int NK = (F2_CW - (F - 2)) / 2;           // level-1 columns per strip at most
+    // level-2 columns per strip: nk = 2 (NM + 1) + F - 2 (one extra column on the left completes the strip's
+    // first pyramid cell), and a level-1 tile row holds 2 NM + 8 ints
+    static constexpr int NM = ((NK - (F - 2)) / 2 - 1) < 60 ? ((NK - (F - 2)) / 2 - 1) : 60;
+    static_assert((F - 2) % F2_SB == 0, "window fill is a whole number of steps");
+    static_assert(RING >= 4 * (LAGS + (F + 3) / 4) + 4 && (RING & (RING - 1)) == 0, "ring");
+    static_assert(4 + 3 + 2 * NM + 1 <= F2_TW1 && 4 + 3 + NM + 1 <= F2_TW2, "tile rows");
+    static_assert(2 * (NM + 1) + F - 2 <= NK && NK <= F2_NKP && NM + 1 + HF <= F2_NKP / 2, "strip width");
+};
+
+struct F2K {
+    int src_h, src_w;
+    int bh1, bw1, bh2, bw2;
+    int Hc, Wc;
+    int sh1, sw1, sh2, sw2;
+    int mode, C;
+    int nstrips, nchunks, NMs, NRc;
+    int use_b;                 // some strip needs box B
+    int32_t *coeffs;
+    double *ll2;               // [nz][bh2][bw2]
+    uint8_t *dp;               // optional
+    uint32_t *maxabs;
+    int NH, NW;
+    double scale[8];
+    double q;
+    const double *u8lut;
+};
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n\t}" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+// one box of the 3-D tensor {columns, rows, planes} -> shared memory, completion on an mbarrier
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *tm, int x, int y, int z, uint32_t bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(x), "r"(y), "r"(z), "r"(bar)
+        : "memory");
+}
+
+template <typename Tin>
+__device__ __forceinline__ double f2_px(uint32_t saddr, const double *lut);
+template <>
+__device__ __forceinline__ double f2_px<float>(uint32_t saddr, const double *)
+{
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr));
+    return (double)v;
+}
+template <>
+__device__ __forceinline__ double f2_px<double>(uint32_t saddr, const double *)
+{
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(saddr));
+    return v;
+}
+template <>
+__device__ __forceinline__ double f2_px<uint8_t>(uint32_t saddr, const double *lut)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(saddr));
+    return lut[v];  // k / 255.0 (utils.py:19), table in shared memory
+}
+
+// One output of the column filters from F/2 (E, O) pairs: ascending tap order, fma accumulation, zero taps
+// skipped -- tap 2v multiplies O[k-v], tap 2v+1 multiplies E[k-v], as in dwt_fwd.cu.
+template <int WID>
+__device__ __forceinline__ void f2_hfilter(const double2 *pairs, double &o_lo, double &o_hi)
+{
+    constexpr int F = Wav<WID>::F, HF = F / 2;
+    double2 pr[HF];
+#pragma unroll
+    for (int p = 0; p < HF; ++p) pr[p] = pairs[p];
+    double lo = 0.0, hi = 0.0;
+#pragma unroll
+    for (int v = 0; v < HF; ++v) {
+        const double2 e = pr[HF - 1 - v];  // pair k - v
+        if (Wav<WID>::dec_lo(2 * v) != 0.0) lo = fma(Wav<WID>::dec_lo(2 * v), e.y, lo);
+        if (wav_dec_hi<WID>(2 * v) != 0.0) hi = fma(wav_dec_hi<WID>(2 * v), e.y, hi);
+        if (Wav<WID>::dec_lo(2 * v + 1) != 0.0) lo = fma(Wav<WID>::dec_lo(2 * v + 1), e.x, lo);
+        if (wav_dec_hi<WID>(2 * v + 1) != 0.0) hi = fma(wav_dec_hi<WID>(2 * v + 1), e.x, hi);
+    }
+    o_lo = lo;
+    o_hi = hi;
+}
+
+// Tile rows -> coefficient array and pyramid cells, for one detail band of one level.
+// A tile row holds band columns kfirst-1 .. kfirst+ncore-1 of one band row at index 3 + sh .. , where
+// sh = (element address of column kfirst) & 3, so that index 4v maps to a 16-byte aligned address.
+struct BandOut {
+    int ro, co;      // band origin in the coefficient array
+    int bh, bw;      // band size
+};
+// copy one tile row (warp-wide): band row r, columns [kfirst, kfirst + ncore)
+__device__ __forceinline__ uint32_t f2_copy_row(const int32_t *trow, int32_t *plane, int Wc, const BandOut &b, int r,
+                                                int kfirst, int ncore, int lane, int tw4)
+{
+    const long long e = (long long)(b.ro + r) * Wc + b.co + kfirst;  // element offset within the plane of column kfirst
+    const int sh = (int)((reinterpret_cast<uintptr_t>(plane + e) >> 2) & 3);
+    int32_t *g0 = plane + e - sh - 4;  // address of tile index 0 (16-byte aligned)
+    uint32_t mx = 0;
+    const int lo = 4 + sh, hi = 4 + sh + ncore;  // valid tile indices
+    for (int v = lane; v < tw4; v += 32) {
+        const int i0 = 4 * v;
+        if (i0 + 4 <= lo || i0 >= hi) continue;
+        const int4 q = *reinterpret_cast<const int4 *>(trow + i0);
+        if (i0 >= lo && i0 + 4 <= hi) {
+            *reinterpret_cast<int4 *>(g0 + i0) = q;
+            mx = max(mx, max(max(absu(q.x), absu(q.y)), max(absu(q.z), absu(q.w))));
+        } else {
+            const int32_t qq[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (i0 + u >= lo && i0 + u < hi) {
+                    g0[i0 + u] = qq[u];
+                    mx = max(mx, absu(qq[u]));
+                }
+        }
+    }
+    return mx;
+}
+// cells whose second row is band row r (array row ro + r odd) and whose second column is stored by this strip
+__device__ __forceinline__ void f2_cells_row(const int32_t *trow_prev, const int32_t *trow, const int32_t *plane, int Wc,
+                                             uint8_t *dpz, int NH, int NW, const BandOut &b, int r, int kfirst, int ncore,
+                                             int lane)
+{
+    const int ar = b.ro + r;
+    const int a = ar >> 1;
+    if (a >= NH) return;
+    const long long e1 = (long long)ar * Wc + b.co + kfirst, e0 = e1 - Wc;
+    const int sh1 = (int)((reinterpret_cast<uintptr_t>(plane + e1) >> 2) & 3);
+    const int sh0 = (int)((reinterpret_cast<uintptr_t>(plane + e0) >> 2) & 3);
+    // second columns: band columns k in [kfirst, kfirst+ncore) with (co + k) odd and k >= 1
+    int k = kfirst + (((b.co + kfirst) & 1) ? 0 : 1) + 2 * lane;
+    for (; k < kfirst + ncore; k += 64) {
+        if (k < 1) continue;
+        const int bcol = (b.co + k) >> 1;
+        if (bcol >= NW) continue;
+        const int i1 = 4 + sh1 + (k - kfirst), i0 = 4 + sh0 + (k - kfirst);
+        const uint32_t m = max(max(absu(trow[i1]), absu(trow[i1 - 1])), max(absu(trow_prev[i0]), absu(trow_prev[i0 - 1])));
+        dpz[(size_t)a * NW + bcol] = (uint8_t)plane1(m);
+    }
+}
+
+template <typename Tin, int WID>
+__global__ void __launch_bounds__(F2_NT, (Wav<WID>::F == 18 ? 1 : 2))
+dwt_fwd12_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const F2K p)
+{
+    using Cfg = F2Cfg<WID>;
+    constexpr int F = Cfg::F, HF = Cfg::HF, FILL1 = Cfg::FILL1, FILL2 = Cfg::FILL2, LAGS = Cfg::LAGS, RING = Cfg::RING;
+    constexpr int ES = (int)sizeof(Tin);
+    constexpr int ROWB = (F2_CW + F2_CWB) * ES;   // bytes of one staged row (box A, then box B)
+    constexpr int STAGEB = F2_SR * ROWB;
+    constexpr bool U8 = sizeof(Tin) == 1;
+
+    extern __shared__ __align__(128) unsigned char smem[];
+    unsigned char *sp = smem;
+    unsigned char *s_in = sp;                 sp += F2_NST * STAGEB;
+    double *s_v1 = reinterpret_cast<double *>(sp);   sp += 2 * F2_SB * F2_CW * sizeof(double);       // [lohi][row][col]
+    double *s_ring = reinterpret_cast<double *>(sp); sp += RING * F2_NKP * sizeof(double);          // [slot][c1]
+    double *s_v2 = reinterpret_cast<double *>(sp);   sp += 2 * 2 * F2_NKP * sizeof(double);         // [lohi][row][c1]
+    int32_t *s_t1 = reinterpret_cast<int32_t *>(sp); sp += 3 * 8 * F2_TW1 * sizeof(int32_t);        // [band][row & 7][i]
+    int32_t *s_t2 = reinterpret_cast<int32_t *>(sp); sp += 3 * 4 * F2_TW2 * sizeof(int32_t);        // [band][row & 3][i]
+    double *s_lut = reinterpret_cast<double *>(sp);  sp += (U8 ? 256 : 0) * sizeof(double);
+    uint64_t *s_bar = reinterpret_cast<uint64_t *>(sp); sp += F2_NST * sizeof(uint64_t);
+    int *s_misc = reinterpret_cast<int *>(sp);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int mode = p.mode;
+    const bool per = mode == SPIHTB_MODE_PERIODIZATION;
+    const int sft = per ? HF - 1 : 0;
+
+    // ---- task
+    int task = blockIdx.x;
+    const int strip = task % p.nstrips;
+    task /= p.nstrips;
+    const int chunk = task % p.nchunks;
+    const int z = task / p.nchunks;
+
+    // level-2 columns [M0, M1) and rows [R0, R1) are stored; column M0 - 1 and row R0 - 1 are computed as well
+    // (details only) so that every pyramid cell whose second row / column is stored here is complete
+    const int M0 = strip * p.NMs, M1 = min(M0 + p.NMs, p.bw2), nm = M1 - M0;
+    const int KV0 = 2 * (M0 - 1) + sft - (F - 2), nk = 2 * (nm + 1) + F - 2;
+    const int XV0 = 2 * KV0 + sft - (F - 2), cw = 2 * nk + F - 2;
+    const int R0 = chunk * p.NRc, R1 = min(R0 + p.NRc, p.bh2);
+    const int VR0 = 2 * (R0 - 1) + sft - (F - 2), VRl = 2 * R1 + sft - 1;
+    const int PR0 = per ? VR0 : max(VR0, 0);
+    const int Pl = per ? VRl : min(VRl, p.bh1 - 1);
+    const int nps = (Pl - PR0 + 1 + F2_SB - 1) / F2_SB;
+    const int nvs = (VRl - VR0 + 1 + F2_SB - 1) / F2_SB;
+    const int nsteps = max(nps, nvs + LAGS);
+    const int IR0 = 2 * PR0 + sft - F2_SR * FILL1;
+    const int nstages = nps + FILL1;
+
+    // ---- column maps
+    if (tid == 0) s_misc[0] = 0x7fffffff;
+    if (U8)
+        for (int k = tid; k < 256; k += F2_NT) s_lut[k] = p.u8lut[k];
+    __syncthreads();
+    const int rc = ext_index(XV0 + min(tid, cw - 1), p.src_w, mode);  // real input column of this thread
+    const bool inA = rc >= XV0 && rc < XV0 + F2_CW;
+    if (!inA) atomicMin(&s_misc[0], rc);
+    __syncthreads();
+    const int BXB = s_misc[0];
+    const bool need_b = BXB != 0x7fffffff;   // CTA-uniform
+    const uint32_t in_off = (uint32_t)((inA ? rc - XV0 : F2_CW + (rc - BXB)) * ES);
+    // level-1 column this thread's V2 window reads (threads < nk)
+    const int c1 = min(tid, nk - 1);
+    const int c1map = per ? c1 : min(max(ext_index(KV0 + c1, p.bw1, mode) - KV0, 0), nk - 1);
+
+    // ---- barriers + first loads
+    const uint32_t bar0 = smem_u32(s_bar);
+    const uint32_t in0 = smem_u32(s_in);
+    if (tid == 0) {
+        for (int s = 0; s < F2_NST; ++s) mbar_init(bar0 + 8 * s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue_stage = [&](int q) {  // one thread
+        const int s = q % F2_NST;
+        const uint32_t bar = bar0 + 8 * s;
+        mbar_expect_tx(bar, (uint32_t)(F2_SR * (F2_CW + (need_b ? F2_CWB : 0)) * ES));
+#pragma unroll
+        for (int i = 0; i < F2_SR; ++i) {
+            const int row = ext_index(IR0 + F2_SR * q + i, p.src_h, mode);
+            const uint32_t dst = in0 + s * STAGEB + i * ROWB;
+            tma_load_3d(dst, &tmA, XV0, row, z, bar);
+            if (need_b) tma_load_3d(dst + F2_CW * ES, &tmB, BXB, row, z, bar);
+        }
+    };
+    if (tid == 0)
+        for (int q = 0; q < F2_NST && q < nstages; ++q) issue_stage(q);
+
+    // ---- per-plane constants
+    const int zc = z % p.C;
+    const double mq = p.scale[zc], qs = p.q;
+    int32_t *cplane = p.coeffs + (size_t)z * p.Hc * p.Wc;
+    uint8_t *dpz = p.dp ? p.dp + (size_t)z * p.NH * p.NW : nullptr;
+    const BandOut B1[3] = {{0, p.sw1, p.bh1, p.bw1}, {p.sh1, 0, p.bh1, p.bw1}, {p.sh1, p.sw1, p.bh1, p.bw1}};  // ad, da, dd
+    // stored level-1 columns / rows of this task
+    const int k1first = 2 * M0, n1core = max(0, min(2 * M1, p.bw1) - k1first);
+    const int c1first = k1first - KV0;
+    const int r1lo = 2 * R0, r1hi = min(2 * R1, p.bh1);
+    const int n2core = nm;
+
+    double w1[F - 2], w2[F - 2];
+#pragma unroll
+    for (int i = 0; i < F - 2; ++i) w1[i] = w2[i] = 0.0;
+    uint32_t mx = 0;
+
+    for (int step = -FILL1; step < nsteps; ++step) {
+        const int q = step + FILL1;  // input stage
+        // ================= V1: 8 input rows -> 4 (lo, hi) row pairs
+        if (q < nstages) {
+            mbar_wait(bar0 + 8 * (q % F2_NST), (uint32_t)((q / F2_NST) & 1));
+            const uint32_t base = in0 + (q % F2_NST) * STAGEB + in_off;
+            double x[F2_SR];
+#pragma unroll
+            for (int i = 0; i < F2_SR; ++i) x[i] = f2_px<Tin>(base + i * ROWB, s_lut);
+            if (step >= 0) {
+#pragma unroll
+                for (int j = 0; j < F2_SB; ++j) {
+                    double lo = 0.0, hi = 0.0;
+#pragma unroll
+                    for (int t = 0; t < F; ++t) {
+                        const int n = 2 * j + F - 1 - t;  // index into [w1 (F-2) | x (8)]
+                        const double v = n < F - 2 ? w1[n < F - 2 ? n : 0] : x[n >= F - 2 ? n - (F - 2) : 0];
+                        if (Wav<WID>::dec_lo(t) != 0.0) lo = fma(Wav<WID>::dec_lo(t), v, lo);
+                        if (wav_dec_hi<WID>(t) != 0.0) hi = fma(wav_dec_hi<WID>(t), v, hi);
+                    }
+                    s_v1[(0 * F2_SB + j) * F2_CW + tid] = lo;
+                    s_v1[(1 * F2_SB + j) * F2_CW + tid] = hi;
+                }
+            }
+            // carry the last F-2 rows
+            double nw[F - 2];
+#pragma unroll
+            for (int i = 0; i < F - 2; ++i) {
+                const int n = i + F2_SR;
+                nw[i] = n < F - 2 ? w1[n < F - 2 ? n : 0] : x[n >= F - 2 ? n - (F - 2) : 0];
+            }
+#pragma unroll
+            for (int i = 0; i < F - 2; ++i) w1[i] = nw[i];
+        }
+        __syncthreads();  // A: (lo, hi) rows visible; the stage is consumed
+        if (tid == 0 && q + F2_NST < nstages && q < nstages) issue_stage(q + F2_NST);
+
+        // ================= H1: level-1 outputs of production rows PR0 + 4 step + j
+        if (step >= 0 && step < nps) {
+            const int lohi = warp & 1, cb = warp >> 1;
+            const int c = cb * 32 + lane;
+            if (c < nk) {
+                const int k = KV0 + c;                      // level-1 column (virtual)
+                const bool kcore = c >= c1first - 1 && k >= 0 && k < k1first + n1core;  // goes to the tile
+#pragma unroll
+                for (int j = 0; j < F2_SB; ++j) {
+                    const int r = PR0 + F2_SB * step + j;
+                    if (r > Pl) break;
+                    const double2 *pairs = reinterpret_cast<const double2 *>(s_v1 + (lohi * F2_SB + j) * F2_CW) + c;
+                    double o_lo, o_hi;
+                    f2_hfilter<WID>(pairs, o_lo, o_hi);
+                    const bool rband = r >= 0 && r < p.bh1;
+                    if (lohi == 0) s_ring[((r - PR0) & (RING - 1)) * F2_NKP + c] = o_lo;  // aa
+                    if (kcore && rband) {
+                        // tile index: 3 + sh + (c - (c1first - 1)), sh from the element address of column k1first
+                        // ad: rows from 0, columns from sw1; da: rows from sh1, columns from 0
+                        const long long e = (long long)((lohi ? p.sh1 : 0) + r) * p.Wc + (lohi ? 0 : p.sw1) + k1first;
+                        const int sh = (int)((reinterpret_cast<uintptr_t>(cplane + e) >> 2) & 3);
+                        const int ti = 3 + sh + (c - (c1first - 1));
+                        if (lohi == 0) {
+                            s_t1[(0 * 8 + (r & 7)) * F2_TW1 + ti] = __double2int_rz((mq * o_hi) * qs);  // ad
+                        } else {
+                            s_t1[(1 * 8 + (r & 7)) * F2_TW1 + ti] = __double2int_rz((mq * o_lo) * qs);  // da
+                            const long long e2 = (long long)(p.sh1 + r) * p.Wc + p.sw1 + k1first;
+                            const int sh2 = (int)((reinterpret_cast<uintptr_t>(cplane + e2) >> 2) & 3);
+                            s_t1[(2 * 8 + (r & 7)) * F2_TW1 + 3 + sh2 + (c - (c1first - 1))] =
+                                __double2int_rz((mq * o_hi) * qs);  // dd
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();  // B: ring rows and level-1 tile rows of this step visible
+
+        // ================= V2 (warps 0-3) | OUT1 (warps 4-7)
+        const int u = step - LAGS;  // V2 step
+        if (warp < 4) {
+            if (u >= 0 && u < nvs) {
+                double y[F2_SB];
+#pragma unroll
+                for (int i = 0; i < F2_SB; ++i) {
+                    const int v = VR0 + F2_SB * u + i;                       // virtual level-1 row
+                    const int rr = per ? v : ext_index(v, p.bh1, mode);      // the row that holds it
+                    y[i] = s_ring[((rr - PR0) & (RING - 1)) * F2_NKP + c1map];
+                }
+                if (u >= FILL2) {
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        double lo = 0.0, hi = 0.0;
+#pragma unroll
+                        for (int t = 0; t < F; ++t) {
+                            const int n = 2 * e + F - 1 - t;  // index into [w2 (F-2) | y (4)]
+                            const double v = n < F - 2 ? w2[n < F - 2 ? n : 0] : y[n >= F - 2 ? n - (F - 2) : 0];
+                            if (Wav<WID>::dec_lo(t) != 0.0) lo = fma(Wav<WID>::dec_lo(t), v, lo);
+                            if (wav_dec_hi<WID>(t) != 0.0) hi = fma(wav_dec_hi<WID>(t), v, hi);
+                        }
+                        s_v2[(0 * 2 + e) * F2_NKP + tid] = lo;
+                        s_v2[(1 * 2 + e) * F2_NKP + tid] = hi;
+                    }
+                }
+                double nw[F - 2];
+#pragma unroll
+                for (int i = 0; i < F - 2; ++i) {
+                    const int n = i + F2_SB;
+                    nw[i] = n < F - 2 ? w2[n < F - 2 ? n : 0] : y[n >= F - 2 ? n - (F - 2) : 0];
+                }
+#pragma unroll
+                for (int i = 0; i < F - 2; ++i) w2[i] = nw[i];
+            }
+        } else if (step >= 0 && step < nps) {
+            // warp 4 + j: production row j of this step, all three bands
+            const int j = warp - 4;
+            const int r = PR0 + F2_SB * step + j;
+            if (r <= Pl && r >= 0 && r < p.bh1 && n1core > 0) {
+                const bool store = r >= r1lo && r < r1hi;
+#pragma unroll
+                for (int b = 0; b < 3; ++b) {
+                    const int32_t *trow = s_t1 + (b * 8 + (r & 7)) * F2_TW1;
+                    if (store) mx = max(mx, f2_copy_row(trow, cplane, p.Wc, B1[b], r, k1first, n1core, lane, F2_TW1 / 4));
+                    if (dpz && store && ((B1[b].ro + r) & 1) && r >= 1 && r - 1 >= PR0)
+                        f2_cells_row(s_t1 + (b * 8 + ((r - 1) & 7)) * F2_TW1, trow, cplane, p.Wc, dpz, p.NH, p.NW, B1[b],
+                                     r, k1first, n1core, lane);
+                }
+            }
+        }
+        __syncthreads();  // C: (lo, hi) rows of level 2 visible
+
+        // ================= H2: level-2 rows m = R0 - 1 + 2 (u - FILL2) + e, columns kk = M0 - 1 + c2
+        if (u >= FILL2 && u < nvs) {
+            const int e = warp >> 2, lohi = (warp >> 1) & 1, cb = warp & 1;
+            const int c2 = cb * 32 + lane;
+            const int m = R0 - 1 + 2 * (u - FILL2) + e;
+            const int kk = M0 - 1 + c2;
+            if (c2 < nm + 1 && m < R1 && m >= 0 && kk >= 0) {
+                const double2 *pairs = reinterpret_cast<const double2 *>(s_v2 + (lohi * 2 + e) * F2_NKP) + c2;
+                double o_lo, o_hi;
+                f2_hfilter<WID>(pairs, o_lo, o_hi);
+                if (lohi == 0 && c2 >= 1 && m >= R0) p.ll2[((size_t)z * p.bh2 + m) * p.bw2 + kk] = o_lo;  // aa -> level 3
+                const long long ea = (long long)((lohi ? p.sh2 : 0) + m) * p.Wc + (lohi ? 0 : p.sw2) + M0;
+                const int sh = (int)((reinterpret_cast<uintptr_t>(cplane + ea) >> 2) & 3);
+                if (lohi == 0) {
+                    s_t2[(0 * 4 + (m & 3)) * F2_TW2 + 3 + sh + c2] = __double2int_rz((mq * o_hi) * qs);  // ad
+                } else {
+                    s_t2[(1 * 4 + (m & 3)) * F2_TW2 + 3 + sh + c2] = __double2int_rz((mq * o_lo) * qs);  // da
+                    const long long e2 = (long long)(p.sh2 + m) * p.Wc + p.sw2 + M0;
+                    const int sh2 = (int)((reinterpret_cast<uintptr_t>(cplane + e2) >> 2) & 3);
+                    s_t2[(2 * 4 + (m & 3)) * F2_TW2 + 3 + sh2 + c2] = __double2int_rz((mq * o_hi) * qs);  // dd
+                }
+            }
+        }
+        __syncthreads();  // D: level-2 tile rows visible
+        // ================= OUT2 (warps 0-5: row e = warp & 1, band = warp >> 1)
+        if (u >= FILL2 && u < nvs && warp < 6) {
+            const int e = warp & 1, b = warp >> 1;
+            const int m = R0 - 1 + 2 * (u - FILL2) + e;
+            if (m >= R0 && m < R1) {
+                const BandOut bo = {b == 0 ? 0 : p.sh2, b == 1 ? 0 : p.sw2, p.bh2, p.bw2};
+                const int32_t *trow = s_t2 + (b * 4 + (m & 3)) * F2_TW2;
+                mx = max(mx, f2_copy_row(trow, cplane, p.Wc, bo, m, M0, n2core, lane, F2_TW2 / 4));
+                if (dpz && ((bo.ro + m) & 1) && m >= 1)
+                    f2_cells_row(s_t2 + (b * 4 + ((m - 1) & 3)) * F2_TW2, trow, cplane, p.Wc, dpz, p.NH, p.NW, bo, m, M0,
+                                 n2core, lane);
+            }
+        }
+    }
+    if (p.maxabs) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+        if (lane == 0 && mx) atomicMax(p.maxabs + z / p.C, mx);
+    }
+}
+
+// ---------------------------------------------------------------- host side
+namespace {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *f = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qr) == cudaSuccess &&
+            qr == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(f);
+        else
+            cudaGetLastError();
+    }
+    return fn;
+}
+
+struct F2Plan {
+    int nstrips, NMs, nchunks, NRc;
+    bool use_b;
+};
+
+// Mirrors the index arithmetic of dwt_fwd12_kernel for every strip and row chunk and checks that each column /
+// row a needed output reads is one the CTA holds (box A or B; a level-1 column it computes; a ring row that is
+// produced and not yet overwritten).  Degenerate geometries (planes a few filter lengths wide) fail here and take
+// the level-by-level kernel.
+template <int WID>
+bool f2_validate(const spihtb_geom &g, const F2Plan &pl)
+{
+    using Cfg = F2Cfg<WID>;
+    constexpr int F = Cfg::F, HF = Cfg::HF, FILL2 = Cfg::FILL2, LAGS = Cfg::LAGS, RING = Cfg::RING;
+    const int mode = g.mode;
+    const bool per = mode == SPIHTB_MODE_PERIODIZATION;
+    const int sft = per ? HF - 1 : 0;
+    const int src_h = g.in_h[0], src_w = g.in_w[0], bh1 = g.band_h[0], bw1 = g.band_w[0], bh2 = g.band_h[1],
+              bw2 = g.band_w[1];
+    (void)src_h;
+    for (int strip = 0; strip < pl.nstrips; ++strip) {
+        const int M0 = strip * pl.NMs, M1 = std::min(M0 + pl.NMs, bw2), nm = M1 - M0;
+        if (nm <= 0 || nm > Cfg::NM) return false;
+        const int KV0 = 2 * (M0 - 1) + sft - (F - 2), nk = 2 * (nm + 1) + F - 2;
+        const int XV0 = 2 * KV0 + sft - (F - 2), cw = 2 * nk + F - 2;
+        if (nk > Cfg::NK || cw > F2_CW) return false;
+        // input columns: box A [XV0, XV0 + CW), the rest within one box B
+        int bmin = 0x7fffffff, bmax = -0x7fffffff;
+        for (int t = 0; t < cw; ++t) {
+            const int rc = ext_index(XV0 + t, src_w, mode);
+            if (!(rc >= XV0 && rc < XV0 + F2_CW)) {
+                bmin = std::min(bmin, rc);
+                bmax = std::max(bmax, rc);
+            }
+        }
+        if (bmin != 0x7fffffff && bmax - bmin >= F2_CWB) return false;
+        // level-2 outputs kk in [max(M0-1, 0), M1): level-1 columns they read must be computed here
+        for (int kk = std::max(M0 - 1, 0); kk < M1; ++kk)
+            for (int i = 0; i < F; ++i) {
+                const int kv = 2 * kk + sft - (F - 2) + i;
+                const int c = (per ? kv : ext_index(kv, bw1, mode)) - KV0;
+                if (c < 0 || c >= nk) return false;
+            }
+        // stored level-1 columns
+        const int n1core = std::max(0, std::min(2 * M1, bw1) - 2 * M0);
+        if (2 * M0 - KV0 - 1 < 0 || 2 * M0 - KV0 + n1core > nk) return false;
+    }
+    if (2 * pl.NMs * pl.nstrips < bw1) return false;  // every level-1 column is stored by some strip
+    for (int chunk = 0; chunk < pl.nchunks; ++chunk) {
+        const int R0 = chunk * pl.NRc, R1 = std::min(R0 + pl.NRc, bh2);
+        if (R1 <= R0) return false;
+        const int VR0 = 2 * (R0 - 1) + sft - (F - 2), VRl = 2 * R1 + sft - 1;
+        const int PR0 = per ? VR0 : std::max(VR0, 0);
+        const int Pl = per ? VRl : std::min(VRl, bh1 - 1);
+        const int nvs = (VRl - VR0 + 1 + F2_SB - 1) / F2_SB;
+        if (Pl < PR0) return false;
+        for (int u = 0; u < nvs; ++u) {
+            const int step = u + LAGS;
+            const int newest = std::min(Pl, PR0 + F2_SB * step + F2_SB - 1);  // last row H1 has written
+            for (int i = 0; i < F2_SB; ++i) {
+                const int v = VR0 + F2_SB * u + i;
+                // is this virtual row read by a level-2 row that matters?  rows m in [max(R0-1,0), R1)
+                const int mlo = (v - sft - 1 + 1) / 2 - 1, mhi = (v - sft + (F - 2)) / 2 + 1;
+                bool used = false;
+                for (int m = std::max(std::max(R0 - 1, 0), mlo); m <= std::min(R1 - 1, mhi); ++m)
+                    if (v >= 2 * m + sft - (F - 2) && v <= 2 * m + sft + 1) used = true;
+                if (!used) continue;
+                const int rr = per ? v : ext_index(v, bh1, mode);
+                if (rr < PR0 || rr > newest || rr + RING <= newest) return false;
+            }
+        }
+        (void)FILL2;
+        // stored level-1 rows are produced
+        const int r1lo = 2 * R0, r1hi = std::min(2 * R1, bh1);
+        if (r1lo < r1hi && (r1lo - 1 < PR0 && r1lo > 0)) return false;
+        if (r1hi - 1 > Pl) return false;
+    }
+    if (2 * pl.NRc * pl.nchunks < bh1) return false;
+    return true;
+}
+
+template <int WID>
+size_t f2_smem_bytes(size_t es)
+{
+    using Cfg = F2Cfg<WID>;
+    size_t b = 0;
+    b += (size_t)F2_NST * F2_SR * (F2_CW + F2_CWB) * es;
+    b += 2 * F2_SB * F2_CW * sizeof(double);
+    b += (size_t)Cfg::RING * F2_NKP * sizeof(double);
+    b += 2 * 2 * F2_NKP * sizeof(double);
+    b += 3 * 8 * F2_TW1 * sizeof(int32_t);
+    b += 3 * 4 * F2_TW2 * sizeof(int32_t);
+    b += (es == 1 ? 256 : 0) * sizeof(double);
+    b += F2_NST * sizeof(uint64_t);
+    b += 64;
+    return b;
+}
+
+template <typename Tin, int WID>
+int f2_launch(spihtb_ctx *ctx, const CUtensorMap &tmA, const CUtensorMap &tmB, const F2K &k, int nz)
+{
+    const size_t smem = f2_smem_bytes<WID>(sizeof(Tin));
+    static bool attr_set = false;
+    if (!attr_set) {
+        SPIHTB_CUDA_CHECK(cudaFuncSetAttribute(dwt_fwd12_kernel<Tin, WID>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               (int)smem));
+        attr_set = true;
+    }
+    const long long nb = (long long)nz * k.nstrips * k.nchunks;
+    if (nb > 0x7fffffffLL) {
+        set_error("forward DWT grid too large");
+        return SPIHTB_ESHAPE;
+    }
+    dwt_fwd12_kernel<Tin, WID><<<(unsigned)nb, F2_NT, smem, ctx->stream>>>(tmA, tmB, k);
+    ctx->launches++;
+    SPIHTB_CUDA_CHECK(cudaGetLastError());
+    return SPIHTB_OK;
+}
+
+template <int WID>
+int f2_run(spihtb_ctx *ctx, const void *src, int pixel_dtype, const XformArgs &x, int32_t *coeffs, double *ll2,
+           const PyrFuse *pf, const double *u8lut, bool *done)
+{
+    using Cfg = F2Cfg<WID>;
+    const spihtb_geom &g = x.g;
+    const int nz = x.B * x.C;
+    *done = false;
+    const size_t es = pixel_dtype == SPIHTB_F64 ? 8 : (pixel_dtype == SPIHTB_U8 ? 1 : 4);
+    const int src_h = g.in_h[0], src_w = g.in_w[0];
+    if (g.levels < 3) return SPIHTB_OK;
+    if (((size_t)src_w * es) % 16 != 0 || (reinterpret_cast<uintptr_t>(src) & 15) != 0) return SPIHTB_OK;
+    if (getenv("SPIHTB_NO_FUSED12")) return SPIHTB_OK;
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return SPIHTB_OK;
+
+    F2Plan pl;
+    const int bw2 = g.band_w[1], bh2 = g.band_h[1];
+    pl.nstrips = (bw2 + Cfg::NM - 1) / Cfg::NM;
+    pl.NMs = (bw2 + pl.nstrips - 1) / pl.nstrips;
+    // row chunks: enough CTAs for a few waves, chunks no shorter than 32 level-2 rows
+    const long long want = 8LL * ctx->sm_count;
+    int nch = (int)std::min<long long>((want + (long long)nz * pl.nstrips - 1) / ((long long)nz * pl.nstrips),
+                                       std::max(1, bh2 / 32));
+    if (const char *e = getenv("SPIHTB_F12_CHUNKS")) nch = std::max(1, atoi(e));
+    nch = std::max(1, std::min(nch, bh2));
+    pl.NRc = (bh2 + nch - 1) / nch;
+    pl.nchunks = (bh2 + pl.NRc - 1) / pl.NRc;
+    if (!f2_validate<WID>(g, pl)) return SPIHTB_OK;
+
+    // tensor maps over the pixel planes {columns, rows, planes}
+    CUtensorMap tmA, tmB;
+    const CUtensorMapDataType dt = pixel_dtype == SPIHTB_F64 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64
+                                   : (pixel_dtype == SPIHTB_U8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32);
+    const cuuint64_t dims[3] = {(cuuint64_t)src_w, (cuuint64_t)src_h, (cuuint64_t)nz};
+    const cuuint64_t strides[2] = {(cuuint64_t)src_w * es, (cuuint64_t)src_w * src_h * es};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const cuuint32_t boxA[3] = {F2_CW, 1, 1}, boxB[3] = {F2_CWB, 1, 1};
+    CUresult r1 = enc(&tmA, dt, 3, const_cast<void *>(src), dims, strides, boxA, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r2 = enc(&tmB, dt, 3, const_cast<void *>(src), dims, strides, boxB, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r1 != CUDA_SUCCESS || r2 != CUDA_SUCCESS) return SPIHTB_OK;  // shape the TMA unit cannot address: other path
+
+    F2K k;
+    k.src_h = src_h; k.src_w = src_w;
+    k.bh1 = g.band_h[0]; k.bw1 = g.band_w[0]; k.bh2 = bh2; k.bw2 = bw2;
+    k.Hc = g.enc_h; k.Wc = g.enc_w;
+    k.sh1 = g.off_h[0]; k.sw1 = g.off_w[0]; k.sh2 = g.off_h[1]; k.sw2 = g.off_w[1];
+    k.mode = g.mode; k.C = x.C;
+    k.nstrips = pl.nstrips; k.nchunks = pl.nchunks; k.NMs = pl.NMs; k.NRc = pl.NRc;
+    k.use_b = 0;
+    k.coeffs = coeffs;
+    k.ll2 = ll2;
+    k.dp = pf ? pf->dp : nullptr;
+    k.maxabs = pf ? pf->maxabs : nullptr;
+    k.NH = g.enc_h / 2; k.NW = g.enc_w / 2;
+    for (int c = 0; c < 8; ++c) k.scale[c] = x.scale[c];
+    k.q = x.q;
+    k.u8lut = u8lut;
+    int rc;
+    if (pixel_dtype == SPIHTB_F64)
+        rc = f2_launch<double, WID>(ctx, tmA, tmB, k, nz);
+    else if (pixel_dtype == SPIHTB_U8)
+        rc = f2_launch<uint8_t, WID>(ctx, tmA, tmB, k, nz);
+    else
+        rc = f2_launch<float, WID>(ctx, tmA, tmB, k, nz);
+    if (rc) return rc;
+    *done = true;
+    return SPIHTB_OK;
+}
+
+}  // namespace
+
+// Levels 1 and 2 in one kernel when the geometry allows it (*done says whether it ran): coefficient bands of both
+// levels, pyramid cells and maxabs (pf), level-2 approximation -> ll2 [nz][band_h[1]][band_w[1]] float64.
+int launch_forward_fused12(spihtb_ctx *ctx, const void *src, int pixel_dtype, const XformArgs &x, int32_t *coeffs,
+                           double *ll2, const PyrFuse *pf, const double *u8lut, bool *done)
+{
+    switch (x.g.wavelet) {
+        case SPIHTB_WAVELET_BIOR22: return f2_run<SPIHTB_WAVELET_BIOR22>(ctx, src, pixel_dtype, x, coeffs, ll2, pf, u8lut, done);
+        case SPIHTB_WAVELET_BIOR44: return f2_run<SPIHTB_WAVELET_BIOR44>(ctx, src, pixel_dtype, x, coeffs, ll2, pf, u8lut, done);
+        case SPIHTB_WAVELET_BIOR68: return f2_run<SPIHTB_WAVELET_BIOR68>(ctx, src, pixel_dtype, x, coeffs, ll2, pf, u8lut, done);
+    }
+    *done = false;
+    return SPIHTB_OK;
+}
+
+}  // namespace spihtb

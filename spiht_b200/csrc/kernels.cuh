@@ -79,5 +79,8 @@ struct PyrFuse {
 int launch_forward(spihtb_ctx *ctx, const void *pixels, const XformArgs &x, int32_t *coeffs,
                    const PyrFuse *pf = nullptr);
 int launch_inverse(spihtb_ctx *ctx, const int32_t *coeffs, const XformArgs &x, void *pixels_out);
+// dwt_fwd2.cu: levels 1 and 2 fused (TMA-staged tiles); *done = false when the geometry takes the other path
+int launch_forward_fused12(spihtb_ctx *ctx, const void *src, int pixel_dtype, const XformArgs &x, int32_t *coeffs,
+                           double *ll2, const PyrFuse *pf, const double *u8lut, bool *done);
 
 }  // namespace spihtb
