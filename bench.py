@@ -358,6 +358,9 @@ def run_b200(args):
     px_bytes = 4 * C * S * S
     coef_bytes = 4 * C * g.enc_h * g.enc_w
     det1 = 4 * C * (g.enc_h * g.enc_w - g.off_h[0] * g.off_w[0])      # level-1 detail blocks (incl. gaps)
+    fused12 = ctx.forward_path() == 12                                 # levels 1+2 in one kernel (csrc/dwt_fwd2.cu)
+    if fused12 and g.levels > 1:
+        det1 += 4 * C * (g.off_h[0] * g.off_w[0] - g.off_h[1] * g.off_w[1])   # + level-2 detail blocks
     stream_bytes = (max_bits + 7) // 8
     alg = {  # bytes per image and launch
         "dwt_fwd_level1": px_bytes + det1,
@@ -407,10 +410,8 @@ def run_b200(args):
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": round(dom_gbs, 1), "peak": peak, "unit": "GB/s",
                      "frac": round(dom_gbs / peak, 4), "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_image": alg[dom], "ms_per_launch": round(stage_ms[dom], 4),
-                     # the same kernel credited with the pyramid's read of the bands it writes (which the fused
-                     # epilogue makes unnecessary); the conservative figure above counts pixels in + details out
-                     "frac_with_fused_pyramid_read": (round((alg[dom] + det1) * B / (stage_ms[dom] / 1e3) / 1e9 / peak, 4)
-                                                      if dom == "dwt_fwd_level1" and stage_ms[dom] > 0 else None)},
+                     "kernel_name": ("dwt_fwd12_kernel (levels 1+2 fused, TMA-staged)" if fused12 and dom == "dwt_fwd_level1"
+                                     else dom)},
         "step_roofline": {"achieved": round(step_gbs, 1), "peak": peak, "unit": "GB/s",
                           "frac": round(step_gbs / peak, 4), "algorithmic_bytes_per_image": A,
                           "strict_io_frac": round((px_bytes + stream_bytes) * B / (ms_per_step / 1e3) / 1e9 / peak, 4)},

@@ -228,7 +228,7 @@ dwt_fwd12_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     using Cfg = F2Cfg<WID>;
     constexpr int F = Cfg::F, HF = Cfg::HF, FILL1 = Cfg::FILL1, FILL2 = Cfg::FILL2, LAGS = Cfg::LAGS, RING = Cfg::RING;
     constexpr int ES = (int)sizeof(Tin);
-    constexpr int ROWB = (F2_CW + F2_CWB) * ES;   // bytes of one staged row (box A, then box B)
+    constexpr int ROWB = ((F2_CW + F2_CWB) * ES + 127) / 128 * 128;   // bytes of one staged row (box A, then box B); TMA destinations are 128-byte aligned
     constexpr int STAGEB = F2_SR * ROWB;
     constexpr bool U8 = sizeof(Tin) == 1;
 
@@ -276,13 +276,16 @@ dwt_fwd12_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (U8)
         for (int k = tid; k < 256; k += F2_NT) s_lut[k] = p.u8lut[k];
     __syncthreads();
+    // TMA boxes start at a 16-byte boundary of the row (the unit's addressing granularity)
+    constexpr int AL = 16 / ES;
+    const int AX0 = XV0 - (((XV0 % AL) + AL) % AL);
     const int rc = ext_index(XV0 + min(tid, cw - 1), p.src_w, mode);  // real input column of this thread
-    const bool inA = rc >= XV0 && rc < XV0 + F2_CW;
+    const bool inA = rc >= AX0 && rc < AX0 + F2_CW;
     if (!inA) atomicMin(&s_misc[0], rc);
     __syncthreads();
-    const int BXB = s_misc[0];
-    const bool need_b = BXB != 0x7fffffff;   // CTA-uniform
-    const uint32_t in_off = (uint32_t)((inA ? rc - XV0 : F2_CW + (rc - BXB)) * ES);
+    const bool need_b = s_misc[0] != 0x7fffffff;   // CTA-uniform
+    const int BXB = need_b ? s_misc[0] - (((s_misc[0] % AL) + AL) % AL) : 0;
+    const uint32_t in_off = (uint32_t)((inA ? rc - AX0 : F2_CW + (rc - BXB)) * ES);
     // level-1 column this thread's V2 window reads (threads < nk)
     const int c1 = min(tid, nk - 1);
     const int c1map = per ? c1 : min(max(ext_index(KV0 + c1, p.bw1, mode) - KV0, 0), nk - 1);
@@ -303,7 +306,7 @@ dwt_fwd12_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int i = 0; i < F2_SR; ++i) {
             const int row = ext_index(IR0 + F2_SR * q + i, p.src_h, mode);
             const uint32_t dst = in0 + s * STAGEB + i * ROWB;
-            tma_load_3d(dst, &tmA, XV0, row, z, bar);
+            tma_load_3d(dst, &tmA, AX0, row, z, bar);
             if (need_b) tma_load_3d(dst + F2_CW * ES, &tmB, BXB, row, z, bar);
         }
     };
@@ -533,7 +536,7 @@ struct F2Plan {
 // produced and not yet overwritten).  Degenerate geometries (planes a few filter lengths wide) fail here and take
 // the level-by-level kernel.
 template <int WID>
-bool f2_validate(const spihtb_geom &g, const F2Plan &pl)
+bool f2_validate(const spihtb_geom &g, const F2Plan &pl, int es)
 {
     using Cfg = F2Cfg<WID>;
     constexpr int F = Cfg::F, HF = Cfg::HF, FILL2 = Cfg::FILL2, LAGS = Cfg::LAGS, RING = Cfg::RING;
@@ -548,17 +551,19 @@ bool f2_validate(const spihtb_geom &g, const F2Plan &pl)
         if (nm <= 0 || nm > Cfg::NM) return false;
         const int KV0 = 2 * (M0 - 1) + sft - (F - 2), nk = 2 * (nm + 1) + F - 2;
         const int XV0 = 2 * KV0 + sft - (F - 2), cw = 2 * nk + F - 2;
-        if (nk > Cfg::NK || cw > F2_CW) return false;
-        // input columns: box A [XV0, XV0 + CW), the rest within one box B
+        const int AL = 16 / es;  // box starts are 16-byte aligned
+        const int AX0 = XV0 - (((XV0 % AL) + AL) % AL);
+        if (nk > Cfg::NK || XV0 + cw > AX0 + F2_CW) return false;
+        // input columns: box A [AX0, AX0 + CW), the rest within one box B
         int bmin = 0x7fffffff, bmax = -0x7fffffff;
         for (int t = 0; t < cw; ++t) {
             const int rc = ext_index(XV0 + t, src_w, mode);
-            if (!(rc >= XV0 && rc < XV0 + F2_CW)) {
+            if (!(rc >= AX0 && rc < AX0 + F2_CW)) {
                 bmin = std::min(bmin, rc);
                 bmax = std::max(bmax, rc);
             }
         }
-        if (bmin != 0x7fffffff && bmax - bmin >= F2_CWB) return false;
+        if (bmin != 0x7fffffff && bmax - (bmin - (((bmin % AL) + AL) % AL)) >= F2_CWB) return false;
         // level-2 outputs kk in [max(M0-1, 0), M1): level-1 columns they read must be computed here
         for (int kk = std::max(M0 - 1, 0); kk < M1; ++kk)
             for (int i = 0; i < F; ++i) {
@@ -609,7 +614,7 @@ size_t f2_smem_bytes(size_t es)
 {
     using Cfg = F2Cfg<WID>;
     size_t b = 0;
-    b += (size_t)F2_NST * F2_SR * (F2_CW + F2_CWB) * es;
+    b += (size_t)F2_NST * F2_SR * (((F2_CW + F2_CWB) * es + 127) / 128 * 128);
     b += 2 * F2_SB * F2_CW * sizeof(double);
     b += (size_t)Cfg::RING * F2_NKP * sizeof(double);
     b += 2 * 2 * F2_NKP * sizeof(double);
@@ -653,6 +658,9 @@ int f2_run(spihtb_ctx *ctx, const void *src, int pixel_dtype, const XformArgs &x
     const size_t es = pixel_dtype == SPIHTB_F64 ? 8 : (pixel_dtype == SPIHTB_U8 ? 1 : 4);
     const int src_h = g.in_h[0], src_w = g.in_w[0];
     if (g.levels < 3) return SPIHTB_OK;
+    // periodization pads an odd-length level-1 band with a repeated sample before level 2: the band is then not the
+    // periodic continuation the strip / chunk halos assume
+    if (g.mode == SPIHTB_MODE_PERIODIZATION && ((g.band_h[0] | g.band_w[0]) & 1)) return SPIHTB_OK;
     if (((size_t)src_w * es) % 16 != 0 || (reinterpret_cast<uintptr_t>(src) & 15) != 0) return SPIHTB_OK;
     if (getenv("SPIHTB_NO_FUSED12")) return SPIHTB_OK;
     EncodeTiledFn enc = encode_tiled_fn();
@@ -660,7 +668,11 @@ int f2_run(spihtb_ctx *ctx, const void *src, int pixel_dtype, const XformArgs &x
 
     F2Plan pl;
     const int bw2 = g.band_w[1], bh2 = g.band_h[1];
-    pl.nstrips = (bw2 + Cfg::NM - 1) / Cfg::NM;
+    // widest strip whose input columns fit box A behind a 16-byte aligned start: cw + (16 / es - 1) <= CW
+    const int nk_max = (F2_CW - (int)(16 / es - 1) - (Cfg::F - 2)) / 2;
+    const int nm_max = std::min(Cfg::NM, (nk_max - (Cfg::F - 2)) / 2 - 1);
+    if (nm_max < 8) return SPIHTB_OK;
+    pl.nstrips = (bw2 + nm_max - 1) / nm_max;
     pl.NMs = (bw2 + pl.nstrips - 1) / pl.nstrips;
     // row chunks: enough CTAs for a few waves, chunks no shorter than 32 level-2 rows
     const long long want = 8LL * ctx->sm_count;
@@ -670,7 +682,7 @@ int f2_run(spihtb_ctx *ctx, const void *src, int pixel_dtype, const XformArgs &x
     nch = std::max(1, std::min(nch, bh2));
     pl.NRc = (bh2 + nch - 1) / nch;
     pl.nchunks = (bh2 + pl.NRc - 1) / pl.NRc;
-    if (!f2_validate<WID>(g, pl)) return SPIHTB_OK;
+    if (!f2_validate<WID>(g, pl, (int)es)) return SPIHTB_OK;
 
     // tensor maps over the pixel planes {columns, rows, planes}
     CUtensorMap tmA, tmB;

@@ -27,8 +27,8 @@ CASES = [
     ((3, 257, 132), "f32", "bior2.2", "symmetric", None, 2),
     ((3, 128, 256), "f32", "bior2.2", "periodization", None, None),
     ((2, 512, 512), "f32", "bior2.2", "periodization", None, 4),      # config-5 shape
-    ((1, 190, 72), "f64", "bior2.2", "periodization", 3, 2),
-    ((1, 333, 304), "u8", "bior2.2", "periodization", 3, None),
+    ((1, 192, 72), "f64", "bior2.2", "periodization", 3, 2),
+    ((1, 336, 304), "u8", "bior2.2", "periodization", 3, None),
     ((2, 256, 192), "f32", "bior4.4", "symmetric", None, None),
     ((3, 403, 368), "f32", "bior4.4", "reflect", 3, 3),
     ((1, 520, 528), "f64", "bior4.4", "periodization", 4, 2),
@@ -95,9 +95,12 @@ def test_fused12_falls_back_on_unsupported_geometry():
     import spiht_b200 as spiht
     from spiht_b200 import _lib, batch
     ctx = _lib.get_context(0)
-    for shape, level in [((1, 61, 83), None), ((1, 148, 140), 2), ((3, 20, 24), None)]:
+    for shape, mode, level in [((1, 61, 83), "reflect", None), ((1, 148, 140), "reflect", 2),
+                               ((3, 20, 24), "reflect", None),
+                               # periodization pads an odd level-1 band before level 2: not the periodic halo
+                               ((1, 190, 72), "periodization", 3)]:
         c, h, w = shape
         px = torch.from_numpy(synth_image(c, h, w, 1)[None].astype(np.float32)).cuda()
-        g = _lib.plan(h, w, "bior2.2", "reflect", level)
-        batch.forward(px, g, spiht.SpihtSettings())
+        g = _lib.plan(h, w, "bior2.2", mode, level)
+        batch.forward(px, g, spiht.SpihtSettings(mode=mode))
         assert ctx.forward_path() == 1
