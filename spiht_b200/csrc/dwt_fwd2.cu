@@ -117,6 +117,9 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *tm,
         : "memory");
 }
 
+// out-of-line boundary rule (keeps the division sequences out of the streaming loop)
+__device__ __noinline__ int ext_index_f2(int g, int n, int mode) { return ext_index(g, n, mode); }
+
 template <typename Tin>
 __device__ __forceinline__ double f2_px(uint32_t saddr, const double *lut);
 template <>
@@ -298,19 +301,27 @@ dwt_fwd12_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    auto issue_stage = [&](int q) {  // one thread
+    // one warp issues a stage: lane i loads row i into box A, lane 8 + i the same row into box B.  (A row
+    // coordinate outside the plane goes through the boundary map; the division sequence of the map stays out of
+    // the common path.)  The expect-tx arrive may land after the first complete-tx: the phase cannot complete
+    // before the arrive, and the transaction count may be transiently negative.
+    auto issue_stage = [&](int q) {
         const int s = q % F2_NST;
         const uint32_t bar = bar0 + 8 * s;
-        mbar_expect_tx(bar, (uint32_t)(F2_SR * (F2_CW + (need_b ? F2_CWB : 0)) * ES));
-#pragma unroll
-        for (int i = 0; i < F2_SR; ++i) {
-            const int row = ext_index(IR0 + F2_SR * q + i, p.src_h, mode);
+        if (lane == 0) mbar_expect_tx(bar, (uint32_t)(F2_SR * (F2_CW + (need_b ? F2_CWB : 0)) * ES));
+        __syncwarp();
+        if (lane < 2 * F2_SR) {
+            const int i = lane & (F2_SR - 1);
+            const int vrow = IR0 + F2_SR * q + i;
+            const int row = (unsigned)vrow < (unsigned)p.src_h ? vrow : ext_index_f2(vrow, p.src_h, mode);
             const uint32_t dst = in0 + s * STAGEB + i * ROWB;
-            tma_load_3d(dst, &tmA, AX0, row, z, bar);
-            if (need_b) tma_load_3d(dst + F2_CW * ES, &tmB, BXB, row, z, bar);
+            if (lane < F2_SR)
+                tma_load_3d(dst, &tmA, AX0, row, z, bar);
+            else if (need_b)
+                tma_load_3d(dst + F2_CW * ES, &tmB, BXB, row, z, bar);
         }
     };
-    if (tid == 0)
+    if (warp == 0)
         for (int q = 0; q < F2_NST && q < nstages; ++q) issue_stage(q);
 
     // ---- per-plane constants
@@ -365,7 +376,7 @@ dwt_fwd12_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             for (int i = 0; i < F - 2; ++i) w1[i] = nw[i];
         }
         __syncthreads();  // A: (lo, hi) rows visible; the stage is consumed
-        if (tid == 0 && q + F2_NST < nstages && q < nstages) issue_stage(q + F2_NST);
+        if (warp == 0 && q + F2_NST < nstages && q < nstages) issue_stage(q + F2_NST);
 
         // ================= H1: level-1 outputs of production rows PR0 + 4 step + j
         if (step >= 0 && step < nps) {
@@ -412,7 +423,7 @@ dwt_fwd12_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
                 for (int i = 0; i < F2_SB; ++i) {
                     const int v = VR0 + F2_SB * u + i;                       // virtual level-1 row
-                    const int rr = per ? v : ext_index(v, p.bh1, mode);      // the row that holds it
+                    const int rr = (per || (unsigned)v < (unsigned)p.bh1) ? v : ext_index_f2(v, p.bh1, mode);  // the row that holds it
                     y[i] = s_ring[((rr - PR0) & (RING - 1)) * F2_NKP + c1map];
                 }
                 if (u >= FILL2) {
