@@ -166,61 +166,52 @@ __device__ __forceinline__ void f2_hfilter(const double2 *pairs, double &o_lo, d
     o_hi = hi;
 }
 
-// Tile rows -> coefficient array and pyramid cells, for one detail band of one level.
-// A tile row holds band columns kfirst-1 .. kfirst+ncore-1 of one band row at index 3 + sh .. , where
-// sh = (element address of column kfirst) & 3, so that index 4v maps to a 16-byte aligned address.
-struct BandOut {
-    int ro, co;      // band origin in the coefficient array
-    int bh, bw;      // band size
+// ---- tiles: quantised detail coefficients of the rows in flight, staged in shared memory ----
+// A tile row holds one band row of one detail band; index i is array column TB + i, TB even (so that the two
+// columns of a pyramid cell sit at an even / odd index pair in every row).  OUT copies the stored part of a tile
+// row to the coefficient array and forms the cells whose second row and second column are stored by this task.
+struct BandTile {
+    int ro, co;   // band origin in the coefficient array
+    int tb;       // array column of tile index 0 (even)
+    int i0, n;    // stored columns: tile indices [i0, i0 + n)
+    int cmin;     // first array column of the band (cells need their first column inside the band)
 };
-// copy one tile row (warp-wide): band row r, columns [kfirst, kfirst + ncore)
-__device__ __forceinline__ uint32_t f2_copy_row(const int32_t *trow, int32_t *plane, int Wc, const BandOut &b, int r,
-                                                int kfirst, int ncore, int lane, int tw4)
+// one tile row -> coefficient array (warp-wide, 4-byte coalesced stores); returns the largest magnitude stored
+__device__ __forceinline__ uint32_t f2_copy_row(const int32_t *trow, int32_t *plane, int Wc, const BandTile &b, int r,
+                                                int lane)
 {
-    const long long e = (long long)(b.ro + r) * Wc + b.co + kfirst;  // element offset within the plane of column kfirst
-    const int sh = (int)((reinterpret_cast<uintptr_t>(plane + e) >> 2) & 3);
-    int32_t *g0 = plane + e - sh - 4;  // address of tile index 0 (16-byte aligned)
+    int32_t *g = plane + (size_t)(b.ro + r) * Wc + (b.tb + b.i0);
+    const int32_t *t = trow + b.i0;
     uint32_t mx = 0;
-    const int lo = 4 + sh, hi = 4 + sh + ncore;  // valid tile indices
-    for (int v = lane; v < tw4; v += 32) {
-        const int i0 = 4 * v;
-        if (i0 + 4 <= lo || i0 >= hi) continue;
-        const int4 q = *reinterpret_cast<const int4 *>(trow + i0);
-        if (i0 >= lo && i0 + 4 <= hi) {
-            *reinterpret_cast<int4 *>(g0 + i0) = q;
-            mx = max(mx, max(max(absu(q.x), absu(q.y)), max(absu(q.z), absu(q.w))));
-        } else {
-            const int32_t qq[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
-                if (i0 + u >= lo && i0 + u < hi) {
-                    g0[i0 + u] = qq[u];
-                    mx = max(mx, absu(qq[u]));
-                }
+    for (int u = 0; u < F2_TW1 / 32; ++u) {
+        const int i = lane + 32 * u;
+        if (i < b.n) {
+            const int32_t v = t[i];
+            g[i] = v;
+            mx = max(mx, absu(v));
         }
     }
     return mx;
 }
-// cells whose second row is band row r (array row ro + r odd) and whose second column is stored by this strip
-__device__ __forceinline__ void f2_cells_row(const int32_t *trow_prev, const int32_t *trow, const int32_t *plane, int Wc,
-                                             uint8_t *dpz, int NH, int NW, const BandOut &b, int r, int kfirst, int ncore,
-                                             int lane)
+// cells whose second row is band row r (array row ro + r, odd) from tile rows r - 1 and r: a lane takes four
+// consecutive tile indices = two cells
+__device__ __forceinline__ void f2_cells_row(const int32_t *trow_prev, const int32_t *trow, uint8_t *dpz, int NH, int NW,
+                                             const BandTile &b, int r, int lane, int tw)
 {
-    const int ar = b.ro + r;
-    const int a = ar >> 1;
+    const int a = (b.ro + r) >> 1;
     if (a >= NH) return;
-    const long long e1 = (long long)ar * Wc + b.co + kfirst, e0 = e1 - Wc;
-    const int sh1 = (int)((reinterpret_cast<uintptr_t>(plane + e1) >> 2) & 3);
-    const int sh0 = (int)((reinterpret_cast<uintptr_t>(plane + e0) >> 2) & 3);
-    // second columns: band columns k in [kfirst, kfirst+ncore) with (co + k) odd and k >= 1
-    int k = kfirst + (((b.co + kfirst) & 1) ? 0 : 1) + 2 * lane;
-    for (; k < kfirst + ncore; k += 64) {
-        if (k < 1) continue;
-        const int bcol = (b.co + k) >> 1;
-        if (bcol >= NW) continue;
-        const int i1 = 4 + sh1 + (k - kfirst), i0 = 4 + sh0 + (k - kfirst);
-        const uint32_t m = max(max(absu(trow[i1]), absu(trow[i1 - 1])), max(absu(trow_prev[i0]), absu(trow_prev[i0 - 1])));
-        dpz[(size_t)a * NW + bcol] = (uint8_t)plane1(m);
+    uint8_t *drow = dpz + (size_t)a * NW;
+    for (int i = 4 * lane; i < tw; i += 128) {
+        if (i + 4 <= b.i0 || i >= b.i0 + b.n) continue;
+        const int4 q1 = *reinterpret_cast<const int4 *>(trow + i);
+        const int4 q0 = *reinterpret_cast<const int4 *>(trow_prev + i);
+        const uint32_t m0 = max(max(absu(q0.x), absu(q0.y)), max(absu(q1.x), absu(q1.y)));
+        const uint32_t m1 = max(max(absu(q0.z), absu(q0.w)), max(absu(q1.z), absu(q1.w)));
+        // a cell is this task's when its second column (odd index) is stored and its first column lies in the band
+        const int bc = (b.tb + i) >> 1;
+        if (i + 1 >= b.i0 && i + 1 < b.i0 + b.n && b.tb + i >= b.cmin && bc < NW) drow[bc] = (uint8_t)plane1(m0);
+        if (i + 3 >= b.i0 && i + 3 < b.i0 + b.n && b.tb + i + 2 >= b.cmin && bc + 1 < NW) drow[bc + 1] = (uint8_t)plane1(m1);
     }
 }
 
@@ -327,21 +318,54 @@ dwt_fwd12_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // ---- per-plane constants
     const int zc = z % p.C;
     const double mq = p.scale[zc], qs = p.q;
+    const bool unit = mq == 1.0;   // (1.0 x) q == x q exactly
     int32_t *cplane = p.coeffs + (size_t)z * p.Hc * p.Wc;
     uint8_t *dpz = p.dp ? p.dp + (size_t)z * p.NH * p.NW : nullptr;
-    const BandOut B1[3] = {{0, p.sw1, p.bh1, p.bw1}, {p.sh1, 0, p.bh1, p.bw1}, {p.sh1, p.sw1, p.bh1, p.bw1}};  // ad, da, dd
-    // stored level-1 columns / rows of this task
+    // stored level-1 columns / rows of this task; level-1 column k sits at H1 thread c = k - KV0
     const int k1first = 2 * M0, n1core = max(0, min(2 * M1, p.bw1) - k1first);
-    const int c1first = k1first - KV0;
     const int r1lo = 2 * R0, r1hi = min(2 * R1, p.bh1);
-    const int n2core = nm;
+    // tiles: band b of level 1 (ad, da, dd), then of level 2
+    auto make_tile = [&](int ro, int co, int kfirst, int n) {
+        BandTile t;
+        t.ro = ro;
+        t.co = co;
+        t.tb = ((co + kfirst) & ~1) - 2;
+        t.i0 = co + kfirst - t.tb;
+        t.n = n;
+        t.cmin = co;
+        return t;
+    };
+    const BandTile T1ad = make_tile(0, p.sw1, k1first, n1core), T1da = make_tile(p.sh1, 0, k1first, n1core),
+                   T1dd = make_tile(p.sh1, p.sw1, k1first, n1core);
+    const BandTile T2ad = make_tile(0, p.sw2, M0, nm), T2da = make_tile(p.sh2, 0, M0, nm), T2dd = make_tile(p.sh2, p.sw2, M0, nm);
+
+    // ---- H1 task of this thread: level-1 column c of the lo (warp even) or hi (warp odd) rows
+    const int h1_lohi = warp & 1;
+    const int h1_c = (warp >> 1) * 32 + lane;
+    const int h1_k = KV0 + h1_c;
+    // tile indices of this column (negative: not staged).  Staged: columns k1first - 1 .. k1first + n1core - 1
+    const bool h1_core = h1_c < nk && h1_k >= max(k1first - 1, 0) && h1_k < k1first + n1core;
+    const int h1_ta = h1_core ? (h1_lohi ? T1da.co + h1_k - T1da.tb : T1ad.co + h1_k - T1ad.tb) : -1;  // ad | da
+    const int h1_tb = h1_core && h1_lohi ? T1dd.co + h1_k - T1dd.tb : -1;                                // dd
+    // ---- H2 task: level-2 row e, lo / hi, column kk = M0 - 1 + c2
+    const int h2_e = warp >> 2, h2_lohi = (warp >> 1) & 1;
+    const int h2_c = (warp & 1) * 32 + lane;
+    const int h2_k = M0 - 1 + h2_c;
+    const bool h2_on = h2_c < nm + 1 && h2_k >= 0;
+    const int h2_ta = h2_on ? (h2_lohi ? T2da.co + h2_k - T2da.tb : T2ad.co + h2_k - T2ad.tb) : -1;
+    const int h2_tb = h2_on && h2_lohi ? T2dd.co + h2_k - T2dd.tb : -1;
+    double *ll2z = p.ll2 + (size_t)z * p.bh2 * p.bw2 + h2_k;
 
     double w1[F - 2], w2[F - 2];
 #pragma unroll
     for (int i = 0; i < F - 2; ++i) w1[i] = w2[i] = 0.0;
     uint32_t mx = 0;
 
-    for (int step = -FILL1; step < nsteps; ++step) {
+    // Schedule of one iteration (three CTA barriers):
+    //   A: V1(step)            + H2(step - 1)
+    //   B: H1(step)            + OUT2(step - 1)
+    //   C: V2(step) warps 0-3  | OUT1(step) warps 4-7
+    for (int step = -FILL1; step <= nsteps; ++step) {
         const int q = step + FILL1;  // input stage
         // ================= V1: 8 input rows -> 4 (lo, hi) row pairs
         if (q < nstages) {
@@ -375,41 +399,61 @@ dwt_fwd12_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
             for (int i = 0; i < F - 2; ++i) w1[i] = nw[i];
         }
-        __syncthreads();  // A: (lo, hi) rows visible; the stage is consumed
+        // ================= H2 of the previous step: level-2 rows m = R0 - 1 + 2 (u - FILL2) + e
+        {
+            const int u = step - 1 - LAGS;
+            const int m = R0 - 1 + 2 * (u - FILL2) + h2_e;
+            if (u >= FILL2 && u < nvs && h2_on && m < R1 && m >= 0) {
+                const double2 *pairs = reinterpret_cast<const double2 *>(s_v2 + (h2_lohi * 2 + h2_e) * F2_NKP) + h2_c;
+                double o_lo, o_hi;
+                f2_hfilter<WID>(pairs, o_lo, o_hi);
+                int32_t *trow = s_t2 + (m & 3) * F2_TW2;
+                if (h2_lohi == 0) {
+                    if (h2_c >= 1 && m >= R0) ll2z[(size_t)m * p.bw2] = o_lo;  // aa -> level 3
+                    trow[0 * 4 * F2_TW2 + h2_ta] = __double2int_rz((unit ? o_hi : mq * o_hi) * qs);  // ad
+                } else {
+                    trow[1 * 4 * F2_TW2 + h2_ta] = __double2int_rz((unit ? o_lo : mq * o_lo) * qs);  // da
+                    trow[2 * 4 * F2_TW2 + h2_tb] = __double2int_rz((unit ? o_hi : mq * o_hi) * qs);  // dd
+                }
+            }
+        }
+        __syncthreads();  // A: (lo, hi) rows of level 1 and level-2 tile rows visible; the input stage is consumed
         if (warp == 0 && q + F2_NST < nstages && q < nstages) issue_stage(q + F2_NST);
 
         // ================= H1: level-1 outputs of production rows PR0 + 4 step + j
-        if (step >= 0 && step < nps) {
-            const int lohi = warp & 1, cb = warp >> 1;
-            const int c = cb * 32 + lane;
-            if (c < nk) {
-                const int k = KV0 + c;                      // level-1 column (virtual)
-                const bool kcore = c >= c1first - 1 && k >= 0 && k < k1first + n1core;  // goes to the tile
+        if (step >= 0 && step < nps && h1_c < nk) {
+            const int rbase = PR0 + F2_SB * step;
 #pragma unroll
-                for (int j = 0; j < F2_SB; ++j) {
-                    const int r = PR0 + F2_SB * step + j;
-                    if (r > Pl) break;
-                    const double2 *pairs = reinterpret_cast<const double2 *>(s_v1 + (lohi * F2_SB + j) * F2_CW) + c;
-                    double o_lo, o_hi;
-                    f2_hfilter<WID>(pairs, o_lo, o_hi);
-                    const bool rband = r >= 0 && r < p.bh1;
-                    if (lohi == 0) s_ring[((r - PR0) & (RING - 1)) * F2_NKP + c] = o_lo;  // aa
-                    if (kcore && rband) {
-                        // tile index: 3 + sh + (c - (c1first - 1)), sh from the element address of column k1first
-                        // ad: rows from 0, columns from sw1; da: rows from sh1, columns from 0
-                        const long long e = (long long)((lohi ? p.sh1 : 0) + r) * p.Wc + (lohi ? 0 : p.sw1) + k1first;
-                        const int sh = (int)((reinterpret_cast<uintptr_t>(cplane + e) >> 2) & 3);
-                        const int ti = 3 + sh + (c - (c1first - 1));
-                        if (lohi == 0) {
-                            s_t1[(0 * 8 + (r & 7)) * F2_TW1 + ti] = __double2int_rz((mq * o_hi) * qs);  // ad
-                        } else {
-                            s_t1[(1 * 8 + (r & 7)) * F2_TW1 + ti] = __double2int_rz((mq * o_lo) * qs);  // da
-                            const long long e2 = (long long)(p.sh1 + r) * p.Wc + p.sw1 + k1first;
-                            const int sh2 = (int)((reinterpret_cast<uintptr_t>(cplane + e2) >> 2) & 3);
-                            s_t1[(2 * 8 + (r & 7)) * F2_TW1 + 3 + sh2 + (c - (c1first - 1))] =
-                                __double2int_rz((mq * o_hi) * qs);  // dd
-                        }
+            for (int j = 0; j < F2_SB; ++j) {
+                const int r = rbase + j;
+                if (r > Pl) break;
+                const double2 *pairs = reinterpret_cast<const double2 *>(s_v1 + (h1_lohi * F2_SB + j) * F2_CW) + h1_c;
+                double o_lo, o_hi;
+                f2_hfilter<WID>(pairs, o_lo, o_hi);
+                if (h1_lohi == 0) s_ring[((r - PR0) & (RING - 1)) * F2_NKP + h1_c] = o_lo;  // aa
+                if (h1_ta >= 0 && (unsigned)r < (unsigned)p.bh1) {
+                    int32_t *trow = s_t1 + (r & 7) * F2_TW1;
+                    if (h1_lohi == 0) {
+                        trow[0 * 8 * F2_TW1 + h1_ta] = __double2int_rz((unit ? o_hi : mq * o_hi) * qs);  // ad
+                    } else {
+                        trow[1 * 8 * F2_TW1 + h1_ta] = __double2int_rz((unit ? o_lo : mq * o_lo) * qs);  // da
+                        trow[2 * 8 * F2_TW1 + h1_tb] = __double2int_rz((unit ? o_hi : mq * o_hi) * qs);  // dd
                     }
+                }
+            }
+        }
+        // ================= OUT2 of the previous step (warps 0-5: row e = warp & 1, band = warp >> 1)
+        {
+            const int u = step - 1 - LAGS;
+            if (u >= FILL2 && u < nvs && warp < 6) {
+                const int e = warp & 1, b = warp >> 1;
+                const int m = R0 - 1 + 2 * (u - FILL2) + e;
+                if (m >= R0 && m < R1) {
+                    const BandTile bt = make_tile(b == 0 ? 0 : p.sh2, b == 1 ? 0 : p.sw2, M0, nm);
+                    const int32_t *trow = s_t2 + (b * 4 + (m & 3)) * F2_TW2;
+                    mx = max(mx, f2_copy_row(trow, cplane, p.Wc, bt, m, lane));
+                    if (dpz && ((bt.ro + m) & 1) && m >= 1)
+                        f2_cells_row(s_t2 + (b * 4 + ((m - 1) & 3)) * F2_TW2, trow, dpz, p.NH, p.NW, bt, m, lane, F2_TW2);
                 }
             }
         }
@@ -452,59 +496,20 @@ dwt_fwd12_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
         } else if (step >= 0 && step < nps) {
             // warp 4 + j: production row j of this step, all three bands
-            const int j = warp - 4;
-            const int r = PR0 + F2_SB * step + j;
-            if (r <= Pl && r >= 0 && r < p.bh1 && n1core > 0) {
-                const bool store = r >= r1lo && r < r1hi;
+            const int r = PR0 + F2_SB * step + (warp - 4);
+            if (r <= Pl && r >= r1lo && r < r1hi && n1core > 0) {
+                const bool has_prev = r >= 1 && r - 1 >= PR0;
 #pragma unroll
                 for (int b = 0; b < 3; ++b) {
+                    const BandTile &bt = b == 0 ? T1ad : (b == 1 ? T1da : T1dd);
                     const int32_t *trow = s_t1 + (b * 8 + (r & 7)) * F2_TW1;
-                    if (store) mx = max(mx, f2_copy_row(trow, cplane, p.Wc, B1[b], r, k1first, n1core, lane, F2_TW1 / 4));
-                    if (dpz && store && ((B1[b].ro + r) & 1) && r >= 1 && r - 1 >= PR0)
-                        f2_cells_row(s_t1 + (b * 8 + ((r - 1) & 7)) * F2_TW1, trow, cplane, p.Wc, dpz, p.NH, p.NW, B1[b],
-                                     r, k1first, n1core, lane);
+                    mx = max(mx, f2_copy_row(trow, cplane, p.Wc, bt, r, lane));
+                    if (dpz && has_prev && ((bt.ro + r) & 1))
+                        f2_cells_row(s_t1 + (b * 8 + ((r - 1) & 7)) * F2_TW1, trow, dpz, p.NH, p.NW, bt, r, lane, F2_TW1);
                 }
             }
         }
         __syncthreads();  // C: (lo, hi) rows of level 2 visible
-
-        // ================= H2: level-2 rows m = R0 - 1 + 2 (u - FILL2) + e, columns kk = M0 - 1 + c2
-        if (u >= FILL2 && u < nvs) {
-            const int e = warp >> 2, lohi = (warp >> 1) & 1, cb = warp & 1;
-            const int c2 = cb * 32 + lane;
-            const int m = R0 - 1 + 2 * (u - FILL2) + e;
-            const int kk = M0 - 1 + c2;
-            if (c2 < nm + 1 && m < R1 && m >= 0 && kk >= 0) {
-                const double2 *pairs = reinterpret_cast<const double2 *>(s_v2 + (lohi * 2 + e) * F2_NKP) + c2;
-                double o_lo, o_hi;
-                f2_hfilter<WID>(pairs, o_lo, o_hi);
-                if (lohi == 0 && c2 >= 1 && m >= R0) p.ll2[((size_t)z * p.bh2 + m) * p.bw2 + kk] = o_lo;  // aa -> level 3
-                const long long ea = (long long)((lohi ? p.sh2 : 0) + m) * p.Wc + (lohi ? 0 : p.sw2) + M0;
-                const int sh = (int)((reinterpret_cast<uintptr_t>(cplane + ea) >> 2) & 3);
-                if (lohi == 0) {
-                    s_t2[(0 * 4 + (m & 3)) * F2_TW2 + 3 + sh + c2] = __double2int_rz((mq * o_hi) * qs);  // ad
-                } else {
-                    s_t2[(1 * 4 + (m & 3)) * F2_TW2 + 3 + sh + c2] = __double2int_rz((mq * o_lo) * qs);  // da
-                    const long long e2 = (long long)(p.sh2 + m) * p.Wc + p.sw2 + M0;
-                    const int sh2 = (int)((reinterpret_cast<uintptr_t>(cplane + e2) >> 2) & 3);
-                    s_t2[(2 * 4 + (m & 3)) * F2_TW2 + 3 + sh2 + c2] = __double2int_rz((mq * o_hi) * qs);  // dd
-                }
-            }
-        }
-        __syncthreads();  // D: level-2 tile rows visible
-        // ================= OUT2 (warps 0-5: row e = warp & 1, band = warp >> 1)
-        if (u >= FILL2 && u < nvs && warp < 6) {
-            const int e = warp & 1, b = warp >> 1;
-            const int m = R0 - 1 + 2 * (u - FILL2) + e;
-            if (m >= R0 && m < R1) {
-                const BandOut bo = {b == 0 ? 0 : p.sh2, b == 1 ? 0 : p.sw2, p.bh2, p.bw2};
-                const int32_t *trow = s_t2 + (b * 4 + (m & 3)) * F2_TW2;
-                mx = max(mx, f2_copy_row(trow, cplane, p.Wc, bo, m, M0, n2core, lane, F2_TW2 / 4));
-                if (dpz && ((bo.ro + m) & 1) && m >= 1)
-                    f2_cells_row(s_t2 + (b * 4 + ((m - 1) & 3)) * F2_TW2, trow, cplane, p.Wc, dpz, p.NH, p.NW, bo, m, M0,
-                                 n2core, lane);
-            }
-        }
     }
     if (p.maxabs) {
 #pragma unroll
