@@ -176,43 +176,57 @@ struct BandTile {
     int i0, n;    // stored columns: tile indices [i0, i0 + n)
     int cmin;     // first array column of the band (cells need their first column inside the band)
 };
-// one tile row -> coefficient array (warp-wide, 4-byte coalesced stores); returns the largest magnitude stored
-__device__ __forceinline__ uint32_t f2_copy_row(const int32_t *trow, int32_t *plane, int Wc, const BandTile &b, int r,
-                                                int lane)
+// What a lane does for one band in OUT, fixed for the whole task (nothing here depends on the row):
+//   copy : tile indices i0 + lane + 32 u, u < 4, those below i0 + n (bit u of cmask)
+//   cells: tile indices 4 lane .. 4 lane + 3 = two cells; bit 0 / 1 of cellmask: the cell is this task's (its
+//          second column is stored here and its first column lies in the band)
+struct LaneOut {
+    uint32_t cmask, cellmask;
+    int goff;   // array column of the lane's first copied element
+    int bc;     // cell column of the lane's first cell
+};
+__device__ __forceinline__ LaneOut make_lane_out(const BandTile &b, int lane, int NW)
 {
-    int32_t *g = plane + (size_t)(b.ro + r) * Wc + (b.tb + b.i0);
-    const int32_t *t = trow + b.i0;
+    LaneOut o;
+    o.cmask = 0;
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+        if (lane + 32 * u < b.n) o.cmask |= 1u << u;
+    o.goff = b.tb + b.i0 + lane;
+    const int i = 4 * lane;
+    o.bc = (b.tb + i) >> 1;
+    o.cellmask = 0;
+    if (i + 1 >= b.i0 && i + 1 < b.i0 + b.n && b.tb + i >= b.cmin && o.bc < NW) o.cellmask |= 1u;
+    if (i + 3 >= b.i0 && i + 3 < b.i0 + b.n && b.tb + i + 2 >= b.cmin && o.bc + 1 < NW) o.cellmask |= 2u;
+    return o;
+}
+// one tile row -> coefficient array row `grow` (warp-wide, 4-byte coalesced stores); returns the largest magnitude
+__device__ __forceinline__ uint32_t f2_copy_row(const int32_t *trow, int32_t *grow, const LaneOut &o, int i0, int lane)
+{
+    const int32_t *t = trow + i0 + lane;
+    int32_t *g = grow + o.goff;
     uint32_t mx = 0;
 #pragma unroll
-    for (int u = 0; u < F2_TW1 / 32; ++u) {
-        const int i = lane + 32 * u;
-        if (i < b.n) {
-            const int32_t v = t[i];
-            g[i] = v;
+    for (int u = 0; u < 4; ++u) {
+        if (o.cmask & (1u << u)) {
+            const int32_t v = t[32 * u];
+            g[32 * u] = v;
             mx = max(mx, absu(v));
         }
     }
     return mx;
 }
-// cells whose second row is band row r (array row ro + r, odd) from tile rows r - 1 and r: a lane takes four
-// consecutive tile indices = two cells
-__device__ __forceinline__ void f2_cells_row(const int32_t *trow_prev, const int32_t *trow, uint8_t *dpz, int NH, int NW,
-                                             const BandTile &b, int r, int lane, int tw)
+// the lane's two cells of the cell row whose second row is `trow` (first row `trow_prev`); drow: dp row of the cells
+__device__ __forceinline__ void f2_cells_row(const int32_t *trow_prev, const int32_t *trow, uint8_t *drow, const LaneOut &o,
+                                             int lane)
 {
-    const int a = (b.ro + r) >> 1;
-    if (a >= NH) return;
-    uint8_t *drow = dpz + (size_t)a * NW;
-    for (int i = 4 * lane; i < tw; i += 128) {
-        if (i + 4 <= b.i0 || i >= b.i0 + b.n) continue;
-        const int4 q1 = *reinterpret_cast<const int4 *>(trow + i);
-        const int4 q0 = *reinterpret_cast<const int4 *>(trow_prev + i);
-        const uint32_t m0 = max(max(absu(q0.x), absu(q0.y)), max(absu(q1.x), absu(q1.y)));
-        const uint32_t m1 = max(max(absu(q0.z), absu(q0.w)), max(absu(q1.z), absu(q1.w)));
-        // a cell is this task's when its second column (odd index) is stored and its first column lies in the band
-        const int bc = (b.tb + i) >> 1;
-        if (i + 1 >= b.i0 && i + 1 < b.i0 + b.n && b.tb + i >= b.cmin && bc < NW) drow[bc] = (uint8_t)plane1(m0);
-        if (i + 3 >= b.i0 && i + 3 < b.i0 + b.n && b.tb + i + 2 >= b.cmin && bc + 1 < NW) drow[bc + 1] = (uint8_t)plane1(m1);
-    }
+    if (o.cellmask == 0) return;
+    const int4 q1 = *reinterpret_cast<const int4 *>(trow + 4 * lane);
+    const int4 q0 = *reinterpret_cast<const int4 *>(trow_prev + 4 * lane);
+    const uint32_t m0 = max(max(absu(q0.x), absu(q0.y)), max(absu(q1.x), absu(q1.y)));
+    const uint32_t m1 = max(max(absu(q0.z), absu(q0.w)), max(absu(q1.z), absu(q1.w)));
+    if (o.cellmask & 1u) drow[o.bc] = (uint8_t)plane1(m0);
+    if (o.cellmask & 2u) drow[o.bc + 1] = (uint8_t)plane1(m1);
 }
 
 template <typename Tin, int WID>
@@ -339,6 +353,13 @@ dwt_fwd12_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                    T1dd = make_tile(p.sh1, p.sw1, k1first, n1core);
     const BandTile T2ad = make_tile(0, p.sw2, M0, nm), T2da = make_tile(p.sh2, 0, M0, nm), T2dd = make_tile(p.sh2, p.sw2, M0, nm);
 
+    // OUT1 (warps 4-7, all three level-1 bands) and OUT2 (warp >> 1 = band) lane constants
+    const LaneOut L1ad = make_lane_out(T1ad, lane, p.NW), L1da = make_lane_out(T1da, lane, p.NW),
+                  L1dd = make_lane_out(T1dd, lane, p.NW);
+    const int o2b = warp >> 1;
+    const BandTile T2mine = o2b == 0 ? T2ad : (o2b == 1 ? T2da : T2dd);
+    const LaneOut L2mine = make_lane_out(T2mine, lane, p.NW);
+
     // ---- H1 task of this thread: level-1 column c of the lo (warp even) or hi (warp odd) rows
     const int h1_lohi = warp & 1;
     const int h1_c = (warp >> 1) * 32 + lane;
@@ -423,21 +444,26 @@ dwt_fwd12_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // ================= H1: level-1 outputs of production rows PR0 + 4 step + j
         if (step >= 0 && step < nps && h1_c < nk) {
             const int rbase = PR0 + F2_SB * step;
+            double o_lo[F2_SB], o_hi[F2_SB];
 #pragma unroll
             for (int j = 0; j < F2_SB; ++j) {
-                const int r = rbase + j;
-                if (r > Pl) break;
                 const double2 *pairs = reinterpret_cast<const double2 *>(s_v1 + (h1_lohi * F2_SB + j) * F2_CW) + h1_c;
-                double o_lo, o_hi;
-                f2_hfilter<WID>(pairs, o_lo, o_hi);
-                if (h1_lohi == 0) s_ring[((r - PR0) & (RING - 1)) * F2_NKP + h1_c] = o_lo;  // aa
-                if (h1_ta >= 0 && (unsigned)r < (unsigned)p.bh1) {
-                    int32_t *trow = s_t1 + (r & 7) * F2_TW1;
+                f2_hfilter<WID>(pairs, o_lo[j], o_hi[j]);
+            }
+            // rows past Pl hold nothing useful: their ring / tile slots are never read
+            if (h1_lohi == 0) {
+#pragma unroll
+                for (int j = 0; j < F2_SB; ++j) s_ring[((rbase + j - PR0) & (RING - 1)) * F2_NKP + h1_c] = o_lo[j];  // aa
+            }
+            if (h1_ta >= 0) {
+#pragma unroll
+                for (int j = 0; j < F2_SB; ++j) {
+                    int32_t *trow = s_t1 + ((rbase + j) & 7) * F2_TW1;
                     if (h1_lohi == 0) {
-                        trow[0 * 8 * F2_TW1 + h1_ta] = __double2int_rz((unit ? o_hi : mq * o_hi) * qs);  // ad
+                        trow[0 * 8 * F2_TW1 + h1_ta] = __double2int_rz((unit ? o_hi[j] : mq * o_hi[j]) * qs);  // ad
                     } else {
-                        trow[1 * 8 * F2_TW1 + h1_ta] = __double2int_rz((unit ? o_lo : mq * o_lo) * qs);  // da
-                        trow[2 * 8 * F2_TW1 + h1_tb] = __double2int_rz((unit ? o_hi : mq * o_hi) * qs);  // dd
+                        trow[1 * 8 * F2_TW1 + h1_ta] = __double2int_rz((unit ? o_lo[j] : mq * o_lo[j]) * qs);  // da
+                        trow[2 * 8 * F2_TW1 + h1_tb] = __double2int_rz((unit ? o_hi[j] : mq * o_hi[j]) * qs);  // dd
                     }
                 }
             }
@@ -446,14 +472,14 @@ dwt_fwd12_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         {
             const int u = step - 1 - LAGS;
             if (u >= FILL2 && u < nvs && warp < 6) {
-                const int e = warp & 1, b = warp >> 1;
-                const int m = R0 - 1 + 2 * (u - FILL2) + e;
+                const int m = R0 - 1 + 2 * (u - FILL2) + (warp & 1);
                 if (m >= R0 && m < R1) {
-                    const BandTile bt = make_tile(b == 0 ? 0 : p.sh2, b == 1 ? 0 : p.sw2, M0, nm);
-                    const int32_t *trow = s_t2 + (b * 4 + (m & 3)) * F2_TW2;
-                    mx = max(mx, f2_copy_row(trow, cplane, p.Wc, bt, m, lane));
-                    if (dpz && ((bt.ro + m) & 1) && m >= 1)
-                        f2_cells_row(s_t2 + (b * 4 + ((m - 1) & 3)) * F2_TW2, trow, dpz, p.NH, p.NW, bt, m, lane, F2_TW2);
+                    const int32_t *trow = s_t2 + (o2b * 4 + (m & 3)) * F2_TW2;
+                    const int ar = T2mine.ro + m;
+                    mx = max(mx, f2_copy_row(trow, cplane + (size_t)ar * p.Wc, L2mine, T2mine.i0, lane));
+                    if (dpz && (ar & 1) && m >= 1 && (ar >> 1) < p.NH)
+                        f2_cells_row(s_t2 + (o2b * 4 + ((m - 1) & 3)) * F2_TW2, trow, dpz + (size_t)(ar >> 1) * p.NW, L2mine,
+                                     lane);
                 }
             }
         }
@@ -498,14 +524,20 @@ dwt_fwd12_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             // warp 4 + j: production row j of this step, all three bands
             const int r = PR0 + F2_SB * step + (warp - 4);
             if (r <= Pl && r >= r1lo && r < r1hi && n1core > 0) {
-                const bool has_prev = r >= 1 && r - 1 >= PR0;
-#pragma unroll
-                for (int b = 0; b < 3; ++b) {
-                    const BandTile &bt = b == 0 ? T1ad : (b == 1 ? T1da : T1dd);
-                    const int32_t *trow = s_t1 + (b * 8 + (r & 7)) * F2_TW1;
-                    mx = max(mx, f2_copy_row(trow, cplane, p.Wc, bt, r, lane));
-                    if (dpz && has_prev && ((bt.ro + r) & 1))
-                        f2_cells_row(s_t1 + (b * 8 + ((r - 1) & 7)) * F2_TW1, trow, dpz, p.NH, p.NW, bt, r, lane, F2_TW1);
+                const bool has_prev = dpz && r >= 1 && r - 1 >= PR0;
+                const int32_t *trow = s_t1 + (r & 7) * F2_TW1, *tprev = s_t1 + ((r - 1) & 7) * F2_TW1;
+                // ad: array row r; da, dd: array row sh1 + r
+                int32_t *g_top = cplane + (size_t)r * p.Wc, *g_bot = cplane + (size_t)(p.sh1 + r) * p.Wc;
+                mx = max(mx, f2_copy_row(trow, g_top, L1ad, T1ad.i0, lane));
+                mx = max(mx, f2_copy_row(trow + 8 * F2_TW1, g_bot, L1da, T1da.i0, lane));
+                mx = max(mx, f2_copy_row(trow + 16 * F2_TW1, g_bot, L1dd, T1dd.i0, lane));
+                if (has_prev && (r & 1) && (r >> 1) < p.NH)
+                    f2_cells_row(tprev, trow, dpz + (size_t)(r >> 1) * p.NW, L1ad, lane);
+                const int ab = p.sh1 + r;
+                if (has_prev && (ab & 1) && (ab >> 1) < p.NH) {
+                    uint8_t *drow = dpz + (size_t)(ab >> 1) * p.NW;
+                    f2_cells_row(tprev + 8 * F2_TW1, trow + 8 * F2_TW1, drow, L1da, lane);
+                    f2_cells_row(tprev + 16 * F2_TW1, trow + 16 * F2_TW1, drow, L1dd, lane);
                 }
             }
         }
@@ -602,7 +634,7 @@ bool f2_validate(const spihtb_geom &g, const F2Plan &pl, int es)
         if (Pl < PR0) return false;
         for (int u = 0; u < nvs; ++u) {
             const int step = u + LAGS;
-            const int newest = std::min(Pl, PR0 + F2_SB * step + F2_SB - 1);  // last row H1 has written
+            const int newest = PR0 + F2_SB * step + F2_SB - 1;  // last ring row H1 has written (rows past Pl are written too)
             for (int i = 0; i < F2_SB; ++i) {
                 const int v = VR0 + F2_SB * u + i;
                 // is this virtual row read by a level-2 row that matters?  rows m in [max(R0-1,0), R1)
@@ -612,7 +644,7 @@ bool f2_validate(const spihtb_geom &g, const F2Plan &pl, int es)
                     if (v >= 2 * m + sft - (F - 2) && v <= 2 * m + sft + 1) used = true;
                 if (!used) continue;
                 const int rr = per ? v : ext_index(v, bh1, mode);
-                if (rr < PR0 || rr > newest || rr + RING <= newest) return false;
+                if (rr < PR0 || rr > std::min(Pl, newest) || rr + RING <= newest) return false;
             }
         }
         (void)FILL2;
