@@ -634,7 +634,8 @@ bool f2_validate(const spihtb_geom &g, const F2Plan &pl, int es)
         if (Pl < PR0) return false;
         for (int u = 0; u < nvs; ++u) {
             const int step = u + LAGS;
-            const int newest = PR0 + F2_SB * step + F2_SB - 1;  // last ring row H1 has written (rows past Pl are written too)
+            const int nps = (Pl - PR0 + 1 + F2_SB - 1) / F2_SB;
+            const int newest = PR0 + F2_SB * std::min(step, nps - 1) + F2_SB - 1;  // last ring row H1 has written (a step's rows past Pl included)
             for (int i = 0; i < F2_SB; ++i) {
                 const int v = VR0 + F2_SB * u + i;
                 // is this virtual row read by a level-2 row that matters?  rows m in [max(R0-1,0), R1)
