@@ -711,7 +711,14 @@ int f2_run(spihtb_ctx *ctx, const void *src, int pixel_dtype, const XformArgs &x
     // periodic continuation the strip / chunk halos assume
     if (g.mode == SPIHTB_MODE_PERIODIZATION && ((g.band_h[0] | g.band_w[0]) & 1)) return SPIHTB_OK;
     if (((size_t)src_w * es) % 16 != 0 || (reinterpret_cast<uintptr_t>(src) & 15) != 0) return SPIHTB_OK;
-    if (getenv("SPIHTB_NO_FUSED12")) return SPIHTB_OK;
+    // Opt-in (SPIHTB_FUSED12=1): measured on B200 the kernel is correct but slower than the level-by-level pair
+    // on every BASELINE shape (3.9 ms against 1.6 + 0.6 ms for 256 x 3 x 1024^2): the transform is issue-bound, and
+    // staging both filter passes through shared memory costs more instructions than the register / shuffle
+    // formulation saves in HBM traffic (profiles/r02_dwt_fwd12_*).
+    {
+        const char *e = getenv("SPIHTB_FUSED12");
+        if (!e || atoi(e) == 0) return SPIHTB_OK;
+    }
     EncodeTiledFn enc = encode_tiled_fn();
     if (!enc) return SPIHTB_OK;
 

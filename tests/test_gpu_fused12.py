@@ -70,12 +70,12 @@ def test_fused12_equals_level_by_level(monkeypatch, shape, dtype, wavelet, mode,
         torch.cuda.synchronize()
         return co, path_fwd, s, nbits, max_n, co2, path_enc
 
-    monkeypatch.delenv("SPIHTB_NO_FUSED12", raising=False)
+    monkeypatch.setenv("SPIHTB_FUSED12", "1")     # the fused kernel is opt-in (slower than the level-by-level pair)
     if chunks:
         monkeypatch.setenv("SPIHTB_F12_CHUNKS", str(chunks))
     a = run()
     assert a[1] == 12 and a[6] == 12, "the fused two-level kernel did not run on this geometry"
-    monkeypatch.setenv("SPIHTB_NO_FUSED12", "1")
+    monkeypatch.setenv("SPIHTB_FUSED12", "0")
     b = run()
     assert b[1] == 1 and b[6] == 1
     bad = (a[0] != b[0])
@@ -88,13 +88,14 @@ def test_fused12_equals_level_by_level(monkeypatch, shape, dtype, wavelet, mode,
         assert torch.equal(a[2][i, :nb], b[2][i, :nb]), f"image {i}: streams differ (a pyramid cell is wrong)"
 
 
-def test_fused12_falls_back_on_unsupported_geometry():
+def test_fused12_falls_back_on_unsupported_geometry(monkeypatch):
     """row strides the TMA unit cannot address (not a multiple of 16 bytes), fewer than three levels, planes only a
     few filter lengths wide: the level-by-level kernel runs and the results stay correct (oracle-checked elsewhere)"""
     import torch
     import spiht_b200 as spiht
     from spiht_b200 import _lib, batch
     ctx = _lib.get_context(0)
+    monkeypatch.setenv("SPIHTB_FUSED12", "1")
     for shape, mode, level in [((1, 61, 83), "reflect", None), ((1, 148, 140), "reflect", 2),
                                ((3, 20, 24), "reflect", None),
                                # periodization pads an odd level-1 band before level 2: not the periodic halo
