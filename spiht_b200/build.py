@@ -10,7 +10,10 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
-LIB_PATH = os.path.join(_HERE, "libspiht_b200.so")
+# SPIHTB_VARIANT=prof selects the debug build with the coders' phase counters (-DSPIHTB_PROF):
+# libspiht_b200_prof.so, objects under csrc/_obj_prof (tools/dec_phases.py); the product library is the default.
+VARIANT = os.environ.get("SPIHTB_VARIANT", "")
+LIB_PATH = os.path.join(_HERE, "libspiht_b200%s.so" % ("_" + VARIANT if VARIANT else ""))
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17",
@@ -51,11 +54,11 @@ def build(force=False, verbose=False, extra_flags=()):
         return LIB_PATH
     # one nvcc process per translation unit (in parallel), objects under csrc/_obj, then one link
     nvcc = find_nvcc()
-    objdir = os.path.join(CSRC, "_obj")
+    objdir = os.path.join(CSRC, "_obj" + ("_" + VARIANT if VARIANT else ""))
     os.makedirs(objdir, exist_ok=True)
     hdr_t = max(os.path.getmtime(d) for d in _deps() if not d.endswith(".cu"))
     flag_tag = os.path.join(objdir, "flags.txt")
-    flags = NVCC_FLAGS + list(extra_flags)
+    flags = NVCC_FLAGS + list(extra_flags) + (["-DSPIHTB_PROF"] if VARIANT == "prof" else [])
     same_flags = os.path.exists(flag_tag) and open(flag_tag).read() == " ".join(flags)
     jobs, objs = [], []
     for src in sources():

@@ -284,6 +284,41 @@ def decode_images(encoding_results: Sequence[EncodingResult], spiht_settings: Sp
     return out
 
 
+def decode_image_prefixes(encoding_result: EncodingResult, spiht_settings: SpihtSettings, byte_lengths: Sequence[int],
+                          return_coeffs: bool = False, as_numpy: bool = True):
+    """Progressive (multi-rate) decode: the images an embedded stream gives when it is cut after each of
+    `byte_lengths` bytes, all decoded by ONE batched library call (one CTA per prefix).  This is the loop of
+    the reference's make_gif.py:46-61 (`encoded.encoded_bytes = original_bytes[:byte_len]; decode_image(...)`
+    per frame) as a batch.  Returns a list of float64 (C,H',W') images in the order of byte_lengths; with
+    return_coeffs also the int32 coefficient arrays (what make_gif.py:61 gets from spiht.decode)."""
+    from . import batch
+    torch = _torch()
+    er = encoding_result
+    if er._encoding_version != ENCODER_DECODER_VERSION:
+        raise ValueError(er._encoding_version)
+    _norm_color(spiht_settings.color_model)
+    lens = np.asarray([min(max(int(n), 0), len(er.encoded_bytes)) for n in byte_lengths], dtype=np.int64)
+    g = _geom(er.h, er.w, spiht_settings, er.level)
+    if len(lens) == 0:
+        return ([], []) if return_coeffs else []
+    stride = (int(lens.max()) + 15) // 8 * 8
+    row = np.zeros((stride,), dtype=np.uint8)
+    row[:int(lens.max())] = np.frombuffer(er.encoded_bytes[:int(lens.max())], dtype=np.uint8)
+    dev_row = torch.from_numpy(row).cuda()
+    # every row holds the whole (longest) prefix: the decoder stops at 8 * nbytes[b] bits, so rows need no zero tail
+    streams = dev_row[None, :].expand(len(lens), stride).contiguous()
+    nbytes = torch.from_numpy(lens).cuda()
+    max_n = torch.full((len(lens),), int(er.max_n), dtype=torch.int32, device=streams.device)
+    pix, coeffs = batch.decode_images(streams, nbytes, max_n, er.c, g, spiht_settings, dtype=torch.float64)
+    if as_numpy:
+        pix = pix.cpu().numpy()
+        coeffs = coeffs.cpu().numpy() if return_coeffs else None
+    images = [pix[i] for i in range(len(lens))]
+    if return_coeffs:
+        return images, [coeffs[i] for i in range(len(lens))]
+    return images
+
+
 def decode_rec_array(encoding_result: EncodingResult, spiht_settings: SpihtSettings, return_metadata: bool = False):
     """spiht_wrapper.py:218-257: bitstream -> int32 coefficient array (+ geometry)"""
     encoded_bytes = encoding_result.encoded_bytes
