@@ -1,6 +1,7 @@
 // C ABI of libspiht_b200.so (see include/spiht_b200.h).
 #include <math.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -194,6 +195,7 @@ int spihtb_profile_enable(spihtb_ctx *ctx, int enable)
         return SPIHTB_EINVAL;
     }
     ctx->profiling = enable != 0;
+    for (int i = 0; i < ctx->nsubs; ++i) ctx->subs[i]->profiling = ctx->profiling;
     return SPIHTB_OK;
 }
 
@@ -205,13 +207,22 @@ int spihtb_profile_read(spihtb_ctx *ctx, double *ms_out, int64_t *count_out, int
     }
     SPIHTB_CUDA_CHECK(cudaSetDevice(ctx->device));
     for (int s = 0; s < SPIHTB_NSTAGES; ++s) {
-        if (ctx->prof[s].made) ctx->harvest(s, true);
-        ms_out[s] = ctx->prof[s].acc_ms;
-        count_out[s] = ctx->prof[s].harvested;
-        if (reset) {
-            ctx->prof[s].acc_ms = 0.0;
-            ctx->prof[s].recorded = 0;
-            ctx->prof[s].harvested = 0;
+        ms_out[s] = 0.0;
+        count_out[s] = 0;
+    }
+    // the context's own timers plus those of the group pipeline's sub-contexts (their intervals may overlap in
+    // time: the sums are per-stage busy times, not a partition of the step)
+    for (int i = -1; i < ctx->nsubs; ++i) {
+        spihtb_ctx *c = i < 0 ? ctx : ctx->subs[i];
+        for (int s = 0; s < SPIHTB_NSTAGES; ++s) {
+            if (c->prof[s].made) c->harvest(s, true);
+            ms_out[s] += c->prof[s].acc_ms;
+            count_out[s] += c->prof[s].harvested;
+            if (reset) {
+                c->prof[s].acc_ms = 0.0;
+                c->prof[s].recorded = 0;
+                c->prof[s].harvested = 0;
+            }
         }
     }
     return SPIHTB_OK;
@@ -257,7 +268,20 @@ int spihtb_destroy(spihtb_ctx *ctx)
 {
     if (!ctx) return SPIHTB_OK;
     cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
+    for (int i = 0; i < ctx->nsubs; ++i) {
+        spihtb_ctx *c = ctx->subs[i];
+        cudaStreamSynchronize(c->coder_stream);
+        cudaStreamDestroy(c->coder_stream);
+        cudaEventDestroy(c->ev_pyr);
+        cudaEventDestroy(c->ev_done);
+        cudaStream_t st = c->stream;
+        spihtb_destroy(c);     // synchronises c->stream, frees its workspaces
+        cudaStreamDestroy(st);
+    }
+    ctx->nsubs = 0;
+    if (ctx->ev_in) cudaEventDestroy(ctx->ev_in);
+    if (!ctx->is_sub) cudaStreamSynchronize(ctx->stream);
+    else cudaStreamSynchronize(ctx->stream);
     if (ctx->aux) {
         cudaStreamSynchronize(ctx->aux);
         cudaStreamDestroy(ctx->aux);
@@ -307,7 +331,13 @@ int spihtb_sync(spihtb_ctx *ctx)
     return SPIHTB_OK;
 }
 
-int64_t spihtb_launch_count(spihtb_ctx *ctx) { return ctx ? ctx->launches : 0; }
+int64_t spihtb_launch_count(spihtb_ctx *ctx)
+{
+    if (!ctx) return 0;
+    int64_t n = ctx->launches;
+    for (int i = 0; i < ctx->nsubs; ++i) n += ctx->subs[i]->launches;
+    return n;
+}
 int spihtb_forward_path(spihtb_ctx *ctx) { return ctx && ctx->last_forward_fused12 ? 12 : 1; }
 
 int spihtb_plan(int32_t h, int32_t w, int32_t wavelet, int32_t mode, int32_t level, spihtb_geom *g)
@@ -400,7 +430,45 @@ static int encode_with_pyramid(spihtb_ctx *ctx, const int32_t *dev_coeffs, int B
     a.nbits = dev_nbits;
     a.max_n = dev_max_n;
     a.status = dev_status;
+    if (ctx->is_sub && ctx->coder_stream) {
+        // pipeline: the coder runs on the sub-context's high-priority stream, behind the pyramid
+        SPIHTB_CUDA_CHECK(cudaEventRecord(ctx->ev_pyr, ctx->stream));
+        SPIHTB_CUDA_CHECK(cudaStreamWaitEvent(ctx->coder_stream, ctx->ev_pyr, 0));
+        cudaStream_t keep = ctx->stream;
+        ctx->stream = ctx->coder_stream;
+        rc = launch_encode(ctx, a);
+        ctx->stream = keep;
+        return rc;
+    }
     return launch_encode(ctx, a);
+}
+
+// sub-contexts of the group pipeline (created on first use)
+static int ensure_subs(spihtb_ctx *ctx, int n)
+{
+    using namespace spihtb;
+    n = std::min(n, (int)spihtb_ctx::MAX_SUBS);
+    int lo = 0, hi = 0;
+    SPIHTB_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));  // lo: least priority (largest number)
+    for (int i = ctx->nsubs; i < n; ++i) {
+        spihtb_ctx *c = new spihtb_ctx();
+        c->device = ctx->device;
+        c->sm_count = ctx->sm_count;
+        c->is_sub = true;
+        SPIHTB_CUDA_CHECK(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, lo));
+        SPIHTB_CUDA_CHECK(cudaStreamCreateWithPriority(&c->coder_stream, cudaStreamNonBlocking, hi));
+        SPIHTB_CUDA_CHECK(cudaStreamCreateWithFlags(&c->aux, cudaStreamNonBlocking));
+        SPIHTB_CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+        SPIHTB_CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+        SPIHTB_CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_order, cudaEventDisableTiming));
+        SPIHTB_CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_pyr, cudaEventDisableTiming));
+        SPIHTB_CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_done, cudaEventDisableTiming));
+        c->profiling = ctx->profiling;
+        ctx->subs[i] = c;
+        ctx->nsubs = i + 1;
+    }
+    if (!ctx->ev_in) SPIHTB_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_in, cudaEventDisableTiming));
+    return SPIHTB_OK;
 }
 
 extern "C" {
@@ -648,6 +716,46 @@ int spihtb_encode_images(spihtb_ctx *ctx, const void *dev_pixels, int32_t pixel_
     PyrBufs pb;
     rc = alloc_pyr(ctx, B, C, geom->enc_h, geom->enc_w, geom->ll_h, geom->ll_w, &pb);
     if (rc) return rc;
+    // ---- group pipeline (see spihtb_ctx::subs): groups of G images on alternating sub-contexts
+    int G = 0, NS = 3;
+    if (const char *e = getenv("SPIHTB_GROUP")) G = atoi(e);
+    if (const char *e = getenv("SPIHTB_GROUP_STREAMS")) NS = std::max(1, std::min(atoi(e), (int)spihtb_ctx::MAX_SUBS));
+    if (G > 0 && G < B && !ctx->is_sub) {
+        rc = ensure_subs(ctx, NS);
+        if (rc) return rc;
+        SPIHTB_CUDA_CHECK(cudaEventRecord(ctx->ev_in, ctx->stream));
+        const size_t esz = pixel_dtype == SPIHTB_F64 ? 8 : (pixel_dtype == SPIHTB_U8 ? 1 : 4);
+        const size_t px_img = (size_t)C * geom->h * geom->w * esz;
+        const size_t co_img = (size_t)C * geom->enc_h * geom->enc_w;
+        const size_t nodes_img = (size_t)C * (geom->enc_h / 2) * (geom->enc_w / 2);
+        const size_t roots_img = (size_t)C * geom->ll_h * geom->ll_w;
+        int g = 0;
+        for (int b0 = 0; b0 < B; b0 += G, ++g) {
+            spihtb_ctx *sc = ctx->subs[g % NS];
+            const int nb = std::min(G, B - b0);
+            SPIHTB_CUDA_CHECK(cudaStreamWaitEvent(sc->stream, ctx->ev_in, 0));
+            XformArgs xg = x;
+            xg.B = nb;
+            PyrBufs pg;
+            pg.dp = pb.dp + b0 * nodes_img;
+            pg.lp = pb.lp + b0 * nodes_img;
+            pg.dpll = pb.dpll + b0 * roots_img;
+            pg.lpll = pb.lpll + b0 * roots_img;
+            pg.maxabs = pb.maxabs + b0;
+            const PyrFuse pfg = {pg.dp, pg.maxabs};
+            int32_t *cg = dev_coeffs_scratch + b0 * co_img;
+            rc = launch_forward(sc, static_cast<const char *>(dev_pixels) + b0 * px_img, xg, cg, &pfg);
+            if (rc) return rc;
+            rc = encode_with_pyramid(sc, cg, nb, C, geom->enc_h, geom->enc_w, geom->ll_h, geom->ll_w, pg, true, max_bits,
+                                     dev_max_bits ? dev_max_bits + b0 : nullptr, dev_out + (size_t)b0 * out_stride,
+                                     out_stride, dev_nbits + b0, dev_max_n + b0, dev_status ? dev_status + b0 : nullptr);
+            if (rc) return rc;
+            SPIHTB_CUDA_CHECK(cudaEventRecord(sc->ev_done, sc->coder_stream));
+        }
+        for (int i = 0; i < std::min(g, NS); ++i) SPIHTB_CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, ctx->subs[i]->ev_done, 0));
+        ctx->last_forward_fused12 = ctx->subs[0]->last_forward_fused12;
+        return SPIHTB_OK;
+    }
     const PyrFuse pf = {pb.dp, pb.maxabs};
     rc = launch_forward(ctx, dev_pixels, x, dev_coeffs_scratch, &pf);
     if (rc) return rc;

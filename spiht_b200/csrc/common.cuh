@@ -49,6 +49,17 @@ struct spihtb_ctx {
     cudaStream_t aux = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaEvent_t ev_order = nullptr;  // orders the shared workspaces across a change of stream (spihtb_set_stream)
+    // Group pipeline of spihtb_encode_images: the batch is cut into groups of images and group g runs on
+    // sub-context g % nsubs -- its own streams and workspaces -- so that the (latency-bound) coder of one group
+    // overlaps the (bandwidth-bound) transform of the next.  A sub-context runs the transform and the pyramid on
+    // `stream` and the coder on `coder_stream` (higher priority: its few CTAs are placed as soon as an SM has room).
+    static constexpr int MAX_SUBS = 4;
+    spihtb_ctx *subs[MAX_SUBS] = {nullptr, nullptr, nullptr, nullptr};
+    int nsubs = 0;
+    bool is_sub = false;
+    cudaStream_t coder_stream = nullptr;                 // sub-contexts only
+    cudaEvent_t ev_pyr = nullptr, ev_done = nullptr;     // sub-contexts: pyramid ready / group finished
+    cudaEvent_t ev_in = nullptr;                         // parent: inputs ready on the caller's stream
     int64_t launches = 0;
     // grow-only device workspaces
     spihtb::DevBuf pyr;      // DP / LP planes + LL-root planes + per-image max

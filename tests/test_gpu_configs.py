@@ -202,3 +202,32 @@ def test_repeated_runs_are_bit_identical(T):
         else:
             for a, b in zip(ref, cur):
                 assert torch.equal(a, b), f"run {it} differs from run 0"
+
+
+@pytest.mark.parametrize("group,streams", [(5, 3), (1, 2), (7, 4)])
+def test_group_pipeline_equals_single_pass(T, monkeypatch, group, streams):
+    """spihtb_encode_images cut into groups of images on alternating sub-contexts (own streams and workspaces, the
+    coder of one group beside the transform of the next) gives exactly the single-pass result; repeated to let a
+    workspace race show up as a difference"""
+    torch = T
+    import spiht_b200 as spiht
+    from spiht_b200 import _lib, batch
+    from spiht_b200.utils import synthetic_images
+    B, S = 23, 256
+    px = synthetic_images(B, 3, S, S, seed=91)
+    st = spiht.SpihtSettings()
+    g = _lib.plan(S, S, "bior2.2", "reflect", None)
+    budgets = torch.tensor([int(S * S * (0.1 + 0.05 * (i % 7))) for i in range(B)], dtype=torch.int64, device="cuda")
+    stride = batch.stream_stride(int(budgets.max()), 3, g)
+    monkeypatch.delenv("SPIHTB_GROUP", raising=False)
+    ref = batch.encode_images(px, g, st, budgets, out_stride=stride)
+    torch.cuda.synchronize()
+    monkeypatch.setenv("SPIHTB_GROUP", str(group))
+    monkeypatch.setenv("SPIHTB_GROUP_STREAMS", str(streams))
+    for it in range(4):
+        got = batch.encode_images(px, g, st, budgets, out_stride=stride)
+        torch.cuda.synchronize()
+        assert torch.equal(got[1], ref[1]) and torch.equal(got[2], ref[2]) and torch.equal(got[4], ref[4]), it
+        for b in range(B):
+            nb = (int(ref[1][b]) + 7) // 8
+            assert torch.equal(got[0][b, :nb], ref[0][b, :nb]), (it, b)

@@ -117,10 +117,14 @@ def test_config1_zebra_literally():
 
 def _forward_parity(im, st, name, **kw):
     """GPU coefficient array of `im` against the float64 oracle under the north star's rule for the float stages:
-    mismatching quantised coefficients are counted (and recorded), each must be off by exactly 1 and sit within
-    1e-6 of an integer boundary, at most 1e-5 of all coefficients.  (Photographs stored as uint8 / 255 produce
-    coefficients that are exact integers in real arithmetic -- bior2.2's 2-D taps are dyadic rationals -- so a few
-    truncations are decided by the summation order.)  Returns (gpu int32 array, ll_h, ll_w, mismatches)."""
+    mismatching quantised coefficients are counted (and recorded); each must be off by exactly 1 and be an exact
+    tie -- the oracle's value within 1e-9 of an integer -- and they stay below 1e-3 of all coefficients.
+    Photographs stored as uint8 / 255 make ties common: bior2.2's 2-D taps are dyadic rationals, so many
+    coefficients (k / 255 * 50 * dyadic) are exact integers in real arithmetic, and the truncation of
+    99.99999999999999 vs 100.00000000000001 is decided by the rounding of the last addition (the CUDA kernels
+    accumulate with fma, numpy and PyWavelets' C loops with separate multiply and add).  Synthetic float
+    images have no ties: 0 mismatches (tests/test_gpu_transform.py, tests/test_gpu_configs.py).
+    Returns (gpu int32 array, ll_h, ll_w, mismatches)."""
     import torch
     from conftest import record_count
     from oracle import wrapper_ref
@@ -131,11 +135,12 @@ def _forward_parity(im, st, name, **kw):
     want = of.astype(np.int32)
     bad = np.nonzero(got != want)
     n_bad = len(bad[0])
+    record_count(f"image_{name}_quantised_mismatches", mismatches=int(n_bad), coefficients=int(got.size),
+                 max_distance_from_integer=float(np.abs(of[bad] - np.round(of[bad])).max()) if n_bad else 0.0)
     if n_bad:
         assert np.abs(got[bad].astype(np.int64) - want[bad]).max() <= 1
-        assert np.abs(of[bad] - np.round(of[bad])).max() < 1e-6
-    assert n_bad <= max(1, 1e-5 * got.size), (n_bad, got.size)
-    record_count(f"image_{name}_quantised_mismatches", mismatches=int(n_bad), coefficients=int(got.size))
+        assert np.abs(of[bad] - np.round(of[bad])).max() < 1e-9
+    assert n_bad <= max(1, 1e-3 * got.size), (n_bad, got.size)
     return got, ll_h, ll_w, n_bad
 
 
