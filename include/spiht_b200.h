@@ -127,6 +127,20 @@ int spihtb_encode(spihtb_ctx *ctx, const int32_t *host_coeffs, int32_t c, int32_
 int spihtb_decode(spihtb_ctx *ctx, const uint8_t *host_data, uint64_t nbytes, int32_t n,
                   int32_t c, int32_t h, int32_t w, int32_t ll_h, int32_t ll_w, int32_t *host_out);
 
+/* src/lib.rs:47-56  decode_with_metadata(data, n, c, h, w, ll_h, ll_w, top_slice, other_slices)
+ * -> (int32[c,h,w], int32[8*nbytes + 1, 8])  -> src/encoder_decoder.rs:616-841.
+ * The second array holds, for every bit position (and one past the last), the decoder state just before that bit
+ * is read: action id 0..6, position of the coefficient inside its band scaled to -100000..100000 (row, column),
+ * channel, filter (0 LL, 1 DA, 2 AD, 3 DD), depth, n, current value of the coefficient (:616-630).
+ * top_slice: {start_i, end_i, start_j, end_j} of the LL band; other_slices: int32 [levels][3][4], coarsest level
+ * first, the three bands in the caller's order da, ad, dd (spiht_wrapper.py:232-250), each
+ * {start_i, end_i, start_j, end_j}.  host_meta holds (8 * nbytes + 1) * 8 int32.  Even LL sizes only
+ * (SPIHTB_EGEOM otherwise): with an odd LL band the reference's trees share cells. */
+int spihtb_decode_with_metadata(spihtb_ctx *ctx, const uint8_t *host_data, uint64_t nbytes, int32_t n,
+                                int32_t c, int32_t h, int32_t w, int32_t ll_h, int32_t ll_w,
+                                const int32_t *top_slice, const int32_t *other_slices, int32_t levels,
+                                int32_t *host_out, int32_t *host_meta);
+
 /* ---- batched SPIHT coder, DEVICE buffers -------------------------------- */
 /* Same coder over a batch of B coefficient arrays of one shape.
  * dev_max_bits: optional uint64[B] per-image budgets (NULL: use max_bits for all).

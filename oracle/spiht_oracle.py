@@ -24,7 +24,7 @@ class OraclePanic(RuntimeError):
 
 
 def build(force=False):
-    srcs = [os.path.join(_HERE, f) for f in ("spiht_ref.c", "spiht_model.c", "Makefile")]
+    srcs = [os.path.join(_HERE, f) for f in ("spiht_ref.c", "spiht_model.c", "spiht_meta.c", "Makefile")]
     if (not force and os.path.exists(_LIB_PATH)
             and all(os.path.getmtime(_LIB_PATH) >= os.path.getmtime(s) for s in srcs)):
         return _LIB_PATH
@@ -51,6 +51,10 @@ def lib():
         L.spiht_ref_decode.restype = ctypes.c_int
         L.spiht_ref_decode.argtypes = [ctypes.c_char_p, u64, ctypes.c_uint, u64, u64, u64, u64, u64,
                                        ctypes.c_void_p]
+        L.spiht_ref_decode_with_metadata.restype = ctypes.c_int
+        L.spiht_ref_decode_with_metadata.argtypes = [ctypes.c_char_p, u64, ctypes.c_uint, u64, u64, u64, u64, u64,
+                                                     ctypes.c_void_p, ctypes.c_void_p, u64, ctypes.c_void_p,
+                                                     ctypes.c_void_p]
         L.spiht_ref_free.argtypes = [ctypes.c_void_p]
         L.spiht_ref_set_bit.restype = ctypes.c_int32
         L.spiht_ref_set_bit.argtypes = [ctypes.c_int32, ctypes.c_uint, ctypes.c_int]
@@ -115,6 +119,22 @@ def decode(data, n, c, h, w, ll_h, ll_w):
     out = np.empty((c, h, w), dtype=np.int32)
     _check(lib().spiht_ref_decode(data, len(data), int(n), c, h, w, ll_h, ll_w, out.ctypes.data))
     return out
+
+
+def decode_with_metadata(data, n, c, h, w, ll_h, ll_w, top_slice, other_slices):
+    """lib.rs:47-56 -> (int32[c,h,w], int32[8 * len(data) + 1, 8]); top_slice = [(si, ei), (sj, ej)],
+    other_slices = per level (coarsest first) three [(si, ei), (sj, ej)] in the caller's order da, ad, dd
+    (spiht_wrapper.py:232-250)"""
+    data = bytes(data)
+    out = np.empty((c, h, w), dtype=np.int32)
+    meta = np.empty((8 * len(data) + 1, 8), dtype=np.int32)
+    top = np.array([top_slice[0][0], top_slice[0][1], top_slice[1][0], top_slice[1][1]], dtype=np.int64)
+    other = np.array([[[f[0][0], f[0][1], f[1][0], f[1][1]] for f in lvl] for lvl in other_slices], dtype=np.int64)
+    other = np.ascontiguousarray(other.reshape(len(other_slices), 3, 4))
+    _check(lib().spiht_ref_decode_with_metadata(data, len(data), int(n), c, h, w, ll_h, ll_w, top.ctypes.data,
+                                                other.ctypes.data, len(other_slices), out.ctypes.data,
+                                                meta.ctypes.data))
+    return out, meta
 
 
 def pyramid(x, ll_h, ll_w):

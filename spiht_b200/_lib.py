@@ -48,7 +48,7 @@ EXPORTS = (
     "spihtb_sync", "spihtb_launch_count", "spihtb_plan", "spihtb_encode", "spihtb_decode",
     "spihtb_encode_coeffs", "spihtb_decode_coeffs", "spihtb_forward", "spihtb_inverse",
     "spihtb_encode_images", "spihtb_decode_images", "spihtb_stream_bound",
-    "spihtb_profile_enable", "spihtb_profile_read", "spihtb_max_abs", "spihtb_convert_color", "spihtb_forward_path",
+    "spihtb_profile_enable", "spihtb_profile_read", "spihtb_max_abs", "spihtb_convert_color", "spihtb_forward_path", "spihtb_decode_with_metadata",
 )
 
 
@@ -82,6 +82,7 @@ def lib():
         L.spihtb_plan.argtypes = [i32, i32, i32, i32, i32, P(Geom)]
         L.spihtb_encode.argtypes = [vp, vp, i32, i32, i32, i32, i32, u64, P(vp), P(u64), P(i32)]
         L.spihtb_decode.argtypes = [vp, ctypes.c_char_p, u64, i32, i32, i32, i32, i32, i32, vp]
+        L.spihtb_decode_with_metadata.argtypes = [vp, ctypes.c_char_p, u64, i32, i32, i32, i32, i32, i32, vp, vp, i32, vp, vp]
         L.spihtb_encode_coeffs.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, u64, vp, vp, u64, vp, vp, vp]
         L.spihtb_decode_coeffs.argtypes = [vp, vp, u64, vp, vp, i32, i32, i32, i32, i32, i32, vp]
         L.spihtb_forward.argtypes = [vp, vp, i32, i32, i32, P(Geom), i32, P(dbl), dbl, vp]

@@ -636,6 +636,77 @@ int spihtb_decode(spihtb_ctx *ctx, const uint8_t *host_data, uint64_t nbytes, in
     return SPIHTB_OK;
 }
 
+int spihtb_decode_with_metadata(spihtb_ctx *ctx, const uint8_t *host_data, uint64_t nbytes, int32_t n, int32_t c,
+                                int32_t h, int32_t w, int32_t ll_h, int32_t ll_w, const int32_t *top_slice,
+                                const int32_t *other_slices, int32_t levels, int32_t *host_out, int32_t *host_meta)
+{
+    if (!ctx || (!host_data && nbytes) || !host_out || !host_meta || !top_slice || (!other_slices && levels > 0)) {
+        set_error("null pointer");
+        return SPIHTB_EINVAL;
+    }
+    if (n < 0 || n > 255 || levels < 0 || levels > 255) {
+        set_error("n and the number of levels must fit a u8 (got %d, %d)", n, levels);
+        return SPIHTB_EINVAL;
+    }
+    int rc = check_coder_geom(c, h, w, ll_h, ll_w);
+    if (rc) return rc;
+    SPIHTB_CUDA_CHECK(cudaSetDevice(ctx->device));
+    const size_t ncoef = (size_t)c * h * w;
+    const uint64_t stride = (nbytes + 15) / 8 * 8;
+    const uint64_t rows = nbytes * 8 + 1;
+    const size_t nsl = (size_t)levels * 12;
+    // io: coefficients | metadata rows;  io2: stream | header | slices | error flag
+    rc = ctx->ensure(ctx->io, (ncoef + rows * 8) * sizeof(int32_t) + 512);
+    if (rc) return rc;
+    rc = ctx->ensure(ctx->io2, stride + 64 + nsl * sizeof(int32_t) + 64);
+    if (rc) return rc;
+    int32_t *d_coef = static_cast<int32_t *>(ctx->io.p);
+    int32_t *d_meta = d_coef + (ncoef + 63) / 64 * 64;   // 256-byte aligned rows
+    uint8_t *d_in = static_cast<uint8_t *>(ctx->io2.p);
+    uint64_t *d_nbytes = reinterpret_cast<uint64_t *>(d_in + stride);
+    int32_t *d_n = reinterpret_cast<int32_t *>(d_in + stride + 8);
+    int32_t *d_err = d_n + 1;
+    int32_t *d_slices = reinterpret_cast<int32_t *>(d_in + stride + 64);
+    rc = ctx->ensure(ctx->io, ((ncoef + 63) / 64 * 64 + rows * 8) * sizeof(int32_t) + 512);
+    if (rc) return rc;
+    d_coef = static_cast<int32_t *>(ctx->io.p);
+    d_meta = d_coef + (ncoef + 63) / 64 * 64;
+    SPIHTB_CUDA_CHECK(cudaMemsetAsync(d_in, 0, stride + 64, ctx->stream));
+    SPIHTB_CUDA_CHECK(cudaMemsetAsync(d_meta, 0, rows * 8 * sizeof(int32_t), ctx->stream));
+    if (nbytes) SPIHTB_CUDA_CHECK(cudaMemcpyAsync(d_in, host_data, nbytes, cudaMemcpyHostToDevice, ctx->stream));
+    struct { uint64_t nb; int32_t n; int32_t err; } hdr = {nbytes, n, 0};
+    SPIHTB_CUDA_CHECK(cudaMemcpyAsync(d_nbytes, &hdr, 16, cudaMemcpyHostToDevice, ctx->stream));
+    if (nsl)
+        SPIHTB_CUDA_CHECK(cudaMemcpyAsync(d_slices, other_slices, nsl * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    DecArgs a;
+    a.in = d_in;
+    a.in_stride = stride;
+    a.nbytes = d_nbytes;
+    a.n = d_n;
+    a.B = 1; a.C = c; a.H = h; a.W = w; a.ll_h = ll_h; a.ll_w = ll_w;
+    a.out = d_coef;
+    a.meta = d_meta;
+    a.meta_rows = rows;
+    a.level = levels;
+    a.top_ei = top_slice[1];
+    a.top_ej = top_slice[3];
+    a.slices = d_slices;
+    a.meta_err = d_err;
+    rc = launch_decode(ctx, a);
+    if (rc) return rc;
+    int32_t err = 0;
+    SPIHTB_CUDA_CHECK(cudaMemcpyAsync(host_out, d_coef, ncoef * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    SPIHTB_CUDA_CHECK(cudaMemcpyAsync(host_meta, d_meta, rows * 8 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    SPIHTB_CUDA_CHECK(cudaMemcpyAsync(&err, d_err, sizeof(err), cudaMemcpyDeviceToHost, ctx->stream));
+    SPIHTB_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    if (err) {
+        set_error("band rectangle index out of range: the tree is deeper than the %d levels of slices given "
+                  "(the reference panics here)", levels);
+        return SPIHTB_EGEOM;
+    }
+    return SPIHTB_OK;
+}
+
 int spihtb_forward(spihtb_ctx *ctx, const void *dev_pixels, int32_t pixel_dtype, int32_t B, int32_t C,
                    const spihtb_geom *geom, int32_t color_model, const double *ch_scales, double q,
                    int32_t *dev_coeffs)

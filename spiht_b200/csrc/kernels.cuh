@@ -57,6 +57,12 @@ struct DecArgs {
     // optional [B*C][ceil(H/64)][ceil(W/64)] bytes, zeroed by the caller: the decoder marks every 64x64 block
     // of the array it writes a coefficient into (the inverse transform skips the detail bands of unmarked blocks)
     uint8_t *blk = nullptr;
+    // decode_with_metadata: rows [B][meta_rows][8] (zero-filled by the caller), band rectangles, error flag
+    int32_t *meta = nullptr;
+    uint64_t meta_rows = 0;
+    int level = 0, top_ei = 1, top_ej = 1;
+    const int32_t *slices = nullptr;
+    int32_t *meta_err = nullptr;
 };
 int launch_decode(spihtb_ctx *ctx, const DecArgs &a);
 

@@ -62,7 +62,72 @@ struct DecK {
     uint32_t *lip, *lsp, *lis;  // lip: 2 buffers per slot; lis: 3 buffers per slot
     size_t pix_cap, lis_cap;
     unsigned int *counter;
+    // decode_with_metadata (encoder_decoder.rs:616-841): one row of 8 int32 per bit position, the decoder state
+    // just before that bit is read; rows [B][meta_rows][8], zero-filled by the launcher
+    int32_t *meta;
+    uint64_t meta_rows;
+    int level;                 // number of detail levels (slices.other_slices.len())
+    int top_ei, top_ej;        // slices.top_slice.end_i / end_j
+    const int32_t *slices;     // device [level][3][4]: start_i, end_i, start_j, end_j in the caller's order da, ad, dd
+    int32_t *meta_err;         // set to 1 when the reference would have panicked (slice index out of range)
 };
+
+// ---- decode_with_metadata helpers ----------------------------------------------------------------------
+// depth and filter of a coefficient from its position (even LL sizes: every cell has one parent).  The
+// reference carries them along the lists (CoefficientMetadata, encoder_decoder.rs:123-151): an LL root has
+// depth = level and filter LL; its offspring take the filter from the root's parity (get_offspring_filter) and
+// depth - 1; below that the filter is inherited and the depth falls by one per generation (u8, wrapping).
+__device__ __forceinline__ void meta_depth_filter(uint32_t i, uint32_t j, uint32_t ll_h, uint32_t ll_w, int level,
+                                                  uint32_t &depth, uint32_t &filter)
+{
+    if (i < ll_h && j < ll_w) {
+        depth = (uint32_t)level & 0xffu;
+        filter = 0;
+        return;
+    }
+    uint32_t d = 0;
+    while (i >= 2 * ll_h || j >= 2 * ll_w) {
+        i >>= 1;
+        j >>= 1;
+        ++d;
+    }
+    const bool io = i >= ll_h, jo = j >= ll_w;   // the LL root's row / column is odd
+    filter = io && jo ? 3u : (!io && jo ? 2u : 1u);
+    depth = (uint32_t)(level - 1 - (int)d) & 0xffu;
+}
+// row `p` of image b's table (get_local_position :593-613 in float32, `as i32` saturating; assign_metadata :663-682)
+__device__ __forceinline__ void meta_row(const DecK &p, int32_t *mrows, uint64_t pos, int action, uint32_t k, uint32_t i,
+                                         uint32_t j, int n, int32_t value)
+{
+    uint32_t depth, filter;
+    meta_depth_filter(i, j, (uint32_t)p.ll_h, (uint32_t)p.ll_w, p.level, depth, filter);
+    float lh, lw;
+    if (depth == ((uint32_t)p.level & 0xffu)) {
+        lh = __fdiv_rn((float)i, (float)p.top_ei);
+        lw = __fdiv_rn((float)j, (float)p.top_ej);
+    } else {
+        const uint32_t di = (uint32_t)(p.level - 1 - (int)depth) & 0xffu;
+        if (di >= (uint32_t)p.level) {
+            *p.meta_err = 1;
+            return;
+        }
+        const int32_t *sl = p.slices + ((size_t)di * 3 + (filter - 1)) * 4;
+        lh = __fdiv_rn(__fsub_rn((float)i, (float)sl[0]), (float)(uint32_t)(sl[1] - sl[0]));
+        lw = __fdiv_rn(__fsub_rn((float)j, (float)sl[2]), (float)(uint32_t)(sl[3] - sl[2]));
+    }
+    int4 a, c;
+    a.x = action;
+    a.y = __float2int_rz(__fsub_rn(__fmul_rn(lh, 200000.0f), 100000.0f));
+    a.z = __float2int_rz(__fsub_rn(__fmul_rn(lw, 200000.0f), 100000.0f));
+    a.w = (int32_t)k;
+    c.x = (int32_t)filter;
+    c.y = (int32_t)depth;
+    c.z = n;
+    c.w = value;
+    int4 *row = reinterpret_cast<int4 *>(mrows + pos * 8);
+    row[0] = a;
+    row[1] = c;
+}
 
 // per-phase cycle counters of image 0's CTA (tools/dec_phases.py): debug builds only (-DSPIHTB_PROF); release
 // builds compile them out and do not export spihtb_debug_dec_prof
@@ -262,7 +327,13 @@ __device__ __noinline__ uint32_t lis_walk(uint32_t a_sw, uint32_t q, uint32_t a_
     return q - q0;
 }
 
-__global__ void __launch_bounds__(DEC_NT, 2) spiht_decode_kernel(const DecK p)
+// META: also fill the decode_with_metadata table.  The parse then runs one bit position further than the data
+// (limit + 1): the reference assigns the row of the bit it is about to read before it finds the data exhausted,
+// so the table has one more row than there are bits.  That phantom bit can change no coefficient -- a record that
+// needs a bit beyond it is cut exactly as at the real end -- except through a refinement, which is therefore
+// applied only below the real limit.
+template <bool META>
+__global__ void __launch_bounds__(DEC_NT, META ? 1 : 2) spiht_decode_kernel(const DecK p)
 {
     __shared__ uint32_t s_tmask[DEC_CH / 32 + 4];  // A sets with offspring (a fired record carries child bits)
     __shared__ __align__(16) uint8_t s_x[DEC_CH];               // child-bit length of fired A sets, 0 elsewhere
@@ -318,7 +389,9 @@ __global__ void __launch_bounds__(DEC_NT, 2) spiht_decode_kernel(const DecK p)
         br.nwords = p.in_stride_words;
         br.nbits = p.nbytes[b] * 8ull;
         if (br.nbits > br.nwords * 32ull) br.nbits = br.nwords * 32ull;
-        const uint64_t limit = br.nbits;
+        const uint64_t data_limit = br.nbits;
+        const uint64_t limit = META ? data_limit + 1 : data_limit;
+        [[maybe_unused]] int32_t *mrows = META ? p.meta + (size_t)b * p.meta_rows * 8 : nullptr;
         int32_t *rec = p.out + (size_t)b * C * H * W;
         int n = p.n[b];
         n = n < 0 ? 0 : (n > 31 ? 31 : n);
@@ -402,6 +475,12 @@ __global__ void __launch_bounds__(DEC_NT, 2) spiht_decode_kernel(const DecK p)
                         // the window holds the last valid bit: a record starting there has no sign bit
                         okm &= ~(1u << (nv - 1));
                     }
+                    if constexpr (META) {
+                        // ... and with the phantom position appended, neither has the record that starts on the
+                        // last real bit: its sign would be the phantom
+                        if (data_limit >= 1 && data_limit - 1 >= wp && data_limit - 1 - wp < 32)
+                            okm &= ~(1u << (uint32_t)(data_limit - 1 - wp));
+                    }
                     const uint32_t nsig = __popc(okm), nkeep = __popc(use & ~wbits);
                     // sign bits: bit i+1 of the window, the last one from the next word
                     const uint32_t nextbits = (uint32_t)(br.get64(wp) >> 1);
@@ -438,6 +517,14 @@ __global__ void __launch_bounds__(DEC_NT, 2) spiht_decode_kernel(const DecK p)
                             const int bpos = __ffs((int)um) - 1;
                             um &= um - 1;
                             const uint32_t key = lip[idx++];
+                            if constexpr (META) {
+                                uint32_t k, i, j;
+                                key_unpack(kf, key, k, i, j);
+                                const int32_t cur = rec[((size_t)k * H + i) * W + j];
+                                meta_row(p, mrows, wp + bpos, 0, k, i, j, n, cur);
+                                if (((wbits >> bpos) & 1u) && wp + bpos + 1 < limit)
+                                    meta_row(p, mrows, wp + bpos + 1, 1, k, i, j, n, cur);
+                            }
                             if ((wbits >> bpos) & 1u) {
                                 if ((okm >> bpos) & 1u) {
                                     uint32_t k, i, j;
@@ -607,6 +694,12 @@ __global__ void __launch_bounds__(DEC_NT, 2) spiht_decode_kernel(const DecK p)
                             uint32_t nlsp = 0, nlip = 0, nnext = 0, sigmask = 0, sgnmask = 0, nread = 0;
                             uint32_t ndef = 0, defmask = 0;
                             const bool isA = (key >> 31) != 0;
+                            if constexpr (META) {
+                                if (avail) {
+                                    key_unpack(kf, key, k, i, j);
+                                    meta_row(p, mrows, pe, isA ? 2 : 5, k, i, j, n, rec[((size_t)k * H + i) * W + j]);
+                                }
+                            }
                             if (fired) {
                                 key_unpack(kf, key, k, i, j);
                                 const bool has = offspring_corner(i, j, H, W, ll_h, ll_w, ci, cj);
@@ -620,10 +713,16 @@ __global__ void __launch_bounds__(DEC_NT, 2) spiht_decode_kernel(const DecK p)
                                             if (cut) break;
                                             if (q >= limit) { cut = true; break; }
                                             const uint32_t sg = cbits & 1u;
+                                            if constexpr (META) {
+                                                const uint32_t y = ci + (c4 >> 1), x = cj + (c4 & 1);
+                                                const int32_t cur = rec[((size_t)k * H + y) * W + x];
+                                                meta_row(p, mrows, q, 3, k, y, x, n, cur);
+                                                if (sg && q + 1 < limit) meta_row(p, mrows, q + 1, 4, k, y, x, n, cur);
+                                            }
                                             cbits >>= 1;
                                             ++q;
                                             if (sg) {
-                                                if (q >= limit) { cut = true; break; }
+                                                if (q >= data_limit) { cut = true; break; }   // the sign must be a real bit
                                                 sigmask |= 1u << c4;
                                                 sgnmask |= (cbits & 1u) << c4;
                                                 cbits >>= 1;
@@ -713,7 +812,9 @@ __global__ void __launch_bounds__(DEC_NT, 2) spiht_decode_kernel(const DecK p)
                     if (q < limit) {
                         uint32_t k, i, j;
                         key_unpack(kf, lsp[e], k, i, j);
-                        refine_cell(rec + ((size_t)k * H + i) * W + j, n, br.bit(q));
+                        int32_t *cell = rec + ((size_t)k * H + i) * W + j;
+                        if constexpr (META) meta_row(p, mrows, q, 6, k, i, j, n, *cell);
+                        if (q < data_limit) refine_cell(cell, n, br.bit(q));
                     }
                 }
             } else {
@@ -781,6 +882,19 @@ extern "C" int spihtb_debug_dec_prof(unsigned long long *out16)
 int launch_decode(spihtb_ctx *ctx, const DecArgs &a)
 {
     DecK k;
+    k.meta = a.meta;
+    k.meta_rows = a.meta_rows;
+    k.level = a.level;
+    k.top_ei = a.top_ei;
+    k.top_ej = a.top_ej;
+    k.slices = a.slices;
+    k.meta_err = a.meta_err;
+    if (a.meta && ((a.ll_h | a.ll_w) & 1)) {
+        set_error("decode_with_metadata needs even LL sizes (got %dx%d): with an odd LL band cells have two parents "
+                  "and the per-coefficient depth / filter of the reference's lists cannot be told from the position",
+                  a.ll_h, a.ll_w);
+        return SPIHTB_EGEOM;
+    }
     if (!make_keyfmt(a.C, a.H, a.W, &k.kf)) {
         set_error("shape c=%d h=%d w=%d does not fit a 31-bit packed list entry", a.C, a.H, a.W);
         return SPIHTB_ESHAPE;
@@ -800,7 +914,10 @@ int launch_decode(spihtb_ctx *ctx, const DecArgs &a)
     k.BW = (a.W + 63) / 64;
 
     int occ = 1;
-    SPIHTB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, spiht_decode_kernel, DEC_NT, 0));
+    if (a.meta)
+        SPIHTB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, spiht_decode_kernel<true>, DEC_NT, 0));
+    else
+        SPIHTB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, spiht_decode_kernel<false>, DEC_NT, 0));
     if (occ < 1) occ = 1;
     const int slots = std::min(a.B, ctx->sm_count * occ);
 
@@ -826,7 +943,10 @@ int launch_decode(spihtb_ctx *ctx, const DecArgs &a)
     ctx->stage_begin(5);
     SPIHTB_CUDA_CHECK(cudaMemsetAsync(a.out, 0, sizeof(int32_t) * (size_t)a.B * a.C * a.H * a.W, ctx->stream));
     SPIHTB_CUDA_CHECK(cudaMemsetAsync(k.counter, 0, sizeof(unsigned int), ctx->stream));
-    spiht_decode_kernel<<<slots, DEC_NT, 0, ctx->stream>>>(k);
+    if (a.meta)
+        spiht_decode_kernel<true><<<slots, DEC_NT, 0, ctx->stream>>>(k);
+    else
+        spiht_decode_kernel<false><<<slots, DEC_NT, 0, ctx->stream>>>(k);
     ctx->launches++;
     ctx->stage_end(5);
     SPIHTB_CUDA_CHECK(cudaGetLastError());

@@ -48,8 +48,25 @@ def decode(data_u8, n, c, h, w, ll_h, ll_w):
 
 
 def decode_with_metadata(data_u8, n, c, h, w, ll_h, ll_w, top_slice, other_slices):
-    """src/lib.rs:47-56.  Not on the accelerated path yet."""
-    raise NotImplementedError("decode_with_metadata is not implemented by spiht_b200 yet")
+    """src/lib.rs:47-56: decode_with_metadata(data, n, c, h, w, ll_h, ll_w, top_slice, other_slices)
+    -> (int32[c,h,w], int32[8 * len(data) + 1, 8]).  top_slice = [(start_i, end_i), (start_j, end_j)];
+    other_slices = per detail level, coarsest first, three [(start_i, end_i), (start_j, end_j)] in the order
+    da, ad, dd (spiht_wrapper.py:232-250)."""
+    data = bytes(data_u8)
+    if not 0 <= int(n) <= 255:
+        raise OverflowError("out of range integral type conversion attempted")  # n: u8
+    out = np.empty((int(c), int(h), int(w)), dtype=np.int32)
+    meta = np.empty((8 * len(data) + 1, 8), dtype=np.int32)
+    top = np.array([top_slice[0][0], top_slice[0][1], top_slice[1][0], top_slice[1][1]], dtype=np.int32)
+    other = np.array([[[f[0][0], f[0][1], f[1][0], f[1][1]] for f in lvl] for lvl in other_slices], dtype=np.int32)
+    other = np.ascontiguousarray(other.reshape(len(other_slices), 3, 4))
+    ctx = _lib.get_context(_current_device())
+    _bind_stream(ctx)
+    _lib.check(_lib.lib().spihtb_decode_with_metadata(ctx.handle, data, len(data), int(n), int(c), int(h), int(w),
+                                                      int(ll_h), int(ll_w), top.ctypes.data,
+                                                      other.ctypes.data if len(other_slices) else None,
+                                                      len(other_slices), out.ctypes.data, meta.ctypes.data))
+    return out, meta
 
 
 def _current_device():

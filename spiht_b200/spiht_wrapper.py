@@ -251,7 +251,10 @@ def decode_image(encoding_result: EncodingResult, spiht_settings: SpihtSettings,
     """spiht_wrapper.py:192-216.  Decodes the encoding_result to pixel values
     (float64 array (C,H',W'); H' = H + 1 for odd H, as pywt.waverec2 returns)."""
     if return_metadata:
-        raise NotImplementedError("decode_with_metadata is not implemented by spiht_b200 yet")
+        # spiht_wrapper.py:203-216: the metadata path goes through the raw coder and the host-side inverse
+        out = decode_rec_array(encoding_result, spiht_settings, return_metadata=True)
+        image = decode_from_rec_arr(out["rec_arr"], out["h"], out["w"], out["level"], spiht_settings, out["slices"])
+        return image, out["spiht_metadata"]
     return decode_images([encoding_result], spiht_settings)[0]
 
 
@@ -335,9 +338,18 @@ def decode_rec_array(encoding_result: EncodingResult, spiht_settings: SpihtSetti
     ll_h, ll_w = slices[0][1].stop, slices[0][2].stop
 
     if return_metadata:
-        raise NotImplementedError("decode_with_metadata is not implemented by spiht_b200 yet")
-    rec_arr = spiht_rs.decode(encoded_bytes, max_n, c, enc_h, enc_w, ll_h, ll_w)
-    return dict(rec_arr=rec_arr, slices=slices, spiht_metadata=None, h=h, w=w, level=level)
+        # spiht_wrapper.py:232-250: band rectangles in the order da, ad, dd, coarsest level first
+        top_slice = [(slices[0][1].start or 0, slices[0][1].stop), (slices[0][2].start or 0, slices[0][2].stop)]
+        other_slices = []
+        for slice_level in slices[1:]:
+            other_slices.append([[(slice_level[key][1].start, slice_level[key][1].stop),
+                                  (slice_level[key][2].start, slice_level[key][2].stop)] for key in ["da", "ad", "dd"]])
+        rec_arr, spiht_metadata = spiht_rs.decode_with_metadata(encoded_bytes, max_n, c, enc_h, enc_w, ll_h, ll_w,
+                                                                top_slice, other_slices)
+    else:
+        rec_arr = spiht_rs.decode(encoded_bytes, max_n, c, enc_h, enc_w, ll_h, ll_w)
+        spiht_metadata = None
+    return dict(rec_arr=rec_arr, slices=slices, spiht_metadata=spiht_metadata, h=h, w=w, level=level)
 
 
 def decode_from_rec_arr(rec_arr: np.ndarray, h: int, w: int, level, spiht_settings: SpihtSettings, slices=None):

@@ -259,8 +259,6 @@ def test_errors(rs):
         rs.encode(arr[0], 2, 2, 100)
     with pytest.raises(_lib.SpihtB200Error):
         rs.decode(b"\x01", 3, 1, 8, 8, 2, 1)
-    with pytest.raises(NotImplementedError):
-        rs.decode_with_metadata(b"", 0, 1, 8, 8, 2, 2, [], [])
 
 
 def test_full_size_config2_against_model_oracle(oracle):
