@@ -296,3 +296,34 @@ def test_full_size_config2_against_model_oracle(oracle):
     assert torch.equal(torch.sign(rec[nz]), torch.sign(xd[nz]))
     top = lambda t: torch.floor(torch.log2(t.abs().double() + 0.5))   # +0.5: exact powers of two stay exact
     assert torch.equal(top(rec[nz]), top(xd[nz]))
+
+
+@pytest.mark.parametrize("cl", [2, 4, 8, 16])
+def test_cluster_coder_matches_oracle(rs, oracle, monkeypatch, cl):
+    """the cluster coder (csrc/spiht_enc_cl.cu: one thread-block cluster per image, chunk totals exchanged through
+    distributed shared memory) gives the oracle's stream at every budget -- lists several super-chunks long, budgets
+    that end in every pass, word-unaligned chunk boundaries, batches with more images than clusters"""
+    import torch
+    from spiht_b200 import batch
+    monkeypatch.setenv("SPIHTB_ENC_CLUSTER", str(cl))
+    rng = np.random.default_rng(100 + cl)
+    # a large flat-spectrum array: long lists (hundreds of thousands of entries) at modest size
+    c, h, w, llh, llw = 3, 264, 392, 8, 12
+    x = (rng.laplace(0, 6, (c, h, w)) * (1 + 40 * (rng.random((c, h, w)) < 0.01))).astype(np.int32)
+    for mb in [10 ** 9, 1, 33, 4097, 65536, 300001, 1234567]:
+        want, want_n = oracle.model_encode(x, llh, llw, mb)
+        got, got_n = rs.encode(x, llh, llw, mb)
+        assert got_n == want_n
+        assert_stream_equal(got, want, f"cluster {cl} mb={mb}")
+    # batch: per-image budgets, more images than clusters can be resident
+    B = 11
+    xb = (rng.laplace(0, 5, (B, 2, 72, 88))).astype(np.int32)
+    xb[3] = 0
+    budgets = np.array([0, 5, 77, 800, 4000, 12345, 10 ** 9, 31, 2048, 9999, 64], dtype=np.int64)
+    streams, nbits, max_n, status = batch.encode_coeffs(torch.from_numpy(xb).cuda(), 4, 6, torch.from_numpy(budgets).cuda(),
+                                                        out_stride=8 * 8192)
+    streams, nbits, max_n = streams.cpu().numpy(), nbits.cpu().numpy(), max_n.cpu().numpy()
+    for b in range(B):
+        want, want_n, want_bits = oracle.encode_nbits(xb[b], 4, 6, int(budgets[b]))
+        assert (int(nbits[b]), int(max_n[b])) == (want_bits, want_n), b
+        assert_stream_equal(streams[b, :(want_bits + 7) // 8].tobytes(), want, f"cluster {cl} image {b}")
