@@ -260,6 +260,10 @@ int spihtb_create(int device, spihtb_ctx **out)
     SPIHTB_CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     SPIHTB_CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     SPIHTB_CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_order, cudaEventDisableTiming));
+    {
+        const int rc = ipt_upload_tables();
+        if (rc) return rc;
+    }
     *out = c;
     return SPIHTB_OK;
 }

@@ -10,6 +10,9 @@
 
 namespace spihtb {
 
+// tables of ipt_fast_pow into the current device's constant memory (once per context)
+int ipt_upload_tables() { return ipt_upload_tables_tu(); }
+
 template <typename Tin>
 __global__ void __launch_bounds__(256) rgb_to_ipt_kernel(const Tin *__restrict__ src, double *__restrict__ dst,
                                                          size_t plane, size_t nimg)

@@ -6,6 +6,8 @@
 //   The way back inverts every matrix in float64: colour-science 0.4.4 defines MATRIX_XYZ_TO_sRGB as
 //   np.linalg.inv(MATRIX_sRGB_TO_XYZ), not the rounded 4-digit inverse of releases before 0.4.
 #pragma once
+#include <math.h>
+
 #include "common.cuh"
 
 namespace spihtb {
@@ -43,17 +45,84 @@ static inline IptInv make_ipt_inv()
     return mi;
 }
 
+// ---- |x|^0.43 and |x|^(1/0.43) without the general pow() ------------------------------------------------
+// The colour transform is three powers per pixel; CUDA's double-precision pow() (~200 instructions) made the
+// stand-alone RGB -> IPT pass of 512 x 3 x 2048^2 take 56 ms against 22 ms for the whole DWT.  For a fixed exponent
+// p:  x = m 2^e, m in [1, 2);  k = top four mantissa bits, c_k = 1 + (k + 1/2) / 16, r = m / c_k - 1, |r| <= 1/33;
+//     x^p = 2^(p e) * c_k^p * (1 + r)^p,   (1 + r)^p = sum_n C(p, n) r^n  (binomial series, 10 terms: < 1e-17).
+// 2^(p e) (e in [-64, 16)) and c_k^p, 1 / c_k are tables computed on the host in long double and rounded once;
+// the result is within a few ulp of the correctly rounded power (tests/test_gpu_transform.py checks 4e-15 absolute
+// on [0, 1] against numpy).  Exponents outside the table (|x| < 2^-64 or >= 2^16) take pow().
+struct PowTab {
+    double p;
+    double expo[80];     // 2^(p e), e = -64 .. 15
+    double inv_c[16];    // 1 / c_k
+    double c_p[16];      // c_k^p
+    double coef[10];     // C(p, n), n = 1 .. 10
+};
+struct IptPowTabs {
+    PowTab fwd, inv;     // p = 0.43, p = 1 / 0.43
+};
+
+static inline void fill_pow_tab(PowTab &t, double p)
+{
+    t.p = p;
+    const long double pl = (long double)p;
+    for (int e = -64; e < 16; ++e) t.expo[e + 64] = (double)powl(2.0L, pl * (long double)e);
+    for (int k = 0; k < 16; ++k) {
+        const long double c = 1.0L + ((long double)k + 0.5L) / 16.0L;
+        t.inv_c[k] = (double)(1.0L / c);
+        t.c_p[k] = (double)powl(c, pl);
+    }
+    long double b = 1.0L;
+    for (int n = 1; n <= 10; ++n) {
+        b = b * (pl - (long double)(n - 1)) / (long double)n;
+        t.coef[n - 1] = (double)b;
+    }
+}
+
 #ifdef __CUDACC__
-__device__ __forceinline__ double ipt_spow(double a, double e) { return a == 0.0 ? 0.0 : copysign(pow(fabs(a), e), a); }
+// one copy per translation unit that includes this header (the library is built without relocatable device
+// code); each such unit uploads its copy with ipt_upload_tables_tu() when a context is created
+static __constant__ IptPowTabs c_ipt_pow;
+static inline int ipt_upload_tables_tu()
+{
+    IptPowTabs t;
+    fill_pow_tab(t.fwd, 0.43);
+    fill_pow_tab(t.inv, 1.0 / 0.43);
+    SPIHTB_CUDA_CHECK(cudaMemcpyToSymbol(c_ipt_pow, &t, sizeof(t)));
+    return SPIHTB_OK;
+}
+
+__device__ __forceinline__ double ipt_fast_pow(double a, const PowTab &t)   // a > 0
+{
+    const long long bits = __double_as_longlong(a);
+    const int e = (int)((bits >> 52) & 0x7ff) - 1023;
+    if (e < -64 || e > 15) return pow(a, t.p);
+    const double m = __longlong_as_double((bits & 0x000fffffffffffffLL) | 0x3ff0000000000000LL);
+    const int k = (int)((bits >> 48) & 15);
+    const double r = fma(m, t.inv_c[k], -1.0);
+    double s = t.coef[9];
+#pragma unroll
+    for (int n = 8; n >= 0; --n) s = fma(s, r, t.coef[n]);
+    s = fma(s, r, 1.0);
+    return (t.expo[e + 64] * t.c_p[k]) * s;
+}
+// sign(a) |a|^p with p = 0.43 (inv = false) or 1 / 0.43 (inv = true)
+__device__ __forceinline__ double ipt_spow(double a, bool inv)
+{
+    if (a == 0.0) return 0.0;
+    return copysign(ipt_fast_pow(fabs(a), inv ? c_ipt_pow.inv : c_ipt_pow.fwd), a);
+}
 
 __device__ __forceinline__ void rgb_to_ipt_px(double R, double G, double B, double &I, double &P, double &T)
 {
     const double X = 0.4124 * R + 0.3576 * G + 0.1805 * B;
     const double Y = 0.2126 * R + 0.7152 * G + 0.0722 * B;
     const double Z = 0.0193 * R + 0.1192 * G + 0.9505 * B;
-    const double L = ipt_spow(0.4002 * X + 0.7075 * Y + -0.0807 * Z, 0.43);
-    const double M = ipt_spow(-0.2280 * X + 1.1500 * Y + 0.0612 * Z, 0.43);
-    const double S = ipt_spow(0.0 * X + 0.0 * Y + 0.9184 * Z, 0.43);
+    const double L = ipt_spow(0.4002 * X + 0.7075 * Y + -0.0807 * Z, false);
+    const double M = ipt_spow(-0.2280 * X + 1.1500 * Y + 0.0612 * Z, false);
+    const double S = ipt_spow(0.0 * X + 0.0 * Y + 0.9184 * Z, false);
     I = 0.4000 * L + 0.4000 * M + 0.2000 * S;
     P = 4.4550 * L + -4.8510 * M + 0.3960 * S;
     T = 0.8056 * L + 0.3572 * M + -1.1628 * S;
@@ -62,10 +131,9 @@ __device__ __forceinline__ void rgb_to_ipt_px(double R, double G, double B, doub
 __device__ __forceinline__ void ipt_to_rgb_px(const IptInv &mi, double I, double P, double T, double &R, double &G,
                                               double &B)
 {
-    const double e = 1.0 / 0.43;
-    const double L = ipt_spow(mi.ipt2lms[0] * I + mi.ipt2lms[1] * P + mi.ipt2lms[2] * T, e);
-    const double M = ipt_spow(mi.ipt2lms[3] * I + mi.ipt2lms[4] * P + mi.ipt2lms[5] * T, e);
-    const double S = ipt_spow(mi.ipt2lms[6] * I + mi.ipt2lms[7] * P + mi.ipt2lms[8] * T, e);
+    const double L = ipt_spow(mi.ipt2lms[0] * I + mi.ipt2lms[1] * P + mi.ipt2lms[2] * T, true);
+    const double M = ipt_spow(mi.ipt2lms[3] * I + mi.ipt2lms[4] * P + mi.ipt2lms[5] * T, true);
+    const double S = ipt_spow(mi.ipt2lms[6] * I + mi.ipt2lms[7] * P + mi.ipt2lms[8] * T, true);
     const double X = mi.lms2xyz[0] * L + mi.lms2xyz[1] * M + mi.lms2xyz[2] * S;
     const double Y = mi.lms2xyz[3] * L + mi.lms2xyz[4] * M + mi.lms2xyz[5] * S;
     const double Z = mi.lms2xyz[6] * L + mi.lms2xyz[7] * M + mi.lms2xyz[8] * S;

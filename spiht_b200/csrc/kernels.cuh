@@ -22,6 +22,7 @@ int launch_max_abs(spihtb_ctx *ctx, const int32_t *coeffs, int B, size_t per_ima
 // ---- color.cu: stand-alone RGB <-> IPT passes over planar [B][3][plane] images
 int launch_rgb_to_ipt(spihtb_ctx *ctx, const void *src, int src_dtype, double *dst, size_t plane, int B);
 int launch_ipt_to_rgb(spihtb_ctx *ctx, const double *src, void *dst, int dst_dtype, size_t plane, int B);
+int ipt_upload_tables();  // power tables of the colour transform -> constant memory of the current device
 
 // ---- spiht_enc.cu
 struct EncArgs {

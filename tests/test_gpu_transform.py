@@ -296,3 +296,29 @@ def test_decode_images_sparse_inverse_equals_full_inverse(torch_cuda, shape, kw,
     assert torch.equal(rec, coeffs)
     full = batch.inverse(rec, g, st, dtype=torch.float64)
     assert torch.equal(fast, full)
+
+
+def test_color_convert_matches_oracle_to_a_few_ulp(torch_cuda):
+    """color_models.convert (spihtb_convert_color): the fixed-exponent power of csrc/ipt.cuh against numpy's
+    pow-based restatement -- a few ulp, i.e. far inside the 1e-9 bar of the float stages -- on pixel values that
+    exercise every mantissa interval and many exponents, in both directions, for every pixel dtype"""
+    from oracle import ipt_ref
+    from spiht_b200.color_models import convert
+    rng = np.random.default_rng(3)
+    rgb = rng.random((3, 96, 128))
+    rgb[:, :8] *= 1e-4                      # small values: other exponents
+    rgb[:, 8:10] = 0.0
+    rgb[:, 10:12] = 1.0
+    rgb[0, 12:14] = 1.7                     # out of gamut: negative LMS possible after the matrices
+    want = ipt_ref.convert(rgb, "RGB", "IPT")
+    got = convert(rgb, "RGB", "IPT")
+    assert got.dtype == np.float64 and np.abs(got - want).max() < 4e-15 * max(1.0, np.abs(want).max())
+    back = convert(got, "IPT", "RGB")
+    assert np.abs(back - ipt_ref.convert(got, "IPT", "RGB")).max() < 2e-14
+    assert np.abs(back - rgb).max() < 1e-13          # every matrix of the way back is the exact inverse
+    u8 = np.round(rng.random((3, 64, 64)) * 255).astype(np.uint8)
+    assert np.abs(convert(u8, "RGB", "IPT") - ipt_ref.convert(u8 / 255, "RGB", "IPT")).max() < 4e-15
+    f32 = rng.random((3, 64, 64)).astype(np.float32)
+    assert np.abs(convert(f32, "rgb", "ipt") - ipt_ref.convert(f32.astype(np.float64), "RGB", "IPT")).max() < 4e-15
+    with pytest.raises(ValueError):
+        convert(rgb, "RGB", "CIE Lab")
