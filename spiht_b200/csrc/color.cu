@@ -13,51 +13,63 @@ namespace spihtb {
 // tables of ipt_fast_pow into the current device's constant memory (once per context)
 int ipt_upload_tables() { return ipt_upload_tables_tu(); }
 
+// gridDim.y = images; the blocks of an image stride over its pixels (no division per pixel)
 template <typename Tin>
 __global__ void __launch_bounds__(256) rgb_to_ipt_kernel(const Tin *__restrict__ src, double *__restrict__ dst,
-                                                         size_t plane, size_t nimg)
+                                                         size_t plane)
 {
-    const size_t total = plane * nimg;
-    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
-        const size_t b = t / plane, o = t - b * plane;
-        const Tin *s = src + b * 3 * plane + o;
-        double R = (double)s[0], G = (double)s[plane], B = (double)s[2 * plane];
+    __shared__ PowTab s_tab;
+    ipt_stage_table(&s_tab, false);
+    const Tin *s = src + (size_t)blockIdx.y * 3 * plane;
+    double *d = dst + (size_t)blockIdx.y * 3 * plane;
+    for (size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x; o < plane; o += (size_t)gridDim.x * blockDim.x) {
+        double R = (double)s[o], G = (double)s[plane + o], B = (double)s[2 * plane + o];
         if (sizeof(Tin) == 1) {  // uint8 pixels: imload's im / 255 (IEEE division, as numpy's)
             R /= 255.0;
             G /= 255.0;
             B /= 255.0;
         }
-        double *d = dst + b * 3 * plane + o;
-        rgb_to_ipt_px(R, G, B, d[0], d[plane], d[2 * plane]);
+        rgb_to_ipt_px(s_tab, R, G, B, d[o], d[plane + o], d[2 * plane + o]);
     }
 }
 
 template <typename Tout>
 __global__ void __launch_bounds__(256) ipt_to_rgb_kernel(const double *__restrict__ src, Tout *__restrict__ dst,
-                                                         size_t plane, size_t nimg, const IptInv mi)
+                                                         size_t plane, const IptInv mi)
 {
-    const size_t total = plane * nimg;
-    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
-        const size_t b = t / plane, o = t - b * plane;
-        const double *s = src + b * 3 * plane + o;
+    __shared__ PowTab s_tab;
+    ipt_stage_table(&s_tab, true);
+    const double *s = src + (size_t)blockIdx.y * 3 * plane;
+    Tout *d = dst + (size_t)blockIdx.y * 3 * plane;
+    for (size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x; o < plane; o += (size_t)gridDim.x * blockDim.x) {
         double R, G, B;
-        ipt_to_rgb_px(mi, s[0], s[plane], s[2 * plane], R, G, B);
-        Tout *d = dst + b * 3 * plane + o;
-        d[0] = (Tout)R;
-        d[plane] = (Tout)G;
-        d[2 * plane] = (Tout)B;
+        ipt_to_rgb_px(s_tab, mi, s[o], s[plane + o], s[2 * plane + o], R, G, B);
+        d[o] = (Tout)R;
+        d[plane + o] = (Tout)G;
+        d[2 * plane + o] = (Tout)B;
     }
+}
+
+static dim3 color_grid(spihtb_ctx *ctx, size_t plane, int B)
+{
+    // enough blocks per image to fill the device a few times over, at most 65535 images per launch (checked by callers)
+    const size_t per_img = std::max<size_t>(1, std::min<size_t>((plane + 255) / 256, ((size_t)ctx->sm_count * 16 + B - 1) / B));
+    return dim3((unsigned)per_img, (unsigned)B);
 }
 
 int launch_rgb_to_ipt(spihtb_ctx *ctx, const void *src, int src_dtype, double *dst, size_t plane, int B)
 {
-    const unsigned nb = (unsigned)std::min<size_t>((plane * B + 255) / 256, (size_t)ctx->sm_count * 32);
+    if (B > 65535) {
+        set_error("colour conversion: more than 65535 images in one call");
+        return SPIHTB_EINVAL;
+    }
+    const dim3 nb = color_grid(ctx, plane, B);
     if (src_dtype == SPIHTB_F64)
-        rgb_to_ipt_kernel<double><<<nb, 256, 0, ctx->stream>>>(static_cast<const double *>(src), dst, plane, B);
+        rgb_to_ipt_kernel<double><<<nb, 256, 0, ctx->stream>>>(static_cast<const double *>(src), dst, plane);
     else if (src_dtype == SPIHTB_U8)
-        rgb_to_ipt_kernel<uint8_t><<<nb, 256, 0, ctx->stream>>>(static_cast<const uint8_t *>(src), dst, plane, B);
+        rgb_to_ipt_kernel<uint8_t><<<nb, 256, 0, ctx->stream>>>(static_cast<const uint8_t *>(src), dst, plane);
     else
-        rgb_to_ipt_kernel<float><<<nb, 256, 0, ctx->stream>>>(static_cast<const float *>(src), dst, plane, B);
+        rgb_to_ipt_kernel<float><<<nb, 256, 0, ctx->stream>>>(static_cast<const float *>(src), dst, plane);
     ctx->launches++;
     SPIHTB_CUDA_CHECK(cudaGetLastError());
     return SPIHTB_OK;
@@ -66,11 +78,15 @@ int launch_rgb_to_ipt(spihtb_ctx *ctx, const void *src, int src_dtype, double *d
 int launch_ipt_to_rgb(spihtb_ctx *ctx, const double *src, void *dst, int dst_dtype, size_t plane, int B)
 {
     const IptInv mi = make_ipt_inv();
-    const unsigned nb = (unsigned)std::min<size_t>((plane * B + 255) / 256, (size_t)ctx->sm_count * 32);
+    if (B > 65535) {
+        set_error("colour conversion: more than 65535 images in one call");
+        return SPIHTB_EINVAL;
+    }
+    const dim3 nb = color_grid(ctx, plane, B);
     if (dst_dtype == SPIHTB_F32)
-        ipt_to_rgb_kernel<float><<<nb, 256, 0, ctx->stream>>>(src, static_cast<float *>(dst), plane, B, mi);
+        ipt_to_rgb_kernel<float><<<nb, 256, 0, ctx->stream>>>(src, static_cast<float *>(dst), plane, mi);
     else
-        ipt_to_rgb_kernel<double><<<nb, 256, 0, ctx->stream>>>(src, static_cast<double *>(dst), plane, B, mi);
+        ipt_to_rgb_kernel<double><<<nb, 256, 0, ctx->stream>>>(src, static_cast<double *>(dst), plane, mi);
     ctx->launches++;
     SPIHTB_CUDA_CHECK(cudaGetLastError());
     return SPIHTB_OK;

@@ -108,32 +108,44 @@ __device__ __forceinline__ double ipt_fast_pow(double a, const PowTab &t)   // a
     s = fma(s, r, 1.0);
     return (t.expo[e + 64] * t.c_p[k]) * s;
 }
-// sign(a) |a|^p with p = 0.43 (inv = false) or 1 / 0.43 (inv = true)
-__device__ __forceinline__ double ipt_spow(double a, bool inv)
+// sign(a) |a|^p.  `t`: the table in SHARED memory (ipt_stage_table): the interval and exponent indices differ from
+// lane to lane, and constant memory serialises divergent indices.
+__device__ __forceinline__ double ipt_spow(double a, const PowTab &t)
 {
     if (a == 0.0) return 0.0;
-    return copysign(ipt_fast_pow(fabs(a), inv ? c_ipt_pow.inv : c_ipt_pow.fwd), a);
+    return copysign(ipt_fast_pow(fabs(a), t), a);
+}
+// copy the forward (p = 0.43) or inverse (p = 1 / 0.43) table from constant to shared memory (whole CTA; barrier)
+__device__ __forceinline__ void ipt_stage_table(PowTab *dst, bool inv)
+{
+    const double *src = reinterpret_cast<const double *>(inv ? &c_ipt_pow.inv : &c_ipt_pow.fwd);
+    double *d = reinterpret_cast<double *>(dst);
+    const int nthreads = blockDim.x * blockDim.y * blockDim.z;
+    const int tid = threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z);
+    for (int i = tid; i < (int)(sizeof(PowTab) / sizeof(double)); i += nthreads) d[i] = src[i];
+    __syncthreads();
 }
 
-__device__ __forceinline__ void rgb_to_ipt_px(double R, double G, double B, double &I, double &P, double &T)
+__device__ __forceinline__ void rgb_to_ipt_px(const PowTab &pt, double R, double G, double B, double &I, double &P,
+                                              double &T)
 {
     const double X = 0.4124 * R + 0.3576 * G + 0.1805 * B;
     const double Y = 0.2126 * R + 0.7152 * G + 0.0722 * B;
     const double Z = 0.0193 * R + 0.1192 * G + 0.9505 * B;
-    const double L = ipt_spow(0.4002 * X + 0.7075 * Y + -0.0807 * Z, false);
-    const double M = ipt_spow(-0.2280 * X + 1.1500 * Y + 0.0612 * Z, false);
-    const double S = ipt_spow(0.0 * X + 0.0 * Y + 0.9184 * Z, false);
+    const double L = ipt_spow(0.4002 * X + 0.7075 * Y + -0.0807 * Z, pt);
+    const double M = ipt_spow(-0.2280 * X + 1.1500 * Y + 0.0612 * Z, pt);
+    const double S = ipt_spow(0.0 * X + 0.0 * Y + 0.9184 * Z, pt);
     I = 0.4000 * L + 0.4000 * M + 0.2000 * S;
     P = 4.4550 * L + -4.8510 * M + 0.3960 * S;
     T = 0.8056 * L + 0.3572 * M + -1.1628 * S;
 }
 
-__device__ __forceinline__ void ipt_to_rgb_px(const IptInv &mi, double I, double P, double T, double &R, double &G,
-                                              double &B)
+__device__ __forceinline__ void ipt_to_rgb_px(const PowTab &pt, const IptInv &mi, double I, double P, double T,
+                                              double &R, double &G, double &B)
 {
-    const double L = ipt_spow(mi.ipt2lms[0] * I + mi.ipt2lms[1] * P + mi.ipt2lms[2] * T, true);
-    const double M = ipt_spow(mi.ipt2lms[3] * I + mi.ipt2lms[4] * P + mi.ipt2lms[5] * T, true);
-    const double S = ipt_spow(mi.ipt2lms[6] * I + mi.ipt2lms[7] * P + mi.ipt2lms[8] * T, true);
+    const double L = ipt_spow(mi.ipt2lms[0] * I + mi.ipt2lms[1] * P + mi.ipt2lms[2] * T, pt);
+    const double M = ipt_spow(mi.ipt2lms[3] * I + mi.ipt2lms[4] * P + mi.ipt2lms[5] * T, pt);
+    const double S = ipt_spow(mi.ipt2lms[6] * I + mi.ipt2lms[7] * P + mi.ipt2lms[8] * T, pt);
     const double X = mi.lms2xyz[0] * L + mi.lms2xyz[1] * M + mi.lms2xyz[2] * S;
     const double Y = mi.lms2xyz[3] * L + mi.lms2xyz[4] * M + mi.lms2xyz[5] * S;
     const double Z = mi.lms2xyz[6] * L + mi.lms2xyz[7] * M + mi.lms2xyz[8] * S;
