@@ -535,6 +535,51 @@ __device__ __forceinline__ void dwt_fwd_task(const FwdK &p, int tx, int ty, int 
         for (int d = 16; d > 0; d >>= 1) mx = max(mx, __shfl_xor_sync(FULL, mx, d));
         if (lane == 0 && mx) atomicMax(p.maxabs + z / p.C, mx);
     }
+    cp_async_wait<0>();  // the ring is free again (the prefetches past the chunk's last row are dropped)
+}
+
+// ---- the coarse levels of one plane in one CTA ------------------------------------------------------------
+// From the level whose plane is a few dozen tasks on, a launch per level is all launch latency and tail: the
+// bench workload spends 0.5 ms in levels 3..7 for 3 % of the coefficients.  Here a CTA of FT_WARPS warps owns
+// one (image, channel) plane and runs those levels back to back: the tasks of a level are dealt to the warps
+// (same tiles, same dwt_fwd_task as the per-level kernel, so the results are bit-identical), a CTA barrier
+// separates the levels (a level reads the approximation plane the previous one wrote; stores invalidate the
+// SM's own L1 lines, so the cp.async reads see them).  Planes are independent: while one CTA is down in its
+// latency-bound 12 x 12 level, its neighbours stream level 2.
+constexpr int FT_WARPS = 8;
+constexpr int FT_MAXLV = 10;
+struct FwdTail {
+    FwdK lv[FT_MAXLV];
+    int nlv;
+};
+template <int WID, int NP, bool UNIT_M, bool PYR>
+__global__ void __launch_bounds__(FT_WARPS * 32, (Wav<WID>::F == 6 ? 2 : 1)) dwt_fwd_tail_kernel(const __grid_constant__ FwdTail p)
+{
+    constexpr int F = Wav<WID>::F;
+    constexpr int NOUT = 32 * NP - (F / 2 - 1);
+    constexpr int DEPTH = FwdCfg<WID>::DEPTH;
+    constexpr int WARP_RING = DEPTH * 2 * 32 * 2 * NP * (int)sizeof(double);
+    extern __shared__ __align__(16) unsigned char s_tail_ring[];
+    const int warp = threadIdx.x >> 5;
+    const uint32_t ring = (uint32_t)__cvta_generic_to_shared(s_tail_ring) + warp * WARP_RING;
+    const int z = blockIdx.x;
+    for (int li = 0; li < p.nlv; ++li) {
+        const FwdK &k = p.lv[li];
+        const int ntp = k.tiles_x * k.tiles_y;
+        const int sft = k.mode == SPIHTB_MODE_PERIODIZATION ? (F / 2 - 1) : 0;
+        for (int t = warp; t < ntp; t += FT_WARPS) {
+            const int tx = t % k.tiles_x, ty = t / k.tiles_x;
+            const int gc_first = 2 * (tx * NOUT - (F / 2 - 1)) + sft;
+            constexpr int VB = 2 * NP * (int)sizeof(double) >= 16 ? 16 : 8;
+            const long long base = (long long)reinterpret_cast<uintptr_t>(k.src) + (long long)z * k.src_h * k.src_w * 8LL;
+            const bool aligned = ((size_t)k.src_w * 8) % VB == 0 && (base + (long long)gc_first * 8LL) % VB == 0;
+            if (k.last)
+                dwt_fwd_task<double, WID, NP, UNIT_M, true, PYR>(k, tx, ty, z, ring, aligned, nullptr);
+            else
+                dwt_fwd_task<double, WID, NP, UNIT_M, false, PYR>(k, tx, ty, z, ring, aligned, nullptr);
+        }
+        __syncthreads();
+    }
 }
 
 template <typename Tin, int WID, int NP, bool UNIT_M, bool LAST, bool PYR>
@@ -609,16 +654,22 @@ __global__ void __launch_bounds__(256) u8_to_f64_kernel(const uint8_t *__restric
         dst[t] = (double)src[t] / 255.0;
 }
 
+// tiles of a level (shared by launch_level, the tail kernel and fix_rects_level)
+template <int WID>
+static void level_tiles(FwdK &k)
+{
+    constexpr int NOUT = FwdCfg<WID>::NOUT;
+    const int RHMAX = fw_rhmax(k.bh);
+    k.tiles_x = (k.bw + NOUT - 1) / NOUT;
+    k.tiles_y = (k.bh + RHMAX - 1) / RHMAX;
+    k.RH = (k.bh + k.tiles_y - 1) / k.tiles_y;
+}
+
 template <typename Tin, int WID>
 static int launch_level(spihtb_ctx *ctx, FwdK k, int nz)
 {
     constexpr int NP = FwdCfg<WID>::NP;
-    constexpr int NOUT = FwdCfg<WID>::NOUT;
-    const int RHMAX = fw_rhmax(k.bh);
-    k.tiles_x = (k.bw + NOUT - 1) / NOUT;
-    // balanced row chunks (no nearly empty tail chunk)
-    k.tiles_y = (k.bh + RHMAX - 1) / RHMAX;
-    k.RH = (k.bh + k.tiles_y - 1) / k.tiles_y;
+    level_tiles<WID>(k);   // balanced row chunks (no nearly empty tail chunk)
     k.ntasks = (long long)k.tiles_x * k.tiles_y * nz;
     const long long nb = (k.ntasks + FW_WARPS - 1) / FW_WARPS;
     if (nb > 0x7fffffffLL) {
@@ -643,6 +694,44 @@ static int launch_level(spihtb_ctx *ctx, FwdK k, int nz)
         go(std::false_type{}, std::true_type{});
     else
         go(std::false_type{}, std::false_type{});
+    ctx->launches++;
+    return SPIHTB_OK;
+}
+
+template <int WID>
+static int launch_tail(spihtb_ctx *ctx, FwdTail &t, int nz)
+{
+    constexpr int NP = FwdCfg<WID>::NP;
+    constexpr int DEPTH = FwdCfg<WID>::DEPTH;
+    constexpr size_t smem = (size_t)FT_WARPS * DEPTH * 2 * 32 * 2 * NP * sizeof(double);
+    bool unit = true;
+    for (int c = 0; c < t.lv[0].C && c < 8; ++c) unit = unit && t.lv[0].scale[c] == 1.0;
+    const bool pyr = t.lv[0].dp != nullptr;
+    for (int i = 0; i < t.nlv; ++i) {
+        level_tiles<WID>(t.lv[i]);
+        t.lv[i].ntasks = (long long)t.lv[i].tiles_x * t.lv[i].tiles_y * nz;
+    }
+    auto go = [&](auto unit_c, auto pyr_c) -> int {
+        constexpr bool U = decltype(unit_c)::value, PY = decltype(pyr_c)::value;
+        static bool attr_set = false;
+        if (!attr_set) {
+            SPIHTB_CUDA_CHECK(cudaFuncSetAttribute(dwt_fwd_tail_kernel<WID, NP, U, PY>,
+                                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_set = true;
+        }
+        dwt_fwd_tail_kernel<WID, NP, U, PY><<<(unsigned)nz, FT_WARPS * 32, smem, ctx->stream>>>(t);
+        return SPIHTB_OK;
+    };
+    int rc;
+    if (unit && pyr)
+        rc = go(std::true_type{}, std::true_type{});
+    else if (unit)
+        rc = go(std::true_type{}, std::false_type{});
+    else if (pyr)
+        rc = go(std::false_type{}, std::true_type{});
+    else
+        rc = go(std::false_type{}, std::false_type{});
+    if (rc) return rc;
     ctx->launches++;
     return SPIHTB_OK;
 }
@@ -820,7 +909,7 @@ int launch_forward(spihtb_ctx *ctx, const void *pixels, const XformArgs &x, int3
     // One launch per level over the whole batch.  (Running the first levels image group by image group,
     // so that a group's float64 approximation planes stay in L2 for the next level, was measured slower
     // on B200: the short launches leave the SMs idle at every kernel boundary.)
-    auto run_level = [&](int l, int z0, int nzg) -> int {
+    auto make_k = [&](int l, int z0) -> FwdK {
         const bool in_f64 = l > 0 || x.pixel_dtype == SPIHTB_F64 || x.color == SPIHTB_COLOR_IPT || conv;
         const bool in_u8 = !in_f64 && x.pixel_dtype == SPIHTB_U8;
         const size_t esz = in_f64 ? sizeof(double) : (in_u8 ? 1 : sizeof(float));
@@ -847,9 +936,17 @@ int launch_forward(spihtb_ctx *ctx, const void *pixels, const XformArgs &x, int3
         k.maxabs = pf ? pf->maxabs : nullptr;  // indexed by z / C: z0 is a multiple of C
         k.NH = g.enc_h / 2;
         k.NW = g.enc_w / 2;
+        k.u8lut = u8lut;
+        k.tiles_x = k.tiles_y = k.RH = 0;
+        k.ntasks = 0;
+        return k;
+    };
+    auto run_level = [&](int l, int z0, int nzg) -> int {
+        const bool in_f64 = l > 0 || x.pixel_dtype == SPIHTB_F64 || x.color == SPIHTB_COLOR_IPT || conv;
+        const bool in_u8 = !in_f64 && x.pixel_dtype == SPIHTB_U8;
+        const FwdK k = make_k(l, z0);
         const int st = l == 0 ? 0 : 1;
         ctx->stage_begin(st);
-        k.u8lut = u8lut;
         const int r = in_f64 ? launch_level_w<double>(ctx, g.wavelet, k, nzg)
                              : (in_u8 ? launch_level_w<uint8_t>(ctx, g.wavelet, k, nzg)
                                       : launch_level_w<float>(ctx, g.wavelet, k, nzg));
@@ -922,9 +1019,35 @@ int launch_forward(spihtb_ctx *ctx, const void *pixels, const XformArgs &x, int3
             gap_forked = true;
         }
     }
-    for (int l = fused12 ? 2 : 1; l < L; ++l) {
-        rc = run_level(l, 0, nz);
-        if (rc) return rc;
+    // per-level launches while a level has many tasks per plane, then all remaining levels of a plane in one CTA
+    // (dwt_fwd_tail_kernel); SPIHTB_NO_TAIL=1 keeps one launch per level
+    {
+        const int F = wavelet_flen(g.wavelet);
+        const int nout = (F == 6 ? 2 : 1) * 32 - (F / 2 - 1);
+        auto tasks_per_plane = [&](int l) {
+            const int rhmax = fw_rhmax(g.band_h[l]);
+            return ((g.band_w[l] + nout - 1) / nout) * ((g.band_h[l] + rhmax - 1) / rhmax);
+        };
+        const bool tail_on = getenv("SPIHTB_NO_TAIL") == nullptr;
+        int l = fused12 ? 2 : 1;
+        for (; l < L; ++l) {
+            if (tail_on && L - l >= 2 && L - l <= FT_MAXLV && tasks_per_plane(l) <= 32) break;
+            rc = run_level(l, 0, nz);
+            if (rc) return rc;
+        }
+        if (l < L) {
+            FwdTail t;
+            t.nlv = L - l;
+            for (int i = 0; i < t.nlv; ++i) t.lv[i] = make_k(l + i, 0);
+            ctx->stage_begin(1);
+            switch (g.wavelet) {
+                case SPIHTB_WAVELET_BIOR22: rc = launch_tail<SPIHTB_WAVELET_BIOR22>(ctx, t, nz); break;
+                case SPIHTB_WAVELET_BIOR44: rc = launch_tail<SPIHTB_WAVELET_BIOR44>(ctx, t, nz); break;
+                default: rc = launch_tail<SPIHTB_WAVELET_BIOR68>(ctx, t, nz); break;
+            }
+            ctx->stage_end(1);
+            if (rc) return rc;
+        }
     }
     (void)src_is_f64;
     if (gap_forked) SPIHTB_CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));  // join the gap fill

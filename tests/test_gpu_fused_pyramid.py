@@ -82,3 +82,35 @@ def test_fused_untruncated():
     rec = batch.decode_coeffs(s1, (nbits1 + 7) // 8, n1, c, g.enc_h, g.enc_w, g.ll_h, g.ll_w)
     rec2 = batch.decode_coeffs(s2, (nbits2 + 7) // 8, n2, c, g.enc_h, g.enc_w, g.ll_h, g.ll_w)
     assert torch.equal(rec, rec2)
+
+
+@pytest.mark.parametrize("shape,wavelet,mode,level,bpp", CASES + [((3, 1024, 1024), "bior2.2", "reflect", None, 0.5),
+                                                                 ((1, 600, 840), "bior4.4", "reflect", None, 0.5),
+                                                                 ((2, 1100, 900), "bior6.8", "symmetric", None, 0.3)])
+def test_tail_kernel_equals_one_launch_per_level(monkeypatch, shape, wavelet, mode, level, bpp):
+    """dwt_fwd_tail_kernel (all coarse levels of a plane in one CTA) against one launch per level: identical
+    coefficient arrays, pyramid cells and per-image maxima (through the stream of an untruncated encode)"""
+    import torch
+    import spiht_b200 as spiht
+    from spiht_b200 import _lib, batch
+    c, h, w = shape
+    imgs = np.stack([synth_image(c, h, w, 200 + s) for s in range(2)]).astype(np.float32)
+    px = torch.from_numpy(imgs).cuda()
+    st = spiht.SpihtSettings(wavelet=wavelet, mode=mode)
+    g = _lib.plan(h, w, wavelet, mode, level)
+    stride = batch.stream_stride(0, c, g)
+
+    def run():
+        co = batch.forward(px, g, st)
+        s, nbits, max_n, _, co2 = batch.encode_images(px, g, st, 0, out_stride=stride)
+        torch.cuda.synchronize()
+        return co, s, nbits, max_n, co2
+    monkeypatch.delenv("SPIHTB_NO_TAIL", raising=False)
+    a = run()
+    monkeypatch.setenv("SPIHTB_NO_TAIL", "1")
+    b = run()
+    assert torch.equal(a[0], b[0]) and torch.equal(a[4], b[4])
+    assert torch.equal(a[3], b[3]) and torch.equal(a[2], b[2])
+    for i in range(2):
+        nb = (int(a[2][i]) + 7) // 8
+        assert torch.equal(a[1][i, :nb], b[1][i, :nb])
