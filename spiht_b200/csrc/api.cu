@@ -293,7 +293,7 @@ int spihtb_destroy(spihtb_ctx *ctx)
         cudaEventDestroy(ctx->ev_join);
         cudaEventDestroy(ctx->ev_order);
     }
-    DevBuf *bufs[] = {&ctx->pyr, &ctx->lists, &ctx->misc, &ctx->tmpa, &ctx->tmpb, &ctx->io, &ctx->io2, &ctx->fix, &ctx->u8lut, &ctx->blk};
+    DevBuf *bufs[] = {&ctx->pyr, &ctx->lists, &ctx->misc, &ctx->tmpa, &ctx->tmpb, &ctx->tail, &ctx->io, &ctx->io2, &ctx->fix, &ctx->u8lut, &ctx->blk};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
     for (int s = 0; s < SPIHTB_NSTAGES; ++s)

@@ -66,6 +66,7 @@ struct spihtb_ctx {
     spihtb::DevBuf lists;    // coder list storage, one slice per resident CTA
     spihtb::DevBuf misc;     // counters, small per-image arrays
     spihtb::DevBuf tmpa, tmpb;  // DWT approximation ping-pong (float64)
+    spihtb::DevBuf tail;        // forward tail kernel: two private approximation planes per (image, channel) plane
     spihtb::DevBuf io;       // staging for the host-pointer entry points
     spihtb::DevBuf io2;
     spihtb::DevBuf u8lut;    // k / 255.0 for uint8 pixels

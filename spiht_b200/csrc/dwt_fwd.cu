@@ -35,6 +35,8 @@ struct FwdK {
     int src_h, src_w;
     int bh, bw;             // band size of this level
     double *dst_ll;         // [nz][bh][bw] scratch (null at the last level)
+    long long src_ps, dst_ps;  // elements between consecutive planes of src / dst_ll (src_h src_w and bh bw, except in
+                               // the tail kernel, whose planes keep private scratch of a fixed stride)
     int32_t *coeffs;        // [nz][Hc][Wc]
     int Hc, Wc, sh, sw;     // detail block offsets of this level
     int mode, C, last;
@@ -225,7 +227,7 @@ __device__ __forceinline__ void dwt_fwd_task(const FwdK &p, int tx, int ty, int 
     const int gc = 2 * kf + sft;               // its first input column
     const int gr0 = 2 * r0 - (F - 2) + sft;    // first input row of the chunk's window
 
-    const Tin *plane = static_cast<const Tin *>(p.src) + (size_t)z * src_h * src_w;
+    const Tin *plane = static_cast<const Tin *>(p.src) + (size_t)z * (size_t)p.src_ps;
     const bool lane_vec = aligned && VFRAG >= 4 && gc >= 0 && gc + NC <= src_w;
     const bool warp_vec = __all_sync(0xffffffffu, lane_vec);
     int col[NC];
@@ -334,7 +336,7 @@ __device__ __forceinline__ void dwt_fwd_task(const FwdK &p, int tx, int ty, int 
     int32_t *prow = p.coeffs + (size_t)z * p.Hc * Wc + (ptrdiff_t)r0 * Wc + kf;
     const int o_ad = p.sw, o_da = p.sh * Wc, o_dd = p.sh * Wc + p.sw;
     constexpr bool ll_scratch = !LAST;
-    double *p_ll = ll_scratch ? p.dst_ll + ((size_t)z * p.bh + r0) * p.bw + kf : nullptr;
+    double *p_ll = ll_scratch ? p.dst_ll + (size_t)z * (size_t)p.dst_ps + (size_t)r0 * p.bw + kf : nullptr;
     const int bw = p.bw;
     // the lane's store plan (see store_pair) and magnitude masks, fixed for the strip
     const bool ok0 = col_ok[0], ok1 = NP == 2 ? col_ok[NP - 1] : false;
@@ -571,7 +573,7 @@ __global__ void __launch_bounds__(FT_WARPS * 32, (Wav<WID>::F == 6 ? 2 : 1)) dwt
             const int tx = t % k.tiles_x, ty = t / k.tiles_x;
             const int gc_first = 2 * (tx * NOUT - (F / 2 - 1)) + sft;
             constexpr int VB = 2 * NP * (int)sizeof(double) >= 16 ? 16 : 8;
-            const long long base = (long long)reinterpret_cast<uintptr_t>(k.src) + (long long)z * k.src_h * k.src_w * 8LL;
+            const long long base = (long long)reinterpret_cast<uintptr_t>(k.src) + (long long)z * k.src_ps * 8LL;
             const bool aligned = ((size_t)k.src_w * 8) % VB == 0 && (base + (long long)gc_first * 8LL) % VB == 0;
             if (k.last)
                 dwt_fwd_task<double, WID, NP, UNIT_M, true, PYR>(k, tx, ty, z, ring, aligned, nullptr);
@@ -607,7 +609,7 @@ __global__ void __launch_bounds__(FW_WARPS * 32, FwdCfg<WID>::MINB) dwt_fwd_leve
     const int gc_first = 2 * (tx * NOUT - (F / 2 - 1)) + sft;
     constexpr int VB = 2 * NP * (int)sizeof(Tin) >= 16 ? 16 : (2 * NP * (int)sizeof(Tin) >= 8 ? 8 : 4);  // vector bytes
     const long long base = (long long)reinterpret_cast<uintptr_t>(p.src) +
-                           (long long)z * p.src_h * p.src_w * (long long)sizeof(Tin);
+                           (long long)z * p.src_ps * (long long)sizeof(Tin);
     const bool aligned = ((size_t)p.src_w * sizeof(Tin)) % VB == 0 &&
                          (base + (long long)gc_first * (long long)sizeof(Tin)) % VB == 0;
     dwt_fwd_task<Tin, WID, NP, UNIT_M, LAST, PYR>(p, tx, ty, z, ring, aligned, s_lut);
@@ -939,6 +941,8 @@ int launch_forward(spihtb_ctx *ctx, const void *pixels, const XformArgs &x, int3
         k.u8lut = u8lut;
         k.tiles_x = k.tiles_y = k.RH = 0;
         k.ntasks = 0;
+        k.src_ps = (long long)k.src_h * k.src_w;
+        k.dst_ps = (long long)k.bh * k.bw;
         return k;
     };
     auto run_level = [&](int l, int z0, int nzg) -> int {
@@ -1029,16 +1033,35 @@ int launch_forward(spihtb_ctx *ctx, const void *pixels, const XformArgs &x, int3
             return ((g.band_w[l] + nout - 1) / nout) * ((g.band_h[l] + rhmax - 1) / rhmax);
         };
         const bool tail_on = getenv("SPIHTB_NO_TAIL") == nullptr;
+        const int tail_max = getenv("SPIHTB_TAIL_TASKS") ? atoi(getenv("SPIHTB_TAIL_TASKS")) : 8;
         int l = fused12 ? 2 : 1;
         for (; l < L; ++l) {
-            if (tail_on && L - l >= 2 && L - l <= FT_MAXLV && tasks_per_plane(l) <= 32) break;
+            if (tail_on && L - l >= 2 && L - l <= FT_MAXLV && tasks_per_plane(l) <= tail_max) break;
             rc = run_level(l, 0, nz);
             if (rc) return rc;
         }
         if (l < L) {
+            // Planes run through their levels independently, so the shared ping-pong planes (whose plane stride
+            // changes with the level) cannot be used: a plane at level l + 2 would write where another still reads
+            // level l.  Every plane gets two private scratch planes of the tail's largest approximation band.
+            const long long S = (((long long)g.band_h[l] * g.band_w[l]) + 1) / 2 * 2;
+            rc = ctx->ensure(ctx->tail, (size_t)nz * 2 * S * sizeof(double) + 256);
+            if (rc) return rc;
+            double *ts = static_cast<double *>(ctx->tail.p);
             FwdTail t;
             t.nlv = L - l;
-            for (int i = 0; i < t.nlv; ++i) t.lv[i] = make_k(l + i, 0);
+            for (int i = 0; i < t.nlv; ++i) {
+                FwdK &k = t.lv[i];
+                k = make_k(l + i, 0);
+                if (i > 0) {           // reads what the tail's previous level wrote
+                    k.src = ts + ((i - 1) & 1) * S;
+                    k.src_ps = 2 * S;
+                }
+                if (!k.last) {
+                    k.dst_ll = ts + (i & 1) * S;
+                    k.dst_ps = 2 * S;
+                }
+            }
             ctx->stage_begin(1);
             switch (g.wavelet) {
                 case SPIHTB_WAVELET_BIOR22: rc = launch_tail<SPIHTB_WAVELET_BIOR22>(ctx, t, nz); break;

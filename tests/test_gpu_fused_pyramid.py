@@ -114,3 +114,25 @@ def test_tail_kernel_equals_one_launch_per_level(monkeypatch, shape, wavelet, mo
     for i in range(2):
         nb = (int(a[2][i]) + 7) // 8
         assert torch.equal(a[1][i, :nb], b[1][i, :nb])
+
+
+def test_tail_kernel_many_planes_vs_oracle(monkeypatch):
+    """many planes running through their coarse levels at their own pace (more CTAs than the device holds at once):
+    every coefficient array still equals the float64 oracle's -- a plane that read another plane's scratch would not"""
+    import torch
+    import spiht_b200 as spiht
+    from oracle import wrapper_ref
+    from spiht_b200 import _lib, batch
+    B, c, h, w = 160, 3, 200, 264
+    rng = np.random.default_rng(9)
+    imgs = rng.random((B, c, h, w))
+    px = torch.from_numpy(imgs).cuda()
+    st = spiht.SpihtSettings()
+    g = _lib.plan(h, w)
+    monkeypatch.setenv("SPIHTB_TAIL_TASKS", "32")      # put as many levels as possible into the tail
+    got = batch.forward(px, g, st).cpu().numpy()
+    for b in (0, 1, 57, 101, 158, 159):
+        of, _, _ = wrapper_ref.forward_coeffs(imgs[b], return_float=True)
+        assert np.array_equal(got[b], of.astype(np.int32)), b
+    monkeypatch.setenv("SPIHTB_NO_TAIL", "1")
+    assert np.array_equal(batch.forward(px, g, st).cpu().numpy(), got)
