@@ -1033,7 +1033,10 @@ int launch_forward(spihtb_ctx *ctx, const void *pixels, const XformArgs &x, int3
             return ((g.band_w[l] + nout - 1) / nout) * ((g.band_h[l] + rhmax - 1) / rhmax);
         };
         const bool tail_on = getenv("SPIHTB_NO_TAIL") == nullptr;
-        const int tail_max = getenv("SPIHTB_TAIL_TASKS") ? atoi(getenv("SPIHTB_TAIL_TASKS")) : 8;
+        // opt-in (SPIHTB_TAIL_TASKS=n: levels with at most n tasks per plane go to the tail kernel): measured on B200
+        // the tail is slower than one launch per level at every threshold -- a plane's coarse
+        // levels are a serial chain of short, latency-bound streams, and one launch per level runs all planes abreast
+        const int tail_max = getenv("SPIHTB_TAIL_TASKS") ? atoi(getenv("SPIHTB_TAIL_TASKS")) : 0;
         int l = fused12 ? 2 : 1;
         for (; l < L; ++l) {
             if (tail_on && L - l >= 2 && L - l <= FT_MAXLV && tasks_per_plane(l) <= tail_max) break;

@@ -106,6 +106,7 @@ def test_tail_kernel_equals_one_launch_per_level(monkeypatch, shape, wavelet, mo
         torch.cuda.synchronize()
         return co, s, nbits, max_n, co2
     monkeypatch.delenv("SPIHTB_NO_TAIL", raising=False)
+    monkeypatch.setenv("SPIHTB_TAIL_TASKS", "16")     # the tail kernel is opt-in (slower than one launch per level)
     a = run()
     monkeypatch.setenv("SPIHTB_NO_TAIL", "1")
     b = run()
