@@ -277,68 +277,52 @@ __device__ __forceinline__ uint32_t lip_state_scan(uint32_t fn, uint32_t s_in, u
 // bit (s_lp + pos mod 32; the table is 32-byte aligned, so q mod 32 is the shift of the stream window), a_x: per-entry
 // child-length bytes to fill, a_t: set-type words (MSB-first), cnt: entries of the round.  Returns the bits consumed
 // (every entry one, every fired A set its child bits).
-// The walk is one dependent chain per fired set: position -> candidate mask -> leading one -> table load (the record's
-// child length) -> next position.  The load (~30 cycles) dominates it, so the step is software-pipelined around the
-// load: while the length of the current record is in flight, the candidate masks of the NEXT step are formed for all
-// five possible lengths (4 .. 8 child bits) from the three stream words and three set-type words held in registers
-// -- independent instructions the lone warp issues back to back -- and the arriving length only picks one of them.
 __device__ __noinline__ uint32_t lis_walk(uint32_t a_sw, uint32_t q, uint32_t a_x, uint32_t a_t, uint32_t cnt)
 {
-    const uint32_t a_swe = a_sw + (DEC_PLW - 1) * 4;               // last staged stream word
-    const uint32_t a_te = a_t + (DEC_CH / 32 + 3) * 4;             // last set-type word
+    const uint32_t a_swe = a_sw + (DEC_PLW - 1) * 4;  // last staged word
+    const uint32_t a_x31 = a_x + 31u;
     const uint32_t q0 = q;
-    // r0: the stream word holding q (bit offset q & 31), r1, r2 the next two, r3 prefetched; likewise t0 .. t3
-    uint32_t r0 = lds_u32(a_sw), r1 = lds_u32(a_sw + 4), r2 = lds_u32(a_sw + 8), r3 = lds_u32(min(a_sw + 12, a_swe));
-    uint32_t t0 = lds_u32(a_t), t1 = lds_u32(a_t + 4), t2 = lds_u32(a_t + 8), t3 = lds_u32(min(a_t + 12, a_te));
-    a_sw += 16;
-    a_t += 16;
-    uint32_t qbase = q & ~31u;   // table address of the first bit of r0
-    uint32_t e = 0, ebase = 0;   // entries consumed; first entry of t0
-    // 32 bits from `off` (0 .. 63) bits after the start of r0 / t0 (the funnel shift takes its count mod 32)
-    auto swin = [&](uint32_t off) { return off < 32 ? __funnelshift_l(r1, r0, off) : __funnelshift_l(r2, r1, off); };
-    auto twin = [&](uint32_t off) { return off < 32 ? __funnelshift_l(t1, t0, off) : __funnelshift_l(t2, t1, off); };
-    constexpr uint32_t LOOK = 0xffffff00u;   // a step looks at the next 24 entries: at most 24 + 8 bits consumed
-    uint32_t m = swin(q - qbase) & twin(0) & LOOK;
+    uint32_t r0 = lds_u32(a_sw), r1 = lds_u32(a_sw + 4), r2 = lds_u32(a_sw + 8);
+    a_sw += 12;
+    uint32_t t0 = lds_u32(a_t), t1 = lds_u32(a_t + 4), t2 = lds_u32(a_t + 8);
+    a_t += 12;
+    uint32_t e = 0;                                 // entries consumed in this round
+    uint32_t nextq = (q & ~31u) + 32, nexte = 32;   // where the windows run out of their first word
 #pragma unroll 1
     while (e < cnt) {
-        bool fresh = false;
+        const uint32_t w0 = __funnelshift_l(r1, r0, q);
+        const uint32_t tt = __funnelshift_l(t1, t0, e);
+        const uint32_t m = w0 & tt & 0xffffff00u;
+        uint32_t hb;
+        asm("bfind.u32 %0, %1;" : "=r"(hb) : "r"(m));  // 31 - distance of the fired set
+        const uint32_t at = q - hb;                     // table address of the set, minus 31
+        const uint32_t len = lds_u8(at + 31u);
+        const uint32_t e1 = e - hb + 32u;
         if (__builtin_expect(m != 0, 1)) {
-            const uint32_t dist = (uint32_t)__clz((int)m);      // entries before the fired set (0 .. 23)
-            const uint32_t fq = q + dist, fe = e + dist;
-            const uint32_t len = lds_u8(fq);                     // child-bit length of the record starting there
-            // next step for every possible length, while the load is in flight
-            const uint32_t tw = twin(fe + 1 - ebase) & LOOK;
-            const uint32_t o = fq + 1 - qbase;                   // <= 31 + 23 + 1; + 8 <= 63
-            const uint32_t m4 = swin(o + 4) & tw, m5 = swin(o + 5) & tw, m6 = swin(o + 6) & tw, m7 = swin(o + 7) & tw,
-                           m8 = swin(o + 8) & tw;
-            sts_u8(a_x + fe, len);
-            const uint32_t ma = len == 4 ? m4 : m5, mb = len == 6 ? m6 : (len == 7 ? m7 : m8);
-            m = len < 6 ? ma : mb;
-            q = fq + 1 + len;
-            e = fe + 1;
+            sts_u8(a_x31 + e - hb, len);
+            e = e1;
+            q = at + len + 32u;
         } else {  // no fired A set within the next 24 entries
             const uint32_t sh = min(24u, cnt - e);
             e += sh;
             q += sh;
-            fresh = true;
         }
-        if (q - qbase >= 32) {
-            qbase += 32;
-            r0 = r1;
-            r1 = r2;
-            r2 = r3;
-            r3 = lds_u32(min(a_sw, a_swe));
-            a_sw += 4;
+        if (__builtin_expect(q >= nextq || e >= nexte, 0)) {
+            if (q >= nextq) {
+                nextq += 32;
+                r0 = r1;
+                r1 = r2;
+                r2 = lds_u32(min(a_sw, a_swe));
+                a_sw += 4;
+            }
+            if (e >= nexte) {
+                nexte += 32;
+                t0 = t1;
+                t1 = t2;
+                t2 = lds_u32(a_t);
+                a_t += 4;
+            }
         }
-        if (e - ebase >= 32) {
-            ebase += 32;
-            t0 = t1;
-            t1 = t2;
-            t2 = t3;
-            t3 = lds_u32(min(a_t, a_te));
-            a_t += 4;
-        }
-        if (fresh) m = swin(q - qbase) & twin(e - ebase) & LOOK;
     }
     return q - q0;
 }
