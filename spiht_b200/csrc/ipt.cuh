@@ -102,10 +102,12 @@ __device__ __forceinline__ double ipt_fast_pow(double a, const PowTab &t)   // a
     const double m = __longlong_as_double((bits & 0x000fffffffffffffLL) | 0x3ff0000000000000LL);
     const int k = (int)((bits >> 48) & 15);
     const double r = fma(m, t.inv_c[k], -1.0);
-    double s = t.coef[9];
-#pragma unroll
-    for (int n = 8; n >= 0; --n) s = fma(s, r, t.coef[n]);
-    s = fma(s, r, 1.0);
+    // 1 + c1 r + ... + c10 r^10 by Estrin's scheme (dependency depth 4 instead of Horner's 10)
+    const double r2 = r * r, r4 = r2 * r2, r8 = r4 * r4;
+    const double p01 = fma(t.coef[0], r, 1.0), p23 = fma(t.coef[2], r, t.coef[1]), p45 = fma(t.coef[4], r, t.coef[3]),
+                 p67 = fma(t.coef[6], r, t.coef[5]), p89 = fma(t.coef[8], r, t.coef[7]);
+    const double q0 = fma(p23, r2, p01), q1 = fma(p67, r2, p45), q2 = fma(t.coef[9], r2, p89);
+    const double s = fma(q2, r8, fma(q1, r4, q0));
     return (t.expo[e + 64] * t.c_p[k]) * s;
 }
 // sign(a) |a|^p.  `t`: the table in SHARED memory (ipt_stage_table): the interval and exponent indices differ from
