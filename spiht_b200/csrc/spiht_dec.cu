@@ -36,6 +36,7 @@
 // CTA scan) and applied by one thread after each parallel step.  Even LL sizes
 // (all BASELINE configs) never take that path.
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "kernels.cuh"
@@ -70,6 +71,7 @@ struct DecK {
     int top_ei, top_ej;        // slices.top_slice.end_i / end_j
     const int32_t *slices;     // device [level][3][4]: start_i, end_i, start_j, end_j in the caller's order da, ad, dd
     int32_t *meta_err;         // set to 1 when the reference would have panicked (slice index out of range)
+    int walk_variant;
 };
 
 // ---- decode_with_metadata helpers ----------------------------------------------------------------------
@@ -327,6 +329,64 @@ __device__ __noinline__ uint32_t lis_walk(uint32_t a_sw, uint32_t q, uint32_t a_
     return q - q0;
 }
 
+// ---- the walk as it ships: the same steps with NO branch inside.  The loop above spends a third of its time in
+// control flow: a lone warp pays the full fetch bubble of every BRA / BSSY / BSYNC, and a step has three.  Here the
+// word rotations are selects (the word after the window is loaded every step, ahead of need), a step past the
+// round's end is a no-op (the set-type window is zero there and cnt - e is 0), so UNROLL steps run as straight-line
+// code and the loop tests its exit once per UNROLL steps.  34 instead of 25 instructions per step, 83 instead of 126
+// cycles (5.8 -> 3.6 M cycles per 1024^2 image at 0.5 bpp; UNROLL 1 / 2 / 4 / 8: 4.9 / 4.0 / 3.8 / 3.6 M).
+// Measured and dropped on the way: windows from byte-granular tables in shared memory instead of registers (28
+// instructions, but a second load on the dependency chain: 4.6 M cycles); the walker warp of the SM's second CTA on
+// another scheduler (decode kernel 4.30 -> 4.46 ms); every thread walking one 32-entry segment from a candidate
+// position, resolved by following the true path through the exits (bit-exact; 512 walkers saturate the schedulers
+// that one walker leaves idle: 5.3 M cycles).
+template <int UNROLL>
+__device__ __noinline__ uint32_t lis_walk_nb(uint32_t a_sw, uint32_t q, uint32_t a_x, uint32_t a_t, uint32_t cnt)
+{
+    const uint32_t a_swe = a_sw + (DEC_PLW - 1) * 4;
+    const uint32_t a_x31 = a_x + 31u;
+    const uint32_t q0 = q;
+    uint32_t r0 = lds_u32(a_sw), r1 = lds_u32(a_sw + 4), r2 = lds_u32(a_sw + 8);
+    a_sw += 12;
+    uint32_t t0 = lds_u32(a_t), t1 = lds_u32(a_t + 4), t2 = lds_u32(a_t + 8);
+    a_t += 12;
+    uint32_t e = 0;
+    uint32_t nextq = (q & ~31u) + 32, nexte = 32;
+#pragma unroll 1
+    while (e < cnt) {
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const uint32_t rn = lds_u32(min(a_sw, a_swe));
+            const uint32_t tn = lds_u32(a_t);
+            const uint32_t w0 = __funnelshift_l(r1, r0, q);
+            const uint32_t tt = __funnelshift_l(t1, t0, e);
+            const uint32_t m = w0 & tt & 0xffffff00u;
+            uint32_t hb;
+            asm("bfind.u32 %0, %1;" : "=r"(hb) : "r"(m));
+            const uint32_t at = q - hb;
+            const uint32_t len = lds_u8(at + 31u);
+            // (once e == cnt the set-type window is all zeros and cnt - e is 0: the step is a no-op)
+            const bool f = m != 0;
+            const uint32_t sh = min(24u, cnt - e);
+            if (f) sts_u8(a_x31 + e - hb, len);
+            e = f ? e - hb + 32u : e + sh;
+            q = f ? at + len + 32u : q + sh;
+            const bool rq = q >= nextq, re = e >= nexte;
+            r0 = rq ? r1 : r0;
+            r1 = rq ? r2 : r1;
+            r2 = rq ? rn : r2;
+            a_sw += rq ? 4u : 0u;
+            nextq += rq ? 32u : 0u;
+            t0 = re ? t1 : t0;
+            t1 = re ? t2 : t1;
+            t2 = re ? tn : t2;
+            a_t += re ? 4u : 0u;
+            nexte += re ? 32u : 0u;
+        }
+    }
+    return q - q0;
+}
+
 // META: also fill the decode_with_metadata table.  The parse then runs one bit position further than the data
 // (limit + 1): the reference assigns the row of the bit it is about to read before it finds the data exhausted,
 // so the table has one more row than there are bits.  That phantom bit can change no coefficient -- a record that
@@ -374,6 +434,9 @@ __global__ void __launch_bounds__(DEC_NT, META ? 1 : 2) spiht_decode_kernel(cons
         s_len[tid] = (uint8_t)len;
     }
     if (tid == 0) s_na = 0;
+    // the walk may run past the end of a short stream into words / table bytes no round has staged yet
+    for (int w = tid; w < DEC_PLW; w += DEC_NT) s_sw[w] = 0;
+    for (int w = tid; w < DEC_PLW * 8; w += DEC_NT) reinterpret_cast<uint32_t *>(s_lp)[w] = 0;
     // bits per thread in a LIP round; the ordered write queue bounds it when cells can be duplicated
     const int BPT = has_dups ? 4 : 32;
 
@@ -395,7 +458,6 @@ __global__ void __launch_bounds__(DEC_NT, META ? 1 : 2) spiht_decode_kernel(cons
         int32_t *rec = p.out + (size_t)b * C * H * W;
         int n = p.n[b];
         n = n < 0 ? 0 : (n > 31 ? 31 : n);
-
         // ---- list initialisation (encoder_decoder.rs:329-348)
         uint32_t *lip = lipA, *lip_alt = lipB;
         const uint32_t T0 = ll_h * ll_w * C;
@@ -587,9 +649,19 @@ __global__ void __launch_bounds__(DEC_NT, META ? 1 : 2) spiht_decode_kernel(cons
                         const uint32_t cnt = min((uint32_t)DEC_CH, cur_len - ebase);
                         DEC_PROF_T0();
                         // set-type mask of this round's entries; clear the child-length bytes
-                        for (uint32_t w = wid; w < (cnt + 31) / 32 + 3; w += DEC_NW) {
+                        constexpr int TMI = (DEC_CH / 32 + 3 + DEC_NW - 1) / DEC_NW;  // iterations per warp
+                        uint32_t tkey[TMI];
+#pragma unroll
+                        for (int it = 0; it < TMI; ++it) {  // all loads in flight before the first is used
+                            const uint32_t e = (uint32_t)(wid + it * DEC_NW) * 32 + lane;
+                            tkey[it] = e < cnt ? cur[ebase + e] : 0u;
+                        }
+#pragma unroll
+                        for (int it = 0; it < TMI; ++it) {
+                            const uint32_t w = (uint32_t)(wid + it * DEC_NW);
+                            if (w >= (cnt + 31) / 32 + 3) break;
                             const uint32_t e = w * 32 + lane;
-                            const uint32_t key = e < cnt ? cur[ebase + e] : 0u;
+                            const uint32_t key = tkey[it];
                             bool a_with_children = false;
                             if (key >> 31) {
                                 uint32_t k, i, j, ci, cj;
@@ -646,10 +718,12 @@ __global__ void __launch_bounds__(DEC_NT, META ? 1 : 2) spiht_decode_kernel(cons
                             // of the stream window and the funnel shift wraps it), the entry index e is the
                             // shift of the set-type window, and both word rotations and the step without a
                             // fired set sit behind one rarely taken branch.
-                            const uint32_t used = lis_walk((uint32_t)__cvta_generic_to_shared(s_sw),
-                                                           (uint32_t)__cvta_generic_to_shared(s_lp) + (uint32_t)(pos & 31),
-                                                           (uint32_t)__cvta_generic_to_shared(s_x),
-                                                           (uint32_t)__cvta_generic_to_shared(s_tmask), cnt);
+                            const uint32_t wa = (uint32_t)__cvta_generic_to_shared(s_sw);
+                            const uint32_t wq = (uint32_t)__cvta_generic_to_shared(s_lp) + (uint32_t)(pos & 31);
+                            const uint32_t wx = (uint32_t)__cvta_generic_to_shared(s_x);
+                            const uint32_t wt = (uint32_t)__cvta_generic_to_shared(s_tmask);
+                            const uint32_t used = p.walk_variant == 0 ? lis_walk(wa, wq, wx, wt, cnt)
+                                                                      : lis_walk_nb<8>(wa, wq, wx, wt, cnt);
                             // bits consumed: every entry one, every fired A set its child bits
                             s_chain_p = pos + used;
                             s_na = 0;
@@ -689,7 +763,10 @@ __global__ void __launch_bounds__(DEC_NT, META ? 1 : 2) spiht_decode_kernel(cons
                             const uint64_t pe = p_base + e + (valid ? s_grp[e >> 5] : 0u) + (inc - xe);
                             const bool avail = valid && pe < limit;
                             const uint32_t key = valid ? cur[ebase + e] : 0u;
-                            const bool fired = avail && br.bit(pe);
+                            // the entry's bit and the 32 after it, from the staged words (MSB-first; staged from the
+                            // word of p_base on, so every bit the round can reach is there)
+                            const uint32_t so = (uint32_t)(p_base & 31) + (uint32_t)(pe - p_base);
+                            const bool fired = avail && ((s_sw[so >> 5] << (so & 31)) >> 31);
                             uint32_t k = 0, i = 0, j = 0, ci = 0, cj = 0;
                             uint32_t nlsp = 0, nlip = 0, nnext = 0, sigmask = 0, sgnmask = 0, nread = 0;
                             uint32_t ndef = 0, defmask = 0;
@@ -705,7 +782,7 @@ __global__ void __launch_bounds__(DEC_NT, META ? 1 : 2) spiht_decode_kernel(cons
                                 const bool has = offspring_corner(i, j, H, W, ll_h, ll_w, ci, cj);
                                 if (isA) {
                                     uint64_t q = pe + 1;
-                                    uint32_t cbits = br.get32(q);
+                                    uint32_t cbits = __brev(__funnelshift_l(s_sw[((so + 1) >> 5) + 1], s_sw[(so + 1) >> 5], so + 1));
                                     bool cut = false;
                                     if (has) {
 #pragma unroll
@@ -913,6 +990,8 @@ int launch_decode(spihtb_ctx *ctx, const DecArgs &a)
     k.BH = (a.H + 63) / 64;
     k.BW = (a.W + 63) / 64;
 
+    k.walk_variant = 8;
+    if (const char *e = getenv("SPIHTB_WALK")) k.walk_variant = atoi(e);
     int occ = 1;
     if (a.meta)
         SPIHTB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, spiht_decode_kernel<true>, DEC_NT, 0));
@@ -941,6 +1020,8 @@ int launch_decode(spihtb_ctx *ctx, const DecArgs &a)
     k.counter = static_cast<unsigned int *>(ctx->misc.p);
 
     ctx->stage_begin(5);
+    // (zeroing each image's array inside the kernel, under the first passes, was measured slower than this memset:
+    // 5.56 against 5.41 ms per 256 images -- one CTA cannot issue 13 MB of stores as fast as the copy engine path)
     SPIHTB_CUDA_CHECK(cudaMemsetAsync(a.out, 0, sizeof(int32_t) * (size_t)a.B * a.C * a.H * a.W, ctx->stream));
     SPIHTB_CUDA_CHECK(cudaMemsetAsync(k.counter, 0, sizeof(unsigned int), ctx->stream));
     if (a.meta)
