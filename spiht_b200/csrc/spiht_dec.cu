@@ -135,6 +135,7 @@ __device__ __forceinline__ void meta_row(const DecK &p, int32_t *mrows, uint64_t
 // builds compile them out and do not export spihtb_debug_dec_prof
 #ifdef SPIHTB_PROF
 __device__ unsigned long long g_dec_prof[16];
+__device__ unsigned long long g_dec_img[1024][4];  // per image: total cycles, walk cycles, smid, start clock
 #define DEC_PROF_T0() const long long _t0 = clock64()
 #define DEC_PROF_ADD(slot)                                                        \
     do {                                                                          \
@@ -333,17 +334,18 @@ __device__ __noinline__ uint32_t lis_walk(uint32_t a_sw, uint32_t q, uint32_t a_
 // control flow: a lone warp pays the full fetch bubble of every BRA / BSSY / BSYNC, and a step has three.  Here the
 // word rotations are selects (the word after the window is loaded every step, ahead of need), a step past the
 // round's end is a no-op (the set-type window is zero there and cnt - e is 0), so UNROLL steps run as straight-line
-// code and the loop tests its exit once per UNROLL steps.  34 instead of 25 instructions per step, 83 instead of 126
-// cycles (5.8 -> 3.6 M cycles per 1024^2 image at 0.5 bpp; UNROLL 1 / 2 / 4 / 8: 4.9 / 4.0 / 3.8 / 3.6 M).
+// code and the loop tests its exit once per UNROLL steps.  The stream window is aligned to the position right after
+// the fired bit (known as soon as the set is located) so that only one shift -- by the child length -- sits behind
+// the length load.  35 instead of 25 instructions per step, 78 instead of 126 cycles: 5.8 -> 3.4 M cycles per 1024^2
+// image at 0.5 bpp (without the alignment trick, UNROLL 1 / 2 / 4 / 8: 4.9 / 4.0 / 3.8 / 3.6 M).
 // Measured and dropped on the way: windows from byte-granular tables in shared memory instead of registers (28
 // instructions, but a second load on the dependency chain: 4.6 M cycles); the walker warp of the SM's second CTA on
 // another scheduler (decode kernel 4.30 -> 4.46 ms); every thread walking one 32-entry segment from a candidate
 // position, resolved by following the true path through the exits (bit-exact; 512 walkers saturate the schedulers
 // that one walker leaves idle: 5.3 M cycles).
 template <int UNROLL>
-__device__ __noinline__ uint32_t lis_walk_nb(uint32_t a_sw, uint32_t q, uint32_t a_x, uint32_t a_t, uint32_t cnt)
+__device__ __noinline__ uint32_t lis_walk_pa(uint32_t a_sw, uint32_t q, uint32_t a_x, uint32_t a_t, uint32_t cnt)
 {
-    const uint32_t a_swe = a_sw + (DEC_PLW - 1) * 4;
     const uint32_t a_x31 = a_x + 31u;
     const uint32_t q0 = q;
     uint32_t r0 = lds_u32(a_sw), r1 = lds_u32(a_sw + 4), r2 = lds_u32(a_sw + 8);
@@ -351,27 +353,30 @@ __device__ __noinline__ uint32_t lis_walk_nb(uint32_t a_sw, uint32_t q, uint32_t
     uint32_t t0 = lds_u32(a_t), t1 = lds_u32(a_t + 4), t2 = lds_u32(a_t + 8);
     a_t += 12;
     uint32_t e = 0;
+    uint32_t A = q, le = 0;   // next bit: A + le (le <= 8); the window registers hold the word of A in r0
     uint32_t nextq = (q & ~31u) + 32, nexte = 32;
 #pragma unroll 1
     while (e < cnt) {
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
-            const uint32_t rn = lds_u32(min(a_sw, a_swe));
+            const uint32_t rn = lds_u32(a_sw);
             const uint32_t tn = lds_u32(a_t);
-            const uint32_t w0 = __funnelshift_l(r1, r0, q);
-            const uint32_t tt = __funnelshift_l(t1, t0, e);
-            const uint32_t m = w0 & tt & 0xffffff00u;
+            const uint32_t whi = __funnelshift_l(r1, r0, A), wlo = __funnelshift_l(r2, r1, A);
+            const uint32_t tts = __funnelshift_l(t1, t0, e) & 0xffffff00u;
+            const uint32_t w0 = __funnelshift_l(wlo, whi, le);
+            const uint32_t m = w0 & tts;
             uint32_t hb;
             asm("bfind.u32 %0, %1;" : "=r"(hb) : "r"(m));
-            const uint32_t at = q - hb;
+            const uint32_t qq = A + le;
+            const uint32_t at = qq - hb;
             const uint32_t len = lds_u8(at + 31u);
-            // (once e == cnt the set-type window is all zeros and cnt - e is 0: the step is a no-op)
             const bool f = m != 0;
             const uint32_t sh = min(24u, cnt - e);
             if (f) sts_u8(a_x31 + e - hb, len);
             e = f ? e - hb + 32u : e + sh;
-            q = f ? at + len + 32u : q + sh;
-            const bool rq = q >= nextq, re = e >= nexte;
+            A = f ? at + 32u : qq + sh;
+            le = f ? len : 0u;
+            const bool rq = A >= nextq, re = e >= nexte;
             r0 = rq ? r1 : r0;
             r1 = rq ? r2 : r1;
             r2 = rq ? rn : r2;
@@ -384,7 +389,7 @@ __device__ __noinline__ uint32_t lis_walk_nb(uint32_t a_sw, uint32_t q, uint32_t
             nexte += re ? 32u : 0u;
         }
     }
-    return q - q0;
+    return A + le - q0;
 }
 
 // META: also fill the decode_with_metadata table.  The parse then runs one bit position further than the data
@@ -483,6 +488,9 @@ __global__ void __launch_bounds__(DEC_NT, META ? 1 : 2) spiht_decode_kernel(cons
 
         uint64_t pos = 0;  // uniform: next unread bit
         DEC_PROF_MARK(_timg);
+#ifdef SPIHTB_PROF
+        unsigned long long walk_cycles = 0;
+#endif
         for (; pos < limit; --n) {
             const int32_t basev = n == 0 ? 1 : (int32_t)((1u << (n - 1)) + (1u << n));
             const uint32_t lsp_len0 = lsp_len;
@@ -723,11 +731,14 @@ __global__ void __launch_bounds__(DEC_NT, META ? 1 : 2) spiht_decode_kernel(cons
                             const uint32_t wx = (uint32_t)__cvta_generic_to_shared(s_x);
                             const uint32_t wt = (uint32_t)__cvta_generic_to_shared(s_tmask);
                             const uint32_t used = p.walk_variant == 0 ? lis_walk(wa, wq, wx, wt, cnt)
-                                                                      : lis_walk_nb<8>(wa, wq, wx, wt, cnt);
+                                                                      : lis_walk_pa<8>(wa, wq, wx, wt, cnt);
                             // bits consumed: every entry one, every fired A set its child bits
                             s_chain_p = pos + used;
                             s_na = 0;
                             DEC_PROF_SINCE(2, _tc);
+#ifdef SPIHTB_PROF
+                            walk_cycles += (unsigned long long)(clock64() - _tc);
+#endif
                             DEC_PROF_CNT(11, 1);
                         }
                         __syncthreads();
@@ -942,11 +953,27 @@ __global__ void __launch_bounds__(DEC_NT, META ? 1 : 2) spiht_decode_kernel(cons
             }
         }
         DEC_PROF_SINCE(5, _timg);
+#ifdef SPIHTB_PROF
+        if (tid == 0 && b < 1024) {
+            uint32_t smid;
+            asm("mov.u32 %0, %%smid;" : "=r"(smid));
+            g_dec_img[b][0] = (unsigned long long)(clock64() - _timg);
+            g_dec_img[b][1] = walk_cycles;
+            g_dec_img[b][2] = smid;
+            g_dec_img[b][3] = (unsigned long long)_timg;
+        }
+#endif
     }
 }
 
 #ifdef SPIHTB_PROF
 // debug: read and clear the phase counters (tools/dec_phases.py)
+extern "C" int spihtb_debug_dec_img(unsigned long long *out, int n)
+{
+    if (n > 1024) n = 1024;
+    if (cudaMemcpyFromSymbol(out, g_dec_img, sizeof(unsigned long long) * 4 * n) != cudaSuccess) return SPIHTB_ECUDA;
+    return SPIHTB_OK;
+}
 extern "C" int spihtb_debug_dec_prof(unsigned long long *out16)
 {
     unsigned long long z[16] = {0};
@@ -990,7 +1017,7 @@ int launch_decode(spihtb_ctx *ctx, const DecArgs &a)
     k.BH = (a.H + 63) / 64;
     k.BW = (a.W + 63) / 64;
 
-    k.walk_variant = 8;
+    k.walk_variant = 1;   // SPIHTB_WALK=0: the branchy loop (A-B measurements)
     if (const char *e = getenv("SPIHTB_WALK")) k.walk_variant = atoi(e);
     int occ = 1;
     if (a.meta)

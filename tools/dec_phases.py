@@ -33,3 +33,18 @@ for it in range(3):
     names = ["lip_rounds", "lis_tmask", "chain", "lis_batches", "refine", "image_total"]
     print({n: v[i] for i, n in enumerate(names)},
           {"lip_rounds_n": v[8], "chain_iters": v[9], "chain_events": v[10], "lis_rounds": v[11], "lis_batches_n": v[12]})
+
+# per image: total / walk cycles and the SM it ran on (prof builds)
+if hasattr(lib, "spihtb_debug_dec_img"):
+    import numpy as np
+    n = min(a.batch, 1024)
+    buf = (ctypes.c_ulonglong * (4 * n))()
+    lib.spihtb_debug_dec_img(buf, n)
+    arr = np.array(list(buf), dtype=np.int64).reshape(n, 4)
+    sm = arr[:, 2]
+    cnt = np.bincount(sm, minlength=160)
+    shared = cnt[sm] > 1
+    for name, m in (("alone on its SM", ~shared), ("sharing its SM", shared)):
+        if m.any():
+            print(name, int(m.sum()), "images: total cycles min/median/max", int(arr[m, 0].min()), int(np.median(arr[m, 0])),
+                  int(arr[m, 0].max()), "walk median", int(np.median(arr[m, 1])))
