@@ -489,7 +489,7 @@ __global__ void __launch_bounds__(DEC_NT, META ? 1 : 2) spiht_decode_kernel(cons
         uint64_t pos = 0;  // uniform: next unread bit
         DEC_PROF_MARK(_timg);
 #ifdef SPIHTB_PROF
-        unsigned long long walk_cycles = 0;
+        unsigned long long walk_cycles = 0, last_walk = 0, prev_tb = 0;
 #endif
         for (; pos < limit; --n) {
             const int32_t basev = n == 0 ? 1 : (int32_t)((1u << (n - 1)) + (1u << n));
@@ -737,7 +737,8 @@ __global__ void __launch_bounds__(DEC_NT, META ? 1 : 2) spiht_decode_kernel(cons
                             s_na = 0;
                             DEC_PROF_SINCE(2, _tc);
 #ifdef SPIHTB_PROF
-                            walk_cycles += (unsigned long long)(clock64() - _tc);
+                            last_walk = (unsigned long long)(clock64() - _tc);
+                            walk_cycles += last_walk;
 #endif
                             DEC_PROF_CNT(11, 1);
                         }
@@ -880,6 +881,20 @@ __global__ void __launch_bounds__(DEC_NT, META ? 1 : 2) spiht_decode_kernel(cons
                         __syncthreads();  // s_x / s_tmask / s_grp are rewritten by the next round
                         DEC_PROF_SINCE(3, _tb);
                         DEC_PROF_CNT(12, (cnt + DEC_NT - 1) / DEC_NT);
+#ifdef SPIHTB_PROF
+                        // how much of the parallel work could run under the next round's walk: rounds that are not
+                        // the last of their generation (slot 13: their batch cycles; slot 14: min(batch cycles of
+                        // round r-1, walk cycles of round r) summed; slot 15: generations)
+                        {
+                            const unsigned long long tb_c = (unsigned long long)(clock64() - _tb);
+                            if (tid == 0 && b == 0) {
+                                if (ebase > 0) g_dec_prof[14] += prev_tb < last_walk ? prev_tb : last_walk;
+                                if (ebase + DEC_CH < cur_len) g_dec_prof[13] += tb_c;
+                                if (ebase == 0) g_dec_prof[15] += 1;
+                            }
+                            prev_tb = tb_c;
+                        }
+#endif
                         if (pos >= limit) ended = true;
                     }
                     uint32_t *old = cur;

@@ -13,7 +13,7 @@
 //     may share with its neighbours in the stream go out with atomicOr (the stream row is zeroed first);
 //   - a fired D-set needs the number of significant offspring of all sets before it: the dense-A step is split
 //     into gather + count (results parked in shared memory), a second exchange, then emit + append.
-// Bit-exact with the single-CTA coder and the oracle (tests/test_gpu_spiht.py runs the suite in both modes).
+// Bit-exact with the single-CTA coder and the CPU oracle (tests/test_gpu_spiht.py runs the suite in both modes).
 #include <cooperative_groups.h>
 
 #include <algorithm>

@@ -32,7 +32,8 @@ for it in range(3):
     v = list(out)
     names = ["lip_rounds", "lis_tmask", "chain", "lis_batches", "refine", "image_total"]
     print({n: v[i] for i, n in enumerate(names)},
-          {"lip_rounds_n": v[8], "chain_iters": v[9], "chain_events": v[10], "lis_rounds": v[11], "lis_batches_n": v[12]})
+          {"lip_rounds_n": v[8], "chain_iters": v[9], "chain_events": v[10], "lis_rounds": v[11], "lis_batches_n": v[12],
+           "batch_cycles_not_last_round": v[13], "overlappable": v[14], "generations": v[15]})
 
 # per image: total / walk cycles and the SM it ran on (prof builds)
 if hasattr(lib, "spihtb_debug_dec_img"):
