@@ -36,6 +36,7 @@
 // CTA scan) and applied by one thread after each parallel step.  Even LL sizes
 // (all BASELINE configs) never take that path.
 #include <algorithm>
+#include <type_traits>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -72,6 +73,7 @@ struct DecK {
     const int32_t *slices;     // device [level][3][4]: start_i, end_i, start_j, end_j in the caller's order da, ad, dd
     int32_t *meta_err;         // set to 1 when the reference would have panicked (slice index out of range)
     int walk_variant;
+    int pipe;   // apply round r-1 under the walk of round r
 };
 
 // ---- decode_with_metadata helpers ----------------------------------------------------------------------
@@ -235,6 +237,42 @@ __device__ void apply_queue(const uint2 *dq, uint32_t cnt, const KeyFmt &kf, int
         else
             *cell = (int32_t)op.y;
     }
+}
+
+// ---- barrier and scan for the threads that apply a round: the whole CTA, or (PIPE) warps 1..15 on named barrier 1
+// while warp 0 walks the next round
+template <bool PIPE>
+__device__ __forceinline__ void dec_sync()
+{
+    if (PIPE)
+        asm volatile("bar.sync 1, %0;" ::"n"(DEC_NT - 32) : "memory");
+    else
+        __syncthreads();
+}
+template <bool PIPE>
+__device__ __forceinline__ uint64_t dec_exscan(uint64_t v, uint64_t *warp_tot, uint64_t &total)
+{
+    if (!PIPE) return block_exscan<DEC_NT>(v, warp_tot, total);
+    constexpr int NW = DEC_NW - 1;
+    const int lane = threadIdx.x & 31, wid = (int)(threadIdx.x >> 5) - 1;
+    uint64_t inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint64_t t = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += t;
+    }
+    dec_sync<true>();  // previous users of warp_tot are done
+    if (lane == 31) warp_tot[wid] = inc;
+    dec_sync<true>();
+    uint64_t base = 0, tot = 0;
+#pragma unroll
+    for (int q = 0; q < NW; ++q) {
+        const uint64_t t = warp_tot[q];
+        if (q < wid) base += t;
+        tot += t;
+    }
+    total = tot;
+    return base + inc - v;
 }
 
 // ---- LIP parse: 2-state automaton over the bits of a pass -------------------
@@ -401,14 +439,15 @@ template <bool META>
 __global__ void __launch_bounds__(DEC_NT, META ? 1 : 2) spiht_decode_kernel(const DecK p)
 {
     __shared__ uint32_t s_tmask[DEC_CH / 32 + 4];  // A sets with offspring (a fired record carries child bits)
-    __shared__ __align__(16) uint8_t s_x[DEC_CH];               // child-bit length of fired A sets, 0 elsewhere
-    __shared__ uint32_t s_grp[DEC_CH / 32];        // exclusive prefix of s_x per 32 entries
+    __shared__ __align__(16) uint8_t s_x2[2][DEC_CH];           // child-bit length of fired A sets, 0 elsewhere (double-buffered)
+    __shared__ uint32_t s_grp2[2][DEC_CH / 32];    // exclusive prefix of s_x per 32 entries
+    __shared__ uint32_t s_cnt[4];                  // list counters handed back by the applying warps
     __shared__ uint64_t s_wtot[DEC_NW];
     __shared__ uint32_t s_wfn[DEC_NW];
     __shared__ uint64_t s_chain_p;
     // staged for the chain: the stream words the round can reach, bit-reversed (MSB-first), and for every
     // bit position the child-bit length of a fired A record whose "1" sits there
-    __shared__ uint32_t s_sw[DEC_PLW];
+    __shared__ uint32_t s_sw2[2][DEC_PLW];
     __shared__ __align__(32) uint8_t s_lp[DEC_PLW * 32];
     __shared__ uint32_t s_na;  // A sets with offspring in the round
     __shared__ uint8_t s_len[256];  // child-bit length of a fired A record from its next 8 bits
@@ -440,7 +479,7 @@ __global__ void __launch_bounds__(DEC_NT, META ? 1 : 2) spiht_decode_kernel(cons
     }
     if (tid == 0) s_na = 0;
     // the walk may run past the end of a short stream into words / table bytes no round has staged yet
-    for (int w = tid; w < DEC_PLW; w += DEC_NT) s_sw[w] = 0;
+    for (int w = tid; w < 2 * DEC_PLW; w += DEC_NT) (&s_sw2[0][0])[w] = 0;
     for (int w = tid; w < DEC_PLW * 8; w += DEC_NT) reinterpret_cast<uint32_t *>(s_lp)[w] = 0;
     // bits per thread in a LIP round; the ordered write queue bounds it when cells can be duplicated
     const int BPT = has_dups ? 4 : 32;
@@ -651,10 +690,16 @@ __global__ void __launch_bounds__(DEC_NT, META ? 1 : 2) spiht_decode_kernel(cons
                 uint32_t *cur = R, *nxt = G0;
                 uint32_t cur_len = r_len, rkeep = 0;
                 int gen = 0;
+                const bool pipe = !META && !has_dups && p.pipe != 0;
                 while (cur_len > 0 && !ended) {
                     uint32_t nxt_len = 0;
-                    for (uint32_t ebase = 0; ebase < cur_len && !ended; ebase += DEC_CH) {
-                        const uint32_t cnt = min((uint32_t)DEC_CH, cur_len - ebase);
+                    // One round = up to DEC_CH entries of the generation: stage (all threads), walk (one thread), apply (parallel).
+                    // Pipelined form (even LL sizes, no metadata table): the staged words, child lengths and group prefixes are
+                    // double-buffered, and while thread 0 walks round r warps 1..15 apply round r-1 behind a named barrier of
+                    // their own; the list counters they advance come back through shared memory.
+                    auto stage_round = [&](uint32_t ebase, uint32_t cnt, int buf) {
+                        uint8_t *sx = s_x2[buf];
+                        uint32_t *ssw = s_sw2[buf];
                         DEC_PROF_T0();
                         // set-type mask of this round's entries; clear the child-length bytes
                         constexpr int TMI = (DEC_CH / 32 + 3 + DEC_NW - 1) / DEC_NW;  // iterations per warp
@@ -681,7 +726,7 @@ __global__ void __launch_bounds__(DEC_NT, META ? 1 : 2) spiht_decode_kernel(cons
                                 s_tmask[w] = __brev(m);  // MSB-first for the chain
                                 if (m) atomicAdd(&s_na, (uint32_t)__popc(m));
                             }
-                            if (e < DEC_CH) s_x[e] = 0;
+                            if (e < DEC_CH) sx[e] = 0;
                         }
                         __syncthreads();
                         // stage what the chain reads (all threads): the stream words the round can reach,
@@ -698,17 +743,21 @@ __global__ void __launch_bounds__(DEC_NT, META ? 1 : 2) spiht_decode_kernel(cons
                                 uint32_t x = __brev(br.word(gw));
                                 const uint64_t first = gw << 5;  // stream position of the word's first bit
                                 if (first + 32 > limit) x = first >= limit ? 0u : (x & ~(0xffffffffu >> (uint32_t)(limit - first)));
-                                s_sw[w] = x;
+                                ssw[w] = x;
                             }
                             __syncthreads();
                             for (uint32_t w = wid; w < npw; w += DEC_NW) {
                                 // lane l: record whose "1" is bit l (MSB-first) of word w; its child bits follow
-                                const uint32_t v = __funnelshift_lc(s_sw[w + 1], s_sw[w], lane + 1) >> 24;
+                                const uint32_t v = __funnelshift_lc(ssw[w + 1], ssw[w], lane + 1) >> 24;
                                 s_lp[w * 32 + lane] = s_len[v];
                             }
                         }
                         __syncthreads();
                         DEC_PROF_ADD(1);
+                    };
+                    auto walk_round = [&](uint32_t cnt, int buf) {
+                        uint8_t *sx = s_x2[buf];
+                        uint32_t *ssw = s_sw2[buf];
                         // ---- chain: one thread jumps from fired A set to fired A set
                         if (tid == 0) {
                             DEC_PROF_MARK(_tc);
@@ -726,9 +775,9 @@ __global__ void __launch_bounds__(DEC_NT, META ? 1 : 2) spiht_decode_kernel(cons
                             // of the stream window and the funnel shift wraps it), the entry index e is the
                             // shift of the set-type window, and both word rotations and the step without a
                             // fired set sit behind one rarely taken branch.
-                            const uint32_t wa = (uint32_t)__cvta_generic_to_shared(s_sw);
+                            const uint32_t wa = (uint32_t)__cvta_generic_to_shared(ssw);
                             const uint32_t wq = (uint32_t)__cvta_generic_to_shared(s_lp) + (uint32_t)(pos & 31);
-                            const uint32_t wx = (uint32_t)__cvta_generic_to_shared(s_x);
+                            const uint32_t wx = (uint32_t)__cvta_generic_to_shared(sx);
                             const uint32_t wt = (uint32_t)__cvta_generic_to_shared(s_tmask);
                             const uint32_t used = p.walk_variant == 0 ? lis_walk(wa, wq, wx, wt, cnt)
                                                                       : lis_walk_pa<8>(wa, wq, wx, wt, cnt);
@@ -742,43 +791,48 @@ __global__ void __launch_bounds__(DEC_NT, META ? 1 : 2) spiht_decode_kernel(cons
 #endif
                             DEC_PROF_CNT(11, 1);
                         }
-                        __syncthreads();
-                        const uint64_t p_base = pos;
-                        pos = s_chain_p;
+                    };
+                    auto apply_round = [&](auto pipe_c, uint32_t ebase, uint32_t cnt, uint64_t p_base, int buf) {
+                        constexpr bool PIPE = decltype(pipe_c)::value;
+                        constexpr int NT = PIPE ? DEC_NT - 32 : DEC_NT;
+                        const int tid = PIPE ? (int)threadIdx.x - 32 : (int)threadIdx.x;   // index among the threads at work here
+                        const uint8_t *sx = s_x2[buf];
+                        const uint32_t *ssw = s_sw2[buf];
+                        uint32_t *sgrp = s_grp2[buf];
                         // ---- prefix of the child lengths per 32 entries
                         {
                             uint32_t v = 0;
                             if ((uint32_t)tid < (cnt + 31) / 32) {
-                                const uint32_t *xw = reinterpret_cast<const uint32_t *>(s_x) + tid * 8;
+                                const uint32_t *xw = reinterpret_cast<const uint32_t *>(sx) + tid * 8;
 #pragma unroll
                                 for (int q = 0; q < 8; ++q) v += __dp4a(xw[q], 0x01010101u, 0u);
                             }
-                            static_assert(DEC_CH / 32 <= DEC_NT, "one thread per 32-entry group");
+                            static_assert(DEC_CH / 32 <= NT, "one thread per 32-entry group");
                             uint64_t tot;
-                            const uint64_t ex = block_exscan<DEC_NT>((uint64_t)v, s_wtot, tot);
-                            if (tid < DEC_CH / 32) s_grp[tid] = (uint32_t)ex;
+                            const uint64_t ex = dec_exscan<PIPE>((uint64_t)v, s_wtot, tot);
+                            if (tid < DEC_CH / 32) sgrp[tid] = (uint32_t)ex;
                         }
-                        __syncthreads();
+                        dec_sync<PIPE>();
                         DEC_PROF_MARK(_tb);
                         // ---- every entry: its own bit, then the fired sets' records
-                        for (uint32_t eb = 0; eb < cnt; eb += DEC_NT) {
+                        for (uint32_t eb = 0; eb < cnt; eb += NT) {
                             const uint32_t e = eb + tid;
                             const bool valid = e < cnt;
                             // bit position: entries before e take one bit each plus the child bits of fired A sets
-                            const uint32_t xe = valid ? s_x[e] : 0u;
+                            const uint32_t xe = valid ? sx[e] : 0u;
                             uint32_t inc = xe;
 #pragma unroll
                             for (int d = 1; d < 32; d <<= 1) {
                                 const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
                                 if (lane >= d) inc += t;
                             }
-                            const uint64_t pe = p_base + e + (valid ? s_grp[e >> 5] : 0u) + (inc - xe);
+                            const uint64_t pe = p_base + e + (valid ? sgrp[e >> 5] : 0u) + (inc - xe);
                             const bool avail = valid && pe < limit;
                             const uint32_t key = valid ? cur[ebase + e] : 0u;
                             // the entry's bit and the 32 after it, from the staged words (MSB-first; staged from the
                             // word of p_base on, so every bit the round can reach is there)
                             const uint32_t so = (uint32_t)(p_base & 31) + (uint32_t)(pe - p_base);
-                            const bool fired = avail && ((s_sw[so >> 5] << (so & 31)) >> 31);
+                            const bool fired = avail && ((ssw[so >> 5] << (so & 31)) >> 31);
                             uint32_t k = 0, i = 0, j = 0, ci = 0, cj = 0;
                             uint32_t nlsp = 0, nlip = 0, nnext = 0, sigmask = 0, sgnmask = 0, nread = 0;
                             uint32_t ndef = 0, defmask = 0;
@@ -794,7 +848,7 @@ __global__ void __launch_bounds__(DEC_NT, META ? 1 : 2) spiht_decode_kernel(cons
                                 const bool has = offspring_corner(i, j, H, W, ll_h, ll_w, ci, cj);
                                 if (isA) {
                                     uint64_t q = pe + 1;
-                                    uint32_t cbits = __brev(__funnelshift_l(s_sw[((so + 1) >> 5) + 1], s_sw[(so + 1) >> 5], so + 1));
+                                    uint32_t cbits = __brev(__funnelshift_l(ssw[((so + 1) >> 5) + 1], ssw[(so + 1) >> 5], so + 1));
                                     bool cut = false;
                                     if (has) {
 #pragma unroll
@@ -839,7 +893,7 @@ __global__ void __launch_bounds__(DEC_NT, META ? 1 : 2) spiht_decode_kernel(cons
                             const uint64_t pack = (uint64_t)nlsp | ((uint64_t)nlip << 12) | ((uint64_t)nnext << 24) |
                                                   ((uint64_t)ndef << 36) | ((uint64_t)(avail && !fired) << 48);
                             uint64_t tot;
-                            const uint64_t ex = block_exscan<DEC_NT>(pack, s_wtot, tot);
+                            const uint64_t ex = dec_exscan<PIPE>(pack, s_wtot, tot);
                             if (avail && !fired) R[rkeep + (uint32_t)(ex >> 48)] = key;
                             if (fired) {
                                 uint32_t os = lsp_len + (uint32_t)(ex & 0xfff);
@@ -873,14 +927,14 @@ __global__ void __launch_bounds__(DEC_NT, META ? 1 : 2) spiht_decode_kernel(cons
                             nxt_len += (uint32_t)((tot >> 24) & 0xfff);
                             rkeep += (uint32_t)(tot >> 48);
                             if (has_dups) {
-                                __syncthreads();
+                                dec_sync<PIPE>();
                                 if (tid == 0) apply_queue(s_dq, (uint32_t)((tot >> 36) & 0xfff), kf, rec, H, W, n);
-                                __syncthreads();
+                                dec_sync<PIPE>();
                             }
                         }
-                        __syncthreads();  // s_x / s_tmask / s_grp are rewritten by the next round
+                        dec_sync<PIPE>();  // s_x / s_tmask / s_grp are rewritten by the next round
                         DEC_PROF_SINCE(3, _tb);
-                        DEC_PROF_CNT(12, (cnt + DEC_NT - 1) / DEC_NT);
+                        DEC_PROF_CNT(12, (cnt + NT - 1) / NT);
 #ifdef SPIHTB_PROF
                         // how much of the parallel work could run under the next round's walk: rounds that are not
                         // the last of their generation (slot 13: their batch cycles; slot 14: min(batch cycles of
@@ -895,7 +949,58 @@ __global__ void __launch_bounds__(DEC_NT, META ? 1 : 2) spiht_decode_kernel(cons
                             prev_tb = tb_c;
                         }
 #endif
+                        if (PIPE && tid == 0) {
+                            s_cnt[0] = lsp_len;
+                            s_cnt[1] = lip_len;
+                            s_cnt[2] = nxt_len;
+                            s_cnt[3] = rkeep;
+                        }
+                    };
+                    bool pend = false;   // a walked round whose entries are not applied yet
+                    uint32_t pend_ebase = 0, pend_cnt = 0;
+                    uint64_t pend_pbase = 0;
+                    int buf = 0;
+                    for (uint32_t ebase = 0; ebase < cur_len && !ended; ebase += DEC_CH, buf ^= 1) {
+                        const uint32_t cnt = min((uint32_t)DEC_CH, cur_len - ebase);
+                        stage_round(ebase, cnt, buf);
+                        if constexpr (!META) {
+                            if (pipe) {
+                                if (tid < 32)
+                                    walk_round(cnt, buf);
+                                else if (pend)
+                                    apply_round(std::true_type{}, pend_ebase, pend_cnt, pend_pbase, buf ^ 1);
+                                __syncthreads();
+                                if (pend) {
+                                    lsp_len = s_cnt[0];
+                                    lip_len = s_cnt[1];
+                                    nxt_len = s_cnt[2];
+                                    rkeep = s_cnt[3];
+                                }
+                                pend = true;
+                                pend_ebase = ebase;
+                                pend_cnt = cnt;
+                                pend_pbase = pos;
+                                pos = s_chain_p;
+                                if (pos >= limit) ended = true;
+                                continue;
+                            }
+                        }
+                        walk_round(cnt, buf);
+                        __syncthreads();
+                        const uint64_t p_base = pos;
+                        pos = s_chain_p;
+                        apply_round(std::false_type{}, ebase, cnt, p_base, buf);
                         if (pos >= limit) ended = true;
+                    }
+                    if constexpr (!META) {
+                        if (pend) {   // the last walked round of the generation
+                            if (tid >= 32) apply_round(std::true_type{}, pend_ebase, pend_cnt, pend_pbase, buf ^ 1);
+                            __syncthreads();
+                            lsp_len = s_cnt[0];
+                            lip_len = s_cnt[1];
+                            nxt_len = s_cnt[2];
+                            rkeep = s_cnt[3];
+                        }
                     }
                     uint32_t *old = cur;
                     cur = nxt;
@@ -1034,6 +1139,8 @@ int launch_decode(spihtb_ctx *ctx, const DecArgs &a)
 
     k.walk_variant = 1;   // SPIHTB_WALK=0: the branchy loop (A-B measurements)
     if (const char *e = getenv("SPIHTB_WALK")) k.walk_variant = atoi(e);
+    k.pipe = 1;
+    if (const char *e = getenv("SPIHTB_DEC_PIPE")) k.pipe = atoi(e);
     int occ = 1;
     if (a.meta)
         SPIHTB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, spiht_decode_kernel<true>, DEC_NT, 0));
