@@ -50,6 +50,14 @@ constexpr int DEC_CH = 2048;           // LIS entries per chain round
 constexpr int DEC_PLW = DEC_CH * 9 / 32 + 8;  // staged stream words per round (an entry takes at most 9 bits)
 constexpr int DEC_SLACK = 8 * DEC_NT + 64;
 constexpr int DEC_DQ = 4 * DEC_NT;     // ordered write queue (odd LL sizes only)
+// pipelined rounds: warp 0 walks; the warps that share its scheduler (4, 8, 12: warp w issues on scheduler w % 4) stay
+// idle meanwhile, the other twelve apply the previous round (all fifteen: 3.97 ms per 256 images; twelve: 3.86).
+// Giving the walker of an SM's second CTA another scheduler was measured again in this form: 3.92 ms -- two walkers
+// on one scheduler disturb each other less than a walker and three warps of parallel work.
+constexpr int DEC_PIPE_NW = DEC_NW - DEC_NW / 4;
+constexpr int DEC_PIPE_NT = DEC_PIPE_NW * 32;
+__device__ __forceinline__ bool dec_pipe_worker(int wid) { return (wid & 3) != 0; }
+__device__ __forceinline__ int dec_pipe_wid(int wid) { return wid - 1 - (wid >> 2); }   // 1,2,3,5,6,7,... -> 0,1,2,3,4,5,...
 
 struct DecK {
     const uint32_t *in;
@@ -245,7 +253,7 @@ template <bool PIPE>
 __device__ __forceinline__ void dec_sync()
 {
     if (PIPE)
-        asm volatile("bar.sync 1, %0;" ::"n"(DEC_NT - 32) : "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(DEC_PIPE_NT) : "memory");
     else
         __syncthreads();
 }
@@ -253,8 +261,8 @@ template <bool PIPE>
 __device__ __forceinline__ uint64_t dec_exscan(uint64_t v, uint64_t *warp_tot, uint64_t &total)
 {
     if (!PIPE) return block_exscan<DEC_NT>(v, warp_tot, total);
-    constexpr int NW = DEC_NW - 1;
-    const int lane = threadIdx.x & 31, wid = (int)(threadIdx.x >> 5) - 1;
+    constexpr int NW = DEC_PIPE_NW;
+    const int lane = threadIdx.x & 31, wid = dec_pipe_wid((int)(threadIdx.x >> 5));
     uint64_t inc = v;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -695,8 +703,9 @@ __global__ void __launch_bounds__(DEC_NT, META ? 1 : 2) spiht_decode_kernel(cons
                     uint32_t nxt_len = 0;
                     // One round = up to DEC_CH entries of the generation: stage (all threads), walk (one thread), apply (parallel).
                     // Pipelined form (even LL sizes, no metadata table): the staged words, child lengths and group prefixes are
-                    // double-buffered, and while thread 0 walks round r warps 1..15 apply round r-1 behind a named barrier of
-                    // their own; the list counters they advance come back through shared memory.
+                    // double-buffered, and while thread 0 walks round r the twelve warps on the other three schedulers apply
+                    // round r-1 behind a named barrier of their own; the list counters they advance come back through
+                    // shared memory.
                     auto stage_round = [&](uint32_t ebase, uint32_t cnt, int buf) {
                         uint8_t *sx = s_x2[buf];
                         uint32_t *ssw = s_sw2[buf];
@@ -794,8 +803,9 @@ __global__ void __launch_bounds__(DEC_NT, META ? 1 : 2) spiht_decode_kernel(cons
                     };
                     auto apply_round = [&](auto pipe_c, uint32_t ebase, uint32_t cnt, uint64_t p_base, int buf) {
                         constexpr bool PIPE = decltype(pipe_c)::value;
-                        constexpr int NT = PIPE ? DEC_NT - 32 : DEC_NT;
-                        const int tid = PIPE ? (int)threadIdx.x - 32 : (int)threadIdx.x;   // index among the threads at work here
+                        constexpr int NT = PIPE ? DEC_PIPE_NT : DEC_NT;
+                        // index among the threads at work here
+                        const int tid = PIPE ? dec_pipe_wid((int)(threadIdx.x >> 5)) * 32 + (int)(threadIdx.x & 31) : (int)threadIdx.x;
                         const uint8_t *sx = s_x2[buf];
                         const uint32_t *ssw = s_sw2[buf];
                         uint32_t *sgrp = s_grp2[buf];
@@ -967,7 +977,7 @@ __global__ void __launch_bounds__(DEC_NT, META ? 1 : 2) spiht_decode_kernel(cons
                             if (pipe) {
                                 if (tid < 32)
                                     walk_round(cnt, buf);
-                                else if (pend)
+                                else if (pend && dec_pipe_worker(wid))
                                     apply_round(std::true_type{}, pend_ebase, pend_cnt, pend_pbase, buf ^ 1);
                                 __syncthreads();
                                 if (pend) {
@@ -994,7 +1004,7 @@ __global__ void __launch_bounds__(DEC_NT, META ? 1 : 2) spiht_decode_kernel(cons
                     }
                     if constexpr (!META) {
                         if (pend) {   // the last walked round of the generation
-                            if (tid >= 32) apply_round(std::true_type{}, pend_ebase, pend_cnt, pend_pbase, buf ^ 1);
+                            if (dec_pipe_worker(wid)) apply_round(std::true_type{}, pend_ebase, pend_cnt, pend_pbase, buf ^ 1);
                             __syncthreads();
                             lsp_len = s_cnt[0];
                             lip_len = s_cnt[1];
