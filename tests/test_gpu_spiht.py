@@ -327,3 +327,44 @@ def test_cluster_coder_matches_oracle(rs, oracle, monkeypatch, cl):
         want, want_n, want_bits = oracle.encode_nbits(xb[b], 4, 6, int(budgets[b]))
         assert (int(nbits[b]), int(max_n[b])) == (want_bits, want_n), b
         assert_stream_equal(streams[b, :(want_bits + 7) // 8].tobytes(), want, f"cluster {cl} image {b}")
+
+
+def test_decoder_pipelined_rounds_and_walk_variants(rs, oracle, monkeypatch):
+    """the decoder's LIS rounds run pipelined (warps apply round r-1 on a named barrier while one thread walks round
+    r) with the branch-free walk; SPIHTB_DEC_PIPE=0 / SPIHTB_WALK=0 select the serial order and the round-1 loop.
+    All combinations must decode every prefix to the oracle's array: lists several rounds (2048 entries) long per
+    generation, prefixes that end inside a walk, inside an apply, inside the first and the last round of a
+    generation, one-byte and empty streams, a batch with per-image lengths"""
+    import torch
+    from spiht_b200 import batch
+    rng = np.random.default_rng(77)
+    c, h, w, llh, llw = 3, 264, 392, 8, 12            # even LL: the pipelined path
+    x = (rng.laplace(0, 9, (c, h, w)) * (1 + 30 * (rng.random((c, h, w)) < 0.02))).astype(np.int32)
+    data, n = rs.encode(x, llh, llw, 0)               # untruncated: ~1.5 Mbit, generations of tens of thousands of entries
+    assert len(data) > 100000
+    lengths = [0, 1, 2, 7, 100, 4099, 20000, 65537, 100003, len(data) // 2, len(data) - 1, len(data)]
+    lengths += [int(v) for v in rng.integers(1000, len(data), 12)]
+    want = {L: oracle.decode(data[:L], n, c, h, w, llh, llw) for L in lengths}
+    for pipe, walk in [("1", "1"), ("0", "1"), ("1", "0"), ("0", "0")]:
+        monkeypatch.setenv("SPIHTB_DEC_PIPE", pipe)
+        monkeypatch.setenv("SPIHTB_WALK", walk)
+        for L in lengths:
+            got = rs.decode(data[:L], n, c, h, w, llh, llw)
+            assert np.array_equal(got, want[L]), (pipe, walk, L, int((got != want[L]).sum()))
+    monkeypatch.delenv("SPIHTB_DEC_PIPE")
+    monkeypatch.delenv("SPIHTB_WALK")
+    # a batch: one row per prefix, more rows than CTAs fit on the device at once would need > 296 rows; 24 rows with
+    # their own lengths check the per-image state (pending round, counters handed back through shared memory)
+    B = len(lengths)
+    stride = (len(data) + 15) // 8 * 8
+    rows = np.zeros((B, stride), np.uint8)
+    for r, L in enumerate(lengths):
+        rows[r, :L] = np.frombuffer(data[:L], np.uint8)
+    rec = batch.decode_coeffs(torch.from_numpy(rows).cuda(), torch.tensor(lengths, dtype=torch.int64),
+                              torch.full((B,), n, dtype=torch.int32), c, h, w, llh, llw).cpu().numpy()
+    for r, L in enumerate(lengths):
+        assert np.array_equal(rec[r], want[L]), (r, L)
+    # repeated runs are bit-identical (a race between the walker and the applying warps would not be)
+    rec2 = batch.decode_coeffs(torch.from_numpy(rows).cuda(), torch.tensor(lengths, dtype=torch.int64),
+                               torch.full((B,), n, dtype=torch.int32), c, h, w, llh, llw).cpu().numpy()
+    assert np.array_equal(rec, rec2)
