@@ -448,8 +448,10 @@ def run_b200(args):
         dec_pix = torch.empty((B, C, g.rec_h, g.rec_w), dtype=torch.float32, device=dev)
 
         def dstep():
+            # pixels are the product: the coefficient array is scratch (SPIHTB_OPT_SCRATCH_COEFFS), as in
+            # spiht_b200.decode_images
             return batch.decode_images(streams, nbytes, max_n, C, g, settings, dtype=torch.float32, coeffs=coeffs,
-                                       out=dec_pix)
+                                       out=dec_pix, scratch_coeffs=True)
         for _ in range(max(args.warmup, 3)):
             dstep()
         barrier()
@@ -675,7 +677,8 @@ def run_b200_mixed(args, c, rank, world, local_rank, dev, dist, numa):
 
             def dec_step(outs):
                 for (s, n, px, g), (mb, stride, co, out, rec), o in zip(plans, bufs, outs):
-                    batch.decode_images(o[0], (o[1] + 7) // 8, o[2], 3, g, st, dtype=torch.float32, coeffs=co, out=rec)
+                    batch.decode_images(o[0], (o[1] + 7) // 8, o[2], 3, g, st, dtype=torch.float32, coeffs=co, out=rec,
+                                        scratch_coeffs=True)
 
             for _ in range(max(args.warmup, 3)):
                 outs = enc_step()

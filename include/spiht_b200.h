@@ -93,6 +93,14 @@ int spihtb_sync(spihtb_ctx *ctx);
 /* number of kernels this context has launched so far (bench.py `gpu_launches`) */
 int64_t spihtb_launch_count(spihtb_ctx *ctx);
 
+/* Context options.
+ * SPIHTB_OPT_SCRATCH_COEFFS (default 0): when non-zero, the caller promises not to read the coefficient array
+ * spihtb_decode_images fills (`dev_coeffs_scratch`): the library then zeroes the finest detail bands of an image --
+ * three quarters of the array -- only if the image's stream reaches them, and leaves them undefined otherwise (the
+ * inverse transform does not read them).  The pixels are identical either way. */
+#define SPIHTB_OPT_SCRATCH_COEFFS 1
+int spihtb_set_option(spihtb_ctx *ctx, int32_t option, int64_t value);
+
 /* which forward-transform path the last spihtb_forward / spihtb_encode_images call on this context took:
  * 12 = levels 1 and 2 fused in one kernel (TMA-staged tiles, dwt_fwd2.cu), 1 = one kernel per level.  bench.py
  * uses it to credit the dominant kernel with the right algorithmic bytes. */

@@ -43,12 +43,15 @@ _lib = None
 _lock = threading.Lock()
 
 # every symbol include/spiht_b200.h declares
+OPT_SCRATCH_COEFFS = 1
+
 EXPORTS = (
     "spihtb_version", "spihtb_last_error", "spihtb_create", "spihtb_destroy", "spihtb_set_stream",
     "spihtb_sync", "spihtb_launch_count", "spihtb_plan", "spihtb_encode", "spihtb_decode",
     "spihtb_encode_coeffs", "spihtb_decode_coeffs", "spihtb_forward", "spihtb_inverse",
     "spihtb_encode_images", "spihtb_decode_images", "spihtb_stream_bound",
     "spihtb_profile_enable", "spihtb_profile_read", "spihtb_max_abs", "spihtb_convert_color", "spihtb_forward_path", "spihtb_decode_with_metadata",
+    "spihtb_set_option",
 )
 
 
@@ -96,6 +99,7 @@ def lib():
         L.spihtb_stream_bound.restype = u64
         L.spihtb_profile_enable.argtypes = [vp, ctypes.c_int]
         L.spihtb_profile_read.argtypes = [vp, P(dbl), P(ctypes.c_int64), ctypes.c_int]
+        L.spihtb_set_option.argtypes = [vp, i32, ctypes.c_int64]
         for name in EXPORTS:
             getattr(L, name)   # every declared symbol must resolve
         _lib = L
@@ -139,6 +143,9 @@ class Context:
 
     def launch_count(self):
         return int(lib().spihtb_launch_count(self._h))
+
+    def set_option(self, option, value):
+        check(lib().spihtb_set_option(self._h, int(option), int(value)))
 
     def forward_path(self):
         """12 when the last forward transform ran levels 1+2 in the fused TMA kernel, else 1"""

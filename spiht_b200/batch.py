@@ -177,8 +177,13 @@ def encode_images(pixels, geom, settings, max_bits, out_stride=None, coeffs=None
     return out, nbits, max_n, status, coeffs
 
 
-def decode_images(streams, nbytes, max_n, C, geom, settings, dtype=torch.float64, coeffs=None, out=None):
-    """spihtb_decode_images -> (pixels [B,C,rec_h,rec_w], coeffs)"""
+def decode_images(streams, nbytes, max_n, C, geom, settings, dtype=torch.float64, coeffs=None, out=None,
+                  scratch_coeffs=False):
+    """spihtb_decode_images -> (pixels [B,C,rec_h,rec_w], coeffs).
+
+    scratch_coeffs=True (SPIHTB_OPT_SCRATCH_COEFFS): the caller does not read `coeffs`; the finest detail bands of an
+    image are then zeroed only if its stream reaches them (undefined otherwise) and None is returned in their place.
+    The pixels are the same either way."""
     _check_cuda(streams, "streams")
     B, stride = streams.shape
     if stride % 8:
@@ -191,7 +196,12 @@ def decode_images(streams, nbytes, max_n, C, geom, settings, dtype=torch.float64
         coeffs = torch.empty((B, C, geom.enc_h, geom.enc_w), dtype=torch.int32, device=streams.device)
     if out is None:
         out = torch.empty((B, C, geom.rec_h, geom.rec_w), dtype=dtype, device=streams.device)
-    _lib.check(_lib.lib().spihtb_decode_images(ctx.handle, _ptr(streams), stride, _ptr(nbytes), _ptr(max_n), B, C,
-                                               ctypes.byref(geom), color_id, sc, q, _ptr(coeffs), _ptr(out),
-                                               _pixel_dtype(out)))
-    return out, coeffs
+    ctx.set_option(_lib.OPT_SCRATCH_COEFFS, 1 if scratch_coeffs else 0)
+    try:
+        _lib.check(_lib.lib().spihtb_decode_images(ctx.handle, _ptr(streams), stride, _ptr(nbytes), _ptr(max_n), B, C,
+                                                   ctypes.byref(geom), color_id, sc, q, _ptr(coeffs), _ptr(out),
+                                                   _pixel_dtype(out)))
+    finally:
+        if scratch_coeffs:
+            ctx.set_option(_lib.OPT_SCRATCH_COEFFS, 0)
+    return out, (None if scratch_coeffs else coeffs)

@@ -6,6 +6,8 @@
 
 #include <algorithm>
 
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.cuh"
 #include "wavelets.cuh"
@@ -197,6 +199,18 @@ int spihtb_profile_enable(spihtb_ctx *ctx, int enable)
     ctx->profiling = enable != 0;
     for (int i = 0; i < ctx->nsubs; ++i) ctx->subs[i]->profiling = ctx->profiling;
     return SPIHTB_OK;
+}
+
+int spihtb_set_option(spihtb_ctx *ctx, int32_t option, int64_t value)
+{
+    if (!ctx) {
+        set_error("ctx is null");
+        return SPIHTB_EINVAL;
+    }
+    switch (option) {
+        case SPIHTB_OPT_SCRATCH_COEFFS: ctx->scratch_coeffs = value != 0; return SPIHTB_OK;
+        default: set_error("unknown option %d", (int)option); return SPIHTB_EINVAL;
+    }
 }
 
 int spihtb_profile_read(spihtb_ctx *ctx, double *ms_out, int64_t *count_out, int reset)
@@ -861,9 +875,9 @@ int spihtb_decode_images(spihtb_ctx *ctx, const uint8_t *dev_in, uint64_t in_str
     // the decoder marks the 64x64 blocks of the array it writes into; the inverse transform skips the detail
     // bands of tasks with no marked block (at low rates the finest levels hold no coefficient at all)
     const size_t nblk = (size_t)B * C * ((h + 63) / 64) * ((w + 63) / 64);
-    rc = ctx->ensure(ctx->blk, nblk + 256);
+    rc = ctx->ensure(ctx->blk, 2 * nblk + 256);
     if (rc) return rc;
-    SPIHTB_CUDA_CHECK(cudaMemsetAsync(ctx->blk.p, 0, nblk, ctx->stream));
+    SPIHTB_CUDA_CHECK(cudaMemsetAsync(ctx->blk.p, 0, 2 * nblk, ctx->stream));
     DecArgs a;
     a.in = dev_in;
     a.in_stride = in_stride;
@@ -872,9 +886,17 @@ int spihtb_decode_images(spihtb_ctx *ctx, const uint8_t *dev_in, uint64_t in_str
     a.B = B; a.C = c; a.H = h; a.W = w; a.ll_h = geom->ll_h; a.ll_w = geom->ll_w;
     a.out = dev_coeffs_scratch;
     a.blk = static_cast<uint8_t *>(ctx->blk.p);
+    // marks of the finest level alone (its bands start at row off_h[0] / column off_w[0] of the array)
+    a.blk1 = a.blk + nblk;
+    a.fine_h0 = geom->off_h[0];
+    a.fine_w0 = geom->off_w[0];
+    // SPIHTB_OPT_SCRATCH_COEFFS: the caller does not read the coefficient array, so the finest detail bands (three
+    // quarters of it) are zeroed only for the images whose streams reach them
+    a.lazy_zero = ctx->scratch_coeffs && !((geom->ll_h | geom->ll_w) & 1) && getenv("SPIHTB_NO_LAZY_ZERO") == nullptr;
     rc = launch_decode(ctx, a);
     if (rc) return rc;
     x.blk = a.blk;
+    x.blk1 = a.blk1;
     return launch_inverse(ctx, dev_coeffs_scratch, x, dev_pixels_out);
 }
 

@@ -75,6 +75,7 @@ struct spihtb_ctx {
     std::vector<int32_t> fix_host;  // their host copy: [key (32 ints)] [nrect, total] [rects] [prefix]
     std::vector<uint8_t> host_out;  // spihtb_encode result
     bool profiling = false;
+    bool scratch_coeffs = false;  // SPIHTB_OPT_SCRATCH_COEFFS
     bool last_forward_fused12 = false;  // the last forward transform ran levels 1+2 in the fused TMA kernel
     spihtb::StageProf prof[SPIHTB_NSTAGES];
     int ensure(spihtb::DevBuf &b, size_t bytes);

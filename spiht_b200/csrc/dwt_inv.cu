@@ -356,7 +356,7 @@ int launch_inverse(spihtb_ctx *ctx, const int32_t *coeffs, const XformArgs &x, v
         k.C = x.C;
         for (int c = 0; c < 8; ++c) k.rscale[c] = 1.0 / x.scale[c];
         k.rq = 1.0 / x.q;
-        k.blk = x.blk;
+        k.blk = (l == 0 && x.blk1) ? x.blk1 : x.blk;
         k.BH = (g.enc_h + 63) / 64;
         k.BW = (g.enc_w + 63) / 64;
         bool out_f32 = false;

@@ -64,6 +64,14 @@ struct DecArgs {
     int level = 0, top_ei = 1, top_ej = 1;
     const int32_t *slices = nullptr;
     int32_t *meta_err = nullptr;
+    // optional second set of block marks, same shape as blk: only coefficients in the finest detail bands (row >=
+    // fine_h0 or column >= fine_w0, the offsets of those bands in the array) mark it.  The level-1 inverse uses these:
+    // a block on the edge of the finest bands is otherwise marked by coarser coefficients too.
+    uint8_t *blk1 = nullptr;
+    int fine_h0 = 0, fine_w0 = 0;
+    // lazy zero fill (needs blk1): only the corner above / left of the finest bands is zeroed before the launch; an
+    // image zeroes its finest bands itself when its stream first reaches them (see DecK)
+    bool lazy_zero = false;
 };
 int launch_decode(spihtb_ctx *ctx, const DecArgs &a);
 
@@ -76,6 +84,7 @@ struct XformArgs {
     double q;
     int pixel_dtype;
     const uint8_t *blk = nullptr;  // inverse only: block marks of the coefficient array (see DecArgs), or null
+    const uint8_t *blk1 = nullptr; // inverse only: the marks the finest level uses instead (see DecArgs), or null
 };
 // Pyramid base pass fused into the forward transform: dp planes [B*C][enc_h/2][enc_w/2] and maxabs [B]
 // are complete when launch_forward returns (stream order).

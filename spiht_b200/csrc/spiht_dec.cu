@@ -82,6 +82,17 @@ struct DecK {
     int32_t *meta_err;         // set to 1 when the reference would have panicked (slice index out of range)
     int walk_variant;
     int pipe;   // apply round r-1 under the walk of round r
+    // lazy zero fill (spihtb_decode_images with the scratch-coefficients option): the launcher zeroes only the
+    // top-left fine_h0 x fine_w0 corner of every plane (everything but the finest detail bands); an image's CTA zeroes
+    // the rest of its planes itself the first time it meets a coefficient there.
+    // fine_h0 == 0: the whole array was zeroed by the launcher.
+    // fine_h0 / fine_w0 are even (a 2x2 child block never straddles them); fine_ht / fine_wt are the rows / columns
+    // where the finest bands really start (at most one less).  The image zeroes its finest bands when a child block
+    // lies past fine_h0 / fine_w0, or when any coefficient at or past fine_ht / fine_wt becomes significant -- so an
+    // image with unzeroed finest bands has no non-zero coefficient there at all, marks nothing in blk1, and the level-1 inverse
+    // never reads them.
+    int fine_h0, fine_w0, fine_ht, fine_wt;
+    uint8_t *blk1;   // marks of the finest bands alone (coefficients at or past fine_ht / fine_wt), or null
 };
 
 // ---- decode_with_metadata helpers ----------------------------------------------------------------------
@@ -449,7 +460,7 @@ __global__ void __launch_bounds__(DEC_NT, META ? 1 : 2) spiht_decode_kernel(cons
     __shared__ uint32_t s_tmask[DEC_CH / 32 + 4];  // A sets with offspring (a fired record carries child bits)
     __shared__ __align__(16) uint8_t s_x2[2][DEC_CH];           // child-bit length of fired A sets, 0 elsewhere (double-buffered)
     __shared__ uint32_t s_grp2[2][DEC_CH / 32];    // exclusive prefix of s_x per 32 entries
-    __shared__ uint32_t s_cnt[4];                  // list counters handed back by the applying warps
+    __shared__ uint32_t s_cnt[5];                  // list counters (and the lazy-zero flag) handed back by the applying warps
     __shared__ uint64_t s_wtot[DEC_NW];
     __shared__ uint32_t s_wfn[DEC_NW];
     __shared__ uint64_t s_chain_p;
@@ -534,6 +545,19 @@ __global__ void __launch_bounds__(DEC_NT, META ? 1 : 2) spiht_decode_kernel(cons
         __syncthreads();
 
         uint64_t pos = 0;  // uniform: next unread bit
+        uint32_t fine_done = p.fine_h0 == 0 ? 1u : 0u;   // uniform: the finest detail bands of this image are zeroed
+        // zero them: rows below fine_h0 whole, rows above it from column fine_w0 on (t: index of the calling thread among
+        // the nt that call)
+        auto zero_fine = [&](int t, int nt) {
+            const uint32_t fh = (uint32_t)p.fine_h0, fw = (uint32_t)p.fine_w0;
+            for (uint32_t kk = 0; kk < C; ++kk) {
+                int32_t *pl = rec + (size_t)kk * H * W;
+                const size_t lo = (size_t)fh * W, hi = (size_t)H * W;
+                for (size_t q = lo + t; q < hi; q += nt) pl[q] = 0;
+                for (uint32_t r = (uint32_t)t >> 5; r < fh; r += nt / 32)
+                    for (uint32_t cc = fw + (t & 31); cc < W; cc += 32) pl[(size_t)r * W + cc] = 0;
+            }
+        };
         DEC_PROF_MARK(_timg);
 #ifdef SPIHTB_PROF
         unsigned long long walk_cycles = 0, last_walk = 0, prev_tb = 0;
@@ -888,6 +912,9 @@ __global__ void __launch_bounds__(DEC_NT, META ? 1 : 2) spiht_decode_kernel(cons
                                         }
                                     }
                                     if (!cut && has_desc_past_offspring(i, j, H, W)) nnext = 1;
+                                    // lazy zero fill: a record with a child in the finest detail bands (the field of the
+                                    // ordered-write count is free: odd LL sizes never run lazily)
+                                    if (!fine_done && nread && (ci >= (uint32_t)p.fine_h0 || cj >= (uint32_t)p.fine_w0)) ndef = 1;
                                     if (has_dups && nlsp) {
                                         for (uint32_t c4 = 0; c4 < nread; ++c4)
                                             if ((sigmask & (1u << c4)) &&
@@ -904,6 +931,13 @@ __global__ void __launch_bounds__(DEC_NT, META ? 1 : 2) spiht_decode_kernel(cons
                                                   ((uint64_t)ndef << 36) | ((uint64_t)(avail && !fired) << 48);
                             uint64_t tot;
                             const uint64_t ex = dec_exscan<PIPE>(pack, s_wtot, tot);
+                            if (!fine_done && ((tot >> 36) & 0xfff)) {
+                                // first coefficient of the image in the finest bands: zero them, all threads at work
+                                // here, then go on
+                                zero_fine(tid, NT);
+                                dec_sync<PIPE>();
+                                fine_done = 1;
+                            }
                             if (avail && !fired) R[rkeep + (uint32_t)(ex >> 48)] = key;
                             if (fired) {
                                 uint32_t os = lsp_len + (uint32_t)(ex & 0xfff);
@@ -964,6 +998,7 @@ __global__ void __launch_bounds__(DEC_NT, META ? 1 : 2) spiht_decode_kernel(cons
                             s_cnt[1] = lip_len;
                             s_cnt[2] = nxt_len;
                             s_cnt[3] = rkeep;
+                            s_cnt[4] = fine_done;
                         }
                     };
                     bool pend = false;   // a walked round whose entries are not applied yet
@@ -985,6 +1020,7 @@ __global__ void __launch_bounds__(DEC_NT, META ? 1 : 2) spiht_decode_kernel(cons
                                     lip_len = s_cnt[1];
                                     nxt_len = s_cnt[2];
                                     rkeep = s_cnt[3];
+                                    fine_done = s_cnt[4];
                                 }
                                 pend = true;
                                 pend_ebase = ebase;
@@ -1010,6 +1046,7 @@ __global__ void __launch_bounds__(DEC_NT, META ? 1 : 2) spiht_decode_kernel(cons
                             lip_len = s_cnt[1];
                             nxt_len = s_cnt[2];
                             rkeep = s_cnt[3];
+                            fine_done = s_cnt[4];
                         }
                     }
                     uint32_t *old = cur;
@@ -1068,6 +1105,7 @@ __global__ void __launch_bounds__(DEC_NT, META ? 1 : 2) spiht_decode_kernel(cons
         if (p.blk) {
             uint8_t *blkb = p.blk + (size_t)b * C * p.BH * p.BW;
             constexpr int MU = 8;  // keys in flight per thread (the loop is pure load latency otherwise)
+            int late = 0;          // a coefficient on the first row / column of the finest bands (inside the zeroed corner)
             for (uint32_t e0 = tid; e0 < lsp_len; e0 += DEC_NT * MU) {
                 uint32_t key[MU];
 #pragma unroll
@@ -1078,9 +1116,17 @@ __global__ void __launch_bounds__(DEC_NT, META ? 1 : 2) spiht_decode_kernel(cons
                         uint32_t k, i, j;
                         key_unpack(kf, key[u], k, i, j);
                         blkb[((size_t)k * p.BH + (i >> 6)) * p.BW + (j >> 6)] = 1;
+                        if (p.blk1 && (i >= (uint32_t)p.fine_ht || j >= (uint32_t)p.fine_wt)) {
+                            p.blk1[(((size_t)b * C + k) * p.BH + (i >> 6)) * p.BW + (j >> 6)] = 1;
+                            late = 1;
+                        }
                     }
                 }
             }
+            // lazy zero fill: the image never read a child past the zeroed corner, but a coefficient on the first row or
+            // column of the finest bands (inside the corner) is non-zero, so the level-1 inverse will read those bands:
+            // zero them now (nothing was ever written there)
+            if (!fine_done && __syncthreads_or(late)) zero_fine(tid, DEC_NT);
         }
         DEC_PROF_SINCE(5, _timg);
 #ifdef SPIHTB_PROF
@@ -1112,6 +1158,26 @@ extern "C" int spihtb_debug_dec_prof(unsigned long long *out16)
     return SPIHTB_OK;
 }
 #endif
+
+// zero the top-left h0 x w0 corner of every plane (lazy zero fill: everything but the finest detail bands).  A CTA
+// takes every gridDim.x-th group of eight rows of one plane (one warp per row); planes in grid.y (strided when there are
+// more than 65535).
+__global__ void __launch_bounds__(256) zero_corner_kernel(int32_t *out, int nplanes, int H, int W, int h0, int w0)
+{
+    const int lane = threadIdx.x & 31;
+    for (int z = blockIdx.y; z < nplanes; z += gridDim.y) {
+        for (int row = blockIdx.x * 8 + (threadIdx.x >> 5); row < h0; row += gridDim.x * 8) {
+            int32_t *r = out + ((size_t)z * H + row) * W;
+            // 16-byte stores over the aligned middle of the row segment, scalar stores at its ends
+            const int head = (int)(((16u - (uint32_t)((uintptr_t)r & 15u)) & 15u) >> 2);
+            const int a0 = min(head, w0), nq = (w0 - a0) >> 2, a1 = a0 + 4 * nq;
+            if (lane < a0) r[lane] = 0;
+            int4 *q = reinterpret_cast<int4 *>(r + a0);
+            for (int t = lane; t < nq; t += 32) q[t] = make_int4(0, 0, 0, 0);
+            if (a1 + lane < w0) r[a1 + lane] = 0;
+        }
+    }
+}
 
 int launch_decode(spihtb_ctx *ctx, const DecArgs &a)
 {
@@ -1181,7 +1247,25 @@ int launch_decode(spihtb_ctx *ctx, const DecArgs &a)
     ctx->stage_begin(5);
     // (zeroing each image's array inside the kernel, under the first passes, was measured slower than this memset:
     // 5.56 against 5.41 ms per 256 images -- one CTA cannot issue 13 MB of stores as fast as the copy engine path)
-    SPIHTB_CUDA_CHECK(cudaMemsetAsync(a.out, 0, sizeof(int32_t) * (size_t)a.B * a.C * a.H * a.W, ctx->stream));
+    k.fine_h0 = k.fine_w0 = 0;
+    k.fine_ht = a.fine_h0;
+    k.fine_wt = a.fine_w0;
+    k.blk1 = a.blk1;
+    if (a.lazy_zero && a.blk1 && a.fine_h0 > 0 && a.fine_w0 > 0 && a.fine_h0 < a.H && a.fine_w0 < a.W && !a.meta &&
+        !((a.ll_h | a.ll_w) & 1)) {
+        // lazy: only the corner that holds everything but the finest detail bands; an image that reaches those bands
+        // zeroes them itself (spiht_decode_kernel)
+        k.fine_h0 = std::min(a.H, (a.fine_h0 + 1) & ~1);
+        k.fine_w0 = std::min(a.W, (a.fine_w0 + 1) & ~1);
+        // (cudaMemset3DAsync over 768 planes of 539-column rows took 3 ms; this kernel runs at memory speed)
+        {
+            const dim3 grid((unsigned)std::max(1, std::min(8, (k.fine_h0 + 63) / 64)), (unsigned)std::min<long long>((long long)a.B * a.C, 65535));
+            zero_corner_kernel<<<grid, 256, 0, ctx->stream>>>(a.out, a.B * a.C, a.H, a.W, k.fine_h0, k.fine_w0);
+            ctx->launches++;
+        }
+    } else {
+        SPIHTB_CUDA_CHECK(cudaMemsetAsync(a.out, 0, sizeof(int32_t) * (size_t)a.B * a.C * a.H * a.W, ctx->stream));
+    }
     SPIHTB_CUDA_CHECK(cudaMemsetAsync(k.counter, 0, sizeof(unsigned int), ctx->stream));
     if (a.meta)
         spiht_decode_kernel<true><<<slots, DEC_NT, 0, ctx->stream>>>(k);

@@ -280,7 +280,8 @@ def decode_images(encoding_results: Sequence[EncodingResult], spiht_settings: Sp
         streams = torch.from_numpy(host).cuda()
         nbytes = torch.from_numpy(lens).cuda()
         max_n = torch.tensor([e.max_n for e in ers], dtype=torch.int32).cuda()
-        pix, _ = batch.decode_images(streams, nbytes, max_n, c, g, spiht_settings, dtype=torch.float64)
+        pix, _ = batch.decode_images(streams, nbytes, max_n, c, g, spiht_settings, dtype=torch.float64,
+                                     scratch_coeffs=True)   # only the pixels leave this function
         pix = pix.cpu().numpy() if as_numpy else pix
         for r, i in enumerate(idxs):
             out[i] = pix[r]

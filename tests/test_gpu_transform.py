@@ -322,3 +322,51 @@ def test_color_convert_matches_oracle_to_a_few_ulp(torch_cuda):
     assert np.abs(convert(f32, "rgb", "ipt") - ipt_ref.convert(f32.astype(np.float64), "RGB", "IPT")).max() < 4e-15
     with pytest.raises(ValueError):
         convert(rgb, "RGB", "CIE Lab")
+
+
+@pytest.mark.parametrize("shape,kw", [
+    ((3, 256, 384), dict()),
+    ((1, 301, 263), dict()),
+    ((3, 256, 256), dict(mode="periodization")),
+    ((2, 200, 328), dict(wavelet="bior4.4", mode="symmetric")),
+    ((1, 320, 333), dict(wavelet="bior6.8")),
+    ((3, 1024, 1024), dict()),
+])
+def test_decode_images_scratch_coefficients_same_pixels(torch_cuda, shape, kw):
+    """SPIHTB_OPT_SCRATCH_COEFFS (the caller does not read the coefficient array): the finest detail bands of an image
+    are zeroed only if its stream reaches them.  One batch holds streams that never reach them (a few hundred bytes),
+    streams that reach them late and untruncated streams; the scratch array is filled with a poison value first, so a
+    transform that read a cell nobody defined could not give the pixels of the plain call.  Bit-identical pixels."""
+    import spiht_b200 as spiht
+    from spiht_b200 import _lib, batch
+    torch = torch_cuda
+    c, h, w = shape
+    B = 6
+    px = torch.from_numpy(np.stack([synth_image(c, h, w, 60 + s) for s in range(B)])).cuda()
+    st = spiht.SpihtSettings(**kw)
+    g = _lib.plan(h, w, kw.get("wavelet", "bior2.2"), kw.get("mode", "reflect"), None)
+    if (g.ll_h | g.ll_w) & 1:
+        pytest.skip("odd LL band: the option is ignored")
+    s, nbits, max_n, _, _ = batch.encode_images(px, g, st, 0)          # untruncated
+    full_bytes = (nbits + 7) // 8
+    # per-image prefixes: tiny, small, medium, 60 %, all but one byte, everything
+    frac = torch.tensor([0.0005, 0.004, 0.05, 0.6, 1.0, 1.0], device="cuda")
+    nbytes = torch.clamp((full_bytes.double() * frac).long(), min=1)
+    nbytes[4] = full_bytes[4] - 1
+    plain, coeffs = batch.decode_images(s, nbytes, max_n, c, g, st, dtype=torch.float64)
+    poison = torch.full((B, c, g.enc_h, g.enc_w), 0x7f7f7f7f, dtype=torch.int32, device="cuda")
+    lazy, none = batch.decode_images(s, nbytes, max_n, c, g, st, dtype=torch.float64, coeffs=poison, scratch_coeffs=True)
+    assert none is None
+    assert torch.equal(lazy, plain)
+    # where the array is defined it holds the decoded coefficients: the corner that is always zeroed ...
+    fh, fw = g.off_h[0], g.off_w[0]
+    assert torch.equal(poison[:, :, :fh, :fw], coeffs[:, :, :fh, :fw])
+    # ... and all of it for the images that reached the finest bands (the untruncated ones certainly did)
+    assert torch.equal(poison[5], coeffs[5])
+    untouched = [b for b in range(B) if int((coeffs[b, :, fh:, :] != 0).sum() + (coeffs[b, :, :fh, fw:] != 0).sum()) == 0]
+    assert 0 in untouched, "the shortest prefix should not reach the finest bands"
+    # float32 output path as well
+    lazy32, _ = batch.decode_images(s, nbytes, max_n, c, g, st, dtype=torch.float32, coeffs=poison.fill_(0x7f7f7f7f),
+                                    scratch_coeffs=True)
+    plain32, _ = batch.decode_images(s, nbytes, max_n, c, g, st, dtype=torch.float32)
+    assert torch.equal(lazy32, plain32)
