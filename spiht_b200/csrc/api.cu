@@ -892,7 +892,12 @@ int spihtb_decode_images(spihtb_ctx *ctx, const uint8_t *dev_in, uint64_t in_str
     a.fine_w0 = geom->off_w[0];
     // SPIHTB_OPT_SCRATCH_COEFFS: the caller does not read the coefficient array, so the finest detail bands (three
     // quarters of it) are zeroed only for the images whose streams reach them
-    a.lazy_zero = ctx->scratch_coeffs && !((geom->ll_h | geom->ll_w) & 1) && getenv("SPIHTB_NO_LAZY_ZERO") == nullptr;
+    // Worth it only where streams rarely reach those bands: an image that does must zero them with one CTA, which is
+    // far slower than the memset it replaces.  The row stride bounds the rate: lazy up to 0.75 bit per pixel.
+    // (SPIHTB_LAZY_ZERO=1 / SPIHTB_NO_LAZY_ZERO=1 force it on / off: tests and A-B runs)
+    a.lazy_zero = ctx->scratch_coeffs && !((geom->ll_h | geom->ll_w) & 1) && getenv("SPIHTB_NO_LAZY_ZERO") == nullptr &&
+                  (getenv("SPIHTB_LAZY_ZERO") != nullptr ||
+                   (double)in_stride * 8.0 <= 0.75 * (double)geom->h * (double)geom->w);
     rc = launch_decode(ctx, a);
     if (rc) return rc;
     x.blk = a.blk;

@@ -553,7 +553,14 @@ __global__ void __launch_bounds__(DEC_NT, META ? 1 : 2) spiht_decode_kernel(cons
             for (uint32_t kk = 0; kk < C; ++kk) {
                 int32_t *pl = rec + (size_t)kk * H * W;
                 const size_t lo = (size_t)fh * W, hi = (size_t)H * W;
-                for (size_t q = lo + t; q < hi; q += nt) pl[q] = 0;
+                // 16-byte stores over the aligned middle, scalar stores at the ends
+                int32_t *z0 = pl + lo;
+                const size_t head = min(hi - lo, (size_t)((16u - (uint32_t)((uintptr_t)z0 & 15u)) & 15u) >> 2);
+                const size_t nq = (hi - lo - head) >> 2, done = head + (nq << 2);
+                if ((size_t)t < head) z0[t] = 0;
+                int4 *zq = reinterpret_cast<int4 *>(z0 + head);
+                for (size_t q = t; q < nq; q += nt) zq[q] = make_int4(0, 0, 0, 0);
+                if (done + t < hi - lo) z0[done + t] = 0;
                 for (uint32_t r = (uint32_t)t >> 5; r < fh; r += nt / 32)
                     for (uint32_t cc = fw + (t & 31); cc < W; cc += 32) pl[(size_t)r * W + cc] = 0;
             }

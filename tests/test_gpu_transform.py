@@ -332,7 +332,7 @@ def test_color_convert_matches_oracle_to_a_few_ulp(torch_cuda):
     ((1, 320, 333), dict(wavelet="bior6.8")),
     ((3, 1024, 1024), dict()),
 ])
-def test_decode_images_scratch_coefficients_same_pixels(torch_cuda, shape, kw):
+def test_decode_images_scratch_coefficients_same_pixels(torch_cuda, monkeypatch, shape, kw):
     """SPIHTB_OPT_SCRATCH_COEFFS (the caller does not read the coefficient array): the finest detail bands of an image
     are zeroed only if its stream reaches them.  One batch holds streams that never reach them (a few hundred bytes),
     streams that reach them late and untruncated streams; the scratch array is filled with a poison value first, so a
@@ -340,6 +340,9 @@ def test_decode_images_scratch_coefficients_same_pixels(torch_cuda, shape, kw):
     import spiht_b200 as spiht
     from spiht_b200 import _lib, batch
     torch = torch_cuda
+    # (the library takes the lazy path by itself only when the rows bound the rate by 0.75 bpp; these rows hold
+    # untruncated streams)
+    monkeypatch.setenv("SPIHTB_LAZY_ZERO", "1")
     c, h, w = shape
     B = 6
     px = torch.from_numpy(np.stack([synth_image(c, h, w, 60 + s) for s in range(B)])).cuda()
