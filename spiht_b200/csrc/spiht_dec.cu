@@ -1143,7 +1143,9 @@ __global__ void __launch_bounds__(DEC_NT, META ? 1 : 2) spiht_decode_kernel(cons
             g_dec_img[b][0] = (unsigned long long)(clock64() - _timg);
             g_dec_img[b][1] = walk_cycles;
             g_dec_img[b][2] = smid;
-            g_dec_img[b][3] = (unsigned long long)_timg;
+            uint32_t hwid;
+            asm("mov.u32 %0, %%warpid;" : "=r"(hwid));
+            g_dec_img[b][3] = hwid;
         }
 #endif
     }

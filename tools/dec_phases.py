@@ -49,3 +49,8 @@ if hasattr(lib, "spihtb_debug_dec_img"):
         if m.any():
             print(name, int(m.sum()), "images: total cycles min/median/max", int(arr[m, 0].min()), int(np.median(arr[m, 0])),
                   int(arr[m, 0].max()), "walk median", int(np.median(arr[m, 1])))
+    # hardware warp slot of warp 0 of the CTAs that share an SM
+    pairs = {}
+    for i in range(n):
+        pairs.setdefault(int(arr[i, 2]), []).append(int(arr[i, 3]))
+    print("hardware warp id of warp 0, CTAs sharing an SM (first 12 SMs):", [v for v in list(pairs.values()) if len(v) > 1][:12])
