@@ -875,9 +875,9 @@ int spihtb_decode_images(spihtb_ctx *ctx, const uint8_t *dev_in, uint64_t in_str
     // the decoder marks the 64x64 blocks of the array it writes into; the inverse transform skips the detail
     // bands of tasks with no marked block (at low rates the finest levels hold no coefficient at all)
     const size_t nblk = (size_t)B * C * ((h + 63) / 64) * ((w + 63) / 64);
-    rc = ctx->ensure(ctx->blk, 2 * nblk + 256);
+    rc = ctx->ensure(ctx->blk, 2 * nblk + (size_t)B + 256);
     if (rc) return rc;
-    SPIHTB_CUDA_CHECK(cudaMemsetAsync(ctx->blk.p, 0, 2 * nblk, ctx->stream));
+    SPIHTB_CUDA_CHECK(cudaMemsetAsync(ctx->blk.p, 0, 2 * nblk + (size_t)B, ctx->stream));
     DecArgs a;
     a.in = dev_in;
     a.in_stride = in_stride;
@@ -888,6 +888,7 @@ int spihtb_decode_images(spihtb_ctx *ctx, const uint8_t *dev_in, uint64_t in_str
     a.blk = static_cast<uint8_t *>(ctx->blk.p);
     // marks of the finest level alone (its bands start at row off_h[0] / column off_w[0] of the array)
     a.blk1 = a.blk + nblk;
+    a.l1_any = a.blk + 2 * nblk;
     a.fine_h0 = geom->off_h[0];
     a.fine_w0 = geom->off_w[0];
     // SPIHTB_OPT_SCRATCH_COEFFS: the caller does not read the coefficient array, so the finest detail bands (three
@@ -902,6 +903,7 @@ int spihtb_decode_images(spihtb_ctx *ctx, const uint8_t *dev_in, uint64_t in_str
     if (rc) return rc;
     x.blk = a.blk;
     x.blk1 = a.blk1;
+    x.l1_any = a.l1_any;
     return launch_inverse(ctx, dev_coeffs_scratch, x, dev_pixels_out);
 }
 

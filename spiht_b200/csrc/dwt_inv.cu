@@ -23,6 +23,7 @@
 // waverec2 drops the approximation's trailing row/column when it is one
 // longer than the detail band (odd sizes); the strips simply never read it.
 #include <algorithm>
+#include <cstdlib>
 #include <type_traits>
 
 #include "common.cuh"
@@ -51,6 +52,15 @@ struct InvK {
     // detail band and skips their half of the arithmetic (at low rates the finest bands are empty)
     const uint8_t *blk;
     int BH, BW;
+    // Fused finest level (FUSE launches: the level-2 launch of spihtb_decode_images, bior2.2, not periodization).
+    // l1_any [images]: 0 = the image has no non-zero coefficient in the finest detail bands.  For such an image the
+    // task does not store its output (the level-1 approximation) but synthesises the pixels from it on the spot --
+    // the finest level is then only an interpolation of the approximation -- and the level-1 launch skips the image
+    // (skip_img).  pix: [nz][ph][pw] of TPix.
+    const uint8_t *l1_any;
+    const uint8_t *skip_img;
+    void *pix;
+    int ph, pw;
 };
 
 template <typename Tout>
@@ -68,7 +78,7 @@ struct Out2<double> {
 
 // spiht_wrapper.py:270-274: (x / m_c) / q.  Evaluated as (x * (1/m_c)) * (1/q): at most 2 ulp from the
 // reference's two divisions, far inside the float tolerance of the inverse path.
-template <typename Tout, int WID, bool LLQ>
+template <typename Tout, int WID, bool LLQ, bool FUSE = false, typename TPix = float>
 __global__ void __launch_bounds__(IV_WARPS * 32) dwt_inv_level_kernel(const InvK p)
 {
     constexpr int F = Wav<WID>::F;
@@ -76,7 +86,7 @@ __global__ void __launch_bounds__(IV_WARPS * 32) dwt_inv_level_kernel(const InvK
     constexpr int NOUT = 32 - (HF - 1);
     // prefetch distance in rows and unroll of the streaming loop (a multiple of HF: static window and queue slots)
     // (6 rows ahead pay off on the latency-bound coarse levels; the float32 output level is issue-bound: 3)
-    constexpr int PD_FULL = HF == 3 ? (sizeof(Tout) == 8 ? 9 : 3) : HF;
+    constexpr int PD_FULL = HF == 3 ? (FUSE ? 3 : (sizeof(Tout) == 8 ? 9 : 3)) : HF;
     constexpr unsigned FULL = 0xffffffffu;
     long long task = (long long)blockIdx.x * IV_WARPS + (threadIdx.x >> 5);
     if (task >= p.ntasks) return;
@@ -84,11 +94,13 @@ __global__ void __launch_bounds__(IV_WARPS * 32) dwt_inv_level_kernel(const InvK
     task /= p.tiles_x;
     const int ty = (int)(task % p.tiles_y);
     const int z = (int)(task / p.tiles_y);
+    if (!FUSE && p.skip_img && p.skip_img[z / p.C] == 0) return;   // the fused level-2 launch wrote this image's pixels
     const int lane = threadIdx.x & 31;
     const bool per = p.mode == SPIHTB_MODE_PERIODIZATION;
     const int S2 = per ? (HF - 1) / 2 : HF - 1;
     const int bh = p.bh, bw = p.bw, Wc = p.Wc;
-    const int q0 = tx * NOUT, p0 = ty * p.RH;
+    // (fused launches: strips and chunks overlap by one output pair, the halo of the second synthesis)
+    const int q0 = tx * (FUSE ? NOUT - 1 : NOUT), p0 = ty * (FUSE ? p.RH - 1 : p.RH);
     const int npair = min(p.RH, p.oh / 2 - p0);  // output row pairs of this chunk
 
     // this lane's coefficient column
@@ -99,8 +111,10 @@ __global__ void __launch_bounds__(IV_WARPS * 32) dwt_inv_level_kernel(const InvK
     } else {
         kc = min(kc, bw - 1);  // lanes past the band only feed dropped outputs
     }
-    const int zc = z % p.C;
+    const int zimg = z / p.C, zc = z - zimg * p.C;
     const double rm = p.rscale[zc], rq = p.rq;
+    bool fuse_img = false;
+    if constexpr (FUSE) fuse_img = p.l1_any[zimg] == 0;
     const int32_t *cz = p.coeffs + (size_t)z * p.Hc * Wc;
     const int32_t *c_ad = cz + p.sw + kc;
     const int32_t *c_da = cz + (size_t)p.sh * Wc + kc;
@@ -220,6 +234,7 @@ __global__ void __launch_bounds__(IV_WARPS * 32) dwt_inv_level_kernel(const InvK
     Tout *dst = static_cast<Tout *>(p.dst) + (size_t)z * p.oh * p.ow + (size_t)(2 * p0) * p.ow + 2 * q_out;
     const int ow = p.ow;
 
+    [[maybe_unused]] double hprev[4] = {0.0, 0.0, 0.0, 0.0};   // fused finest level: column-synthesised row 2P-1
     const int niter = (npair + UN - 1) / UN;
     for (int it = 0; it < niter; ++it) {
 #pragma unroll
@@ -250,7 +265,74 @@ __global__ void __launch_bounds__(IV_WARPS * 32) dwt_inv_level_kernel(const InvK
                     o1 = fma(wav_rec_hi<WID>(2 * u + 1), xhi[slot][1], o1);
                 }
             }
-            if (col_ok && i < npair) {
+            if constexpr (FUSE) {
+                if (fuse_img) {
+                    // e0 e1 / o0 o1 are rows 2P, 2P+1 (P = p0 + i), columns 2q', 2q'+1 (q' = q_out) of the level-1
+                    // approximation A.  Without detail bands the finest synthesis is, per axis,
+                    //   X[2m] = sum_u g[2u] A[m + 2 - u],  X[2m+1] = sum_u g[2u+1] A[m + 2 - u]     (g = rec_lo, F = 6),
+                    // evaluated in the order of the level-by-level kernel above (bit-identical pixels).
+                    // Columns: pairs m = 2q'-1 (from A[2q'-1 .. 2q'+1]) and m = 2q' (from A[2q' .. 2q'+2]):
+                    // pixel columns 4q'-2 .. 4q'+1; the neighbours' columns come by shuffle.
+                    auto hsyn = [&](double c0, double c1, double (&h)[4]) {
+                        constexpr double g0 = Wav<WID>::rec_lo(0), g1 = Wav<WID>::rec_lo(1), g2 = Wav<WID>::rec_lo(2),
+                                         g3 = Wav<WID>::rec_lo(3), g4 = Wav<WID>::rec_lo(4), g5 = Wav<WID>::rec_lo(5);
+                        const double nx = __shfl_down_sync(FULL, c0, 1);                        // A[2q'+2]
+                        const double pv = (g4 != 0.0 || g5 != 0.0) ? __shfl_up_sync(FULL, c1, 1) : 0.0;   // A[2q'-1]
+                        double a = 0.0, b = 0.0, c = 0.0, d = 0.0;
+                        // m = 2q'-1: A[m+2-u] = c1, c0, pv for u = 0, 1, 2
+                        if (g0 != 0.0) a = fma(g0, c1, a);
+                        if (g1 != 0.0) b = fma(g1, c1, b);
+                        if (g2 != 0.0) a = fma(g2, c0, a);
+                        if (g3 != 0.0) b = fma(g3, c0, b);
+                        if (g4 != 0.0) a = fma(g4, pv, a);
+                        if (g5 != 0.0) b = fma(g5, pv, b);
+                        // m = 2q': A[m+2-u] = nx, c1, c0
+                        if (g0 != 0.0) c = fma(g0, nx, c);
+                        if (g1 != 0.0) d = fma(g1, nx, d);
+                        if (g2 != 0.0) c = fma(g2, c1, c);
+                        if (g3 != 0.0) d = fma(g3, c1, d);
+                        if (g4 != 0.0) c = fma(g4, c0, c);
+                        if (g5 != 0.0) d = fma(g5, c0, d);
+                        h[0] = a; h[1] = b; h[2] = c; h[3] = d;
+                    };
+                    double h0[4], h1[4];
+                    hsyn(e0, e1, h0);
+                    hsyn(o0, o1, h1);
+                    // Rows: pair r needs rows r+2, r+1 (, r) of the column-synthesised signal: r = 2P-2 from (h0, hprev),
+                    // r = 2P-1 from (h1, h0); rows 2r, 2r+1 of the image.
+                    static_assert(!FUSE || (Wav<WID>::rec_lo(4) == 0.0 && Wav<WID>::rec_lo(5) == 0.0 && Wav<WID>::F == 6),
+                                  "fused finest level: two-row window (bior2.2)");
+                    using P2 = Out2<TPix>;
+                    const int P = p0 + i;
+                    const int qp = q_out;   // q'
+                    const bool lane_ok = lane < NOUT - 1 && qp < p.ow / 2 && i < npair;
+                    auto emit = [&](int r, const double (&hb)[4], const double (&ha)[4]) {   // hb = row r+2, ha = row r+1
+                        if (!lane_ok || r < 0 || r >= p.ph / 2) return;
+                        constexpr double g0 = Wav<WID>::rec_lo(0), g1 = Wav<WID>::rec_lo(1), g2 = Wav<WID>::rec_lo(2),
+                                         g3 = Wav<WID>::rec_lo(3);
+                        TPix *row = static_cast<TPix *>(p.pix) + ((size_t)z * p.ph + 2 * (size_t)r) * p.pw;
+#pragma unroll
+                        for (int half = 0; half < 2; ++half) {
+                            const int m = 2 * qp - 1 + half;   // output column pair
+                            if (m < 0 || m >= p.pw / 2) continue;
+                            double ev0 = 0.0, ev1 = 0.0, od0 = 0.0, od1 = 0.0;
+                            if (g0 != 0.0) { ev0 = fma(g0, hb[2 * half], ev0); ev1 = fma(g0, hb[2 * half + 1], ev1); }
+                            if (g1 != 0.0) { od0 = fma(g1, hb[2 * half], od0); od1 = fma(g1, hb[2 * half + 1], od1); }
+                            if (g2 != 0.0) { ev0 = fma(g2, ha[2 * half], ev0); ev1 = fma(g2, ha[2 * half + 1], ev1); }
+                            if (g3 != 0.0) { od0 = fma(g3, ha[2 * half], od0); od1 = fma(g3, ha[2 * half + 1], od1); }
+                            *reinterpret_cast<typename P2::type *>(row + 2 * m) = P2::make(ev0, ev1);
+                            *reinterpret_cast<typename P2::type *>(row + p.pw + 2 * m) = P2::make(od0, od1);
+                        }
+                    };
+                    if (i > 0) emit(2 * P - 2, h0, hprev);
+                    emit(2 * P - 1, h1, h0);
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) hprev[t] = h1[t];
+                } else if (col_ok && i < npair) {
+                    *reinterpret_cast<typename O2::type *>(dst) = O2::make(e0, e1);
+                    *reinterpret_cast<typename O2::type *>(dst + ow) = O2::make(o0, o1);
+                }
+            } else if (col_ok && i < npair) {
                 *reinterpret_cast<typename O2::type *>(dst) = O2::make(e0, e1);
                 *reinterpret_cast<typename O2::type *>(dst + ow) = O2::make(o0, o1);
             }
@@ -265,7 +347,7 @@ __global__ void __launch_bounds__(IV_WARPS * 32) dwt_inv_level_kernel(const InvK
 }
 
 template <int WID>
-static int launch_inv_level(spihtb_ctx *ctx, InvK k, int nz, bool out_f32)
+static int launch_inv_level(spihtb_ctx *ctx, InvK k, int nz, bool out_f32, bool fuse = false, bool pix_f32 = true)
 {
     constexpr int F = Wav<WID>::F;
     constexpr int NOUT = 32 - (F / 2 - 1);
@@ -273,9 +355,16 @@ static int launch_inv_level(spihtb_ctx *ctx, InvK k, int nz, bool out_f32)
     // output row pairs per chunk (multiples of the bior2.2 loop unroll): long chunks amortise the window fill on
     // the coarse levels, shorter ones balance the big finest level better (measured)
     const int RHMAX = oph >= 384 ? 60 : 96;
-    k.tiles_x = (opw + NOUT - 1) / NOUT;
-    k.tiles_y = (oph + RHMAX - 1) / RHMAX;
-    k.RH = (oph + k.tiles_y - 1) / k.tiles_y;
+    if (fuse) {
+        // strips / chunks advance by one pair less than they compute (see the kernel)
+        k.tiles_x = (opw + NOUT - 2) / (NOUT - 1);
+        k.tiles_y = std::max(1, (oph - 1 + RHMAX - 2) / (RHMAX - 1));
+        k.RH = std::max(2, (oph - 1 + k.tiles_y - 1) / k.tiles_y + 1);
+    } else {
+        k.tiles_x = (opw + NOUT - 1) / NOUT;
+        k.tiles_y = (oph + RHMAX - 1) / RHMAX;
+        k.RH = (oph + k.tiles_y - 1) / k.tiles_y;
+    }
     k.ntasks = (long long)k.tiles_x * k.tiles_y * nz;
     const long long nb = (k.ntasks + IV_WARPS - 1) / IV_WARPS;
     if (nb > 0x7fffffffLL) {
@@ -284,6 +373,20 @@ static int launch_inv_level(spihtb_ctx *ctx, InvK k, int nz, bool out_f32)
     }
     const dim3 grid((unsigned)nb), block(IV_WARPS * 32);
     const bool llq = k.src_a == nullptr;
+    if constexpr (WID == SPIHTB_WAVELET_BIOR22) {
+        if (fuse) {
+            if (llq && pix_f32)
+                dwt_inv_level_kernel<double, WID, true, true, float><<<grid, block, 0, ctx->stream>>>(k);
+            else if (llq)
+                dwt_inv_level_kernel<double, WID, true, true, double><<<grid, block, 0, ctx->stream>>>(k);
+            else if (pix_f32)
+                dwt_inv_level_kernel<double, WID, false, true, float><<<grid, block, 0, ctx->stream>>>(k);
+            else
+                dwt_inv_level_kernel<double, WID, false, true, double><<<grid, block, 0, ctx->stream>>>(k);
+            ctx->launches++;
+            return SPIHTB_OK;
+        }
+    }
     if (out_f32) {
         if (llq)
             dwt_inv_level_kernel<float, WID, true><<<grid, block, 0, ctx->stream>>>(k);
@@ -366,8 +469,26 @@ int launch_inverse(spihtb_ctx *ctx, const int32_t *coeffs, const XformArgs &x, v
         } else {
             k.dst = ((L - 1 - l) & 1) ? ctx->tmpb.p : ctx->tmpa.p;
         }
+        // images without a coefficient in the finest bands (spihtb_decode_images knows which): their pixels come out of
+        // the level-2 launch, and the level-1 launch skips them
+        const bool fusable = x.l1_any && L >= 2 && g.wavelet == SPIHTB_WAVELET_BIOR22 && !per &&
+                             getenv("SPIHTB_NO_FUSED_INV") == nullptr;
+        k.l1_any = nullptr;
+        k.skip_img = nullptr;
+        k.pix = nullptr;
+        k.ph = k.pw = 0;
+        bool fuse = false, pix_f32 = true;
+        if (fusable && l == 1) {
+            fuse = true;
+            k.l1_any = x.l1_any;
+            k.pix = color ? ctx->io2.p : pixels_out;
+            pix_f32 = !color && x.pixel_dtype == SPIHTB_F32;
+            k.ph = out_len(g.band_h[0]);
+            k.pw = out_len(g.band_w[0]);
+        }
+        if (fusable && l == 0) k.skip_img = x.l1_any;
         switch (g.wavelet) {
-            case SPIHTB_WAVELET_BIOR22: rc = launch_inv_level<SPIHTB_WAVELET_BIOR22>(ctx, k, nz, out_f32); break;
+            case SPIHTB_WAVELET_BIOR22: rc = launch_inv_level<SPIHTB_WAVELET_BIOR22>(ctx, k, nz, out_f32, fuse, pix_f32); break;
             case SPIHTB_WAVELET_BIOR44: rc = launch_inv_level<SPIHTB_WAVELET_BIOR44>(ctx, k, nz, out_f32); break;
             case SPIHTB_WAVELET_BIOR68: rc = launch_inv_level<SPIHTB_WAVELET_BIOR68>(ctx, k, nz, out_f32); break;
             default: set_error("unknown wavelet id %d", g.wavelet); rc = SPIHTB_EINVAL;

@@ -68,6 +68,7 @@ struct DecArgs {
     // fine_h0 or column >= fine_w0, the offsets of those bands in the array) mark it.  The level-1 inverse uses these:
     // a block on the edge of the finest bands is otherwise marked by coarser coefficients too.
     uint8_t *blk1 = nullptr;
+    uint8_t *l1_any = nullptr;   // [B], zeroed by the caller: set to 1 for an image that marks anything in blk1
     int fine_h0 = 0, fine_w0 = 0;
     // lazy zero fill (needs blk1): only the corner above / left of the finest bands is zeroed before the launch; an
     // image zeroes its finest bands itself when its stream first reaches them (see DecK)
@@ -85,6 +86,7 @@ struct XformArgs {
     int pixel_dtype;
     const uint8_t *blk = nullptr;  // inverse only: block marks of the coefficient array (see DecArgs), or null
     const uint8_t *blk1 = nullptr; // inverse only: the marks the finest level uses instead (see DecArgs), or null
+    const uint8_t *l1_any = nullptr;  // inverse only: per image, 0 = no non-zero coefficient in the finest bands, or null
 };
 // Pyramid base pass fused into the forward transform: dp planes [B*C][enc_h/2][enc_w/2] and maxabs [B]
 // are complete when launch_forward returns (stream order).

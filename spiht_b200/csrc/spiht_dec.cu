@@ -93,6 +93,7 @@ struct DecK {
     // never reads them.
     int fine_h0, fine_w0, fine_ht, fine_wt;
     uint8_t *blk1;   // marks of the finest bands alone (coefficients at or past fine_ht / fine_wt), or null
+    uint8_t *l1_any; // [B]: 1 = the image marked something in blk1
 };
 
 // ---- decode_with_metadata helpers ----------------------------------------------------------------------
@@ -1125,6 +1126,7 @@ __global__ void __launch_bounds__(DEC_NT, META ? 1 : 2) spiht_decode_kernel(cons
                         blkb[((size_t)k * p.BH + (i >> 6)) * p.BW + (j >> 6)] = 1;
                         if (p.blk1 && (i >= (uint32_t)p.fine_ht || j >= (uint32_t)p.fine_wt)) {
                             p.blk1[(((size_t)b * C + k) * p.BH + (i >> 6)) * p.BW + (j >> 6)] = 1;
+                            if (p.l1_any) p.l1_any[b] = 1;
                             late = 1;
                         }
                     }
@@ -1260,6 +1262,7 @@ int launch_decode(spihtb_ctx *ctx, const DecArgs &a)
     k.fine_ht = a.fine_h0;
     k.fine_wt = a.fine_w0;
     k.blk1 = a.blk1;
+    k.l1_any = a.l1_any;
     if (a.lazy_zero && a.blk1 && a.fine_h0 > 0 && a.fine_w0 > 0 && a.fine_h0 < a.H && a.fine_w0 < a.W && !a.meta &&
         !((a.ll_h | a.ll_w) & 1)) {
         // lazy: only the corner that holds everything but the finest detail bands; an image that reaches those bands

@@ -373,3 +373,40 @@ def test_decode_images_scratch_coefficients_same_pixels(torch_cuda, monkeypatch,
                                     scratch_coeffs=True)
     plain32, _ = batch.decode_images(s, nbytes, max_n, c, g, st, dtype=torch.float32)
     assert torch.equal(lazy32, plain32)
+
+
+@pytest.mark.parametrize("shape,kw,level", [
+    ((3, 256, 384), dict(), None),
+    ((1, 301, 263), dict(), None),
+    ((2, 200, 328), dict(mode="symmetric"), None),
+    ((3, 128, 160), dict(), 2),                       # two levels: the fused launch is also the coarsest (LL from the array)
+    ((3, 1024, 1024), dict(), None),                  # several strips and row chunks
+    ((3, 640, 1000), dict(color_model="IPT", per_channel_quant_scales=[50, 15, 15]), None),
+])
+def test_decode_images_fused_finest_level_same_pixels(torch_cuda, monkeypatch, shape, kw, level):
+    """images without a coefficient in the finest detail bands get their pixels from the level-2 launch (the finest
+    level is then an interpolation of the approximation, done in registers) and the level-1 launch skips them.  The
+    pixels must equal those of the level-by-level inverse bit for bit: batches that mix such images with images that do
+    reach the finest bands (which take the two-launch path inside the same launches), float64 and float32 output."""
+    import spiht_b200 as spiht
+    from spiht_b200 import _lib, batch
+    torch = torch_cuda
+    c, h, w = shape
+    B = 6
+    px = torch.from_numpy(np.stack([synth_image(c, h, w, 80 + s) for s in range(B)])).cuda()
+    st = spiht.SpihtSettings(**kw)
+    g = _lib.plan(h, w, kw.get("wavelet", "bior2.2"), kw.get("mode", "reflect"), level)
+    s, nbits, max_n, _, _ = batch.encode_images(px, g, st, 0)          # untruncated
+    full_bytes = (nbits + 7) // 8
+    frac = torch.tensor([0.001, 0.01, 0.03, 0.1, 0.5, 1.0], device="cuda")
+    nbytes = torch.clamp((full_bytes.double() * frac).long(), min=1)
+    for dtype in (torch.float64, torch.float32):
+        fused, co = batch.decode_images(s, nbytes, max_n, c, g, st, dtype=dtype)
+        monkeypatch.setenv("SPIHTB_NO_FUSED_INV", "1")
+        plain, co2 = batch.decode_images(s, nbytes, max_n, c, g, st, dtype=dtype)
+        monkeypatch.delenv("SPIHTB_NO_FUSED_INV")
+        assert torch.equal(co, co2)
+        assert torch.equal(fused, plain), (dtype, int((fused != plain).sum()))
+    fh, fw = g.off_h[0], g.off_w[0]
+    empty = [b for b in range(B) if int((co[b, :, fh:, :] != 0).sum() + (co[b, :, :fh, fw:] != 0).sum()) == 0]
+    assert 0 in empty and 5 not in empty, "the batch should mix both kinds of image"
