@@ -471,8 +471,12 @@ int launch_inverse(spihtb_ctx *ctx, const int32_t *coeffs, const XformArgs &x, v
         }
         // images without a coefficient in the finest bands (spihtb_decode_images knows which): their pixels come out of
         // the level-2 launch, and the level-1 launch skips them
+        // (float32 pixels only: with float64 output -- and the colour transform works on float64 -- the pixels dominate
+        // the traffic either way and the fused launch is the slower one, 42.4 against 39.4 ms at 512 x 3 x 2048^2;
+        // SPIHTB_FUSED_INV_F64=1 takes it anyway: tests)
         const bool fusable = x.l1_any && L >= 2 && g.wavelet == SPIHTB_WAVELET_BIOR22 && !per &&
-                             getenv("SPIHTB_NO_FUSED_INV") == nullptr;
+                             getenv("SPIHTB_NO_FUSED_INV") == nullptr &&
+                             ((!color && x.pixel_dtype == SPIHTB_F32) || getenv("SPIHTB_FUSED_INV_F64") != nullptr);
         k.l1_any = nullptr;
         k.skip_img = nullptr;
         k.pix = nullptr;

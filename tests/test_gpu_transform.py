@@ -400,6 +400,7 @@ def test_decode_images_fused_finest_level_same_pixels(torch_cuda, monkeypatch, s
     full_bytes = (nbits + 7) // 8
     frac = torch.tensor([0.001, 0.01, 0.03, 0.1, 0.5, 1.0], device="cuda")
     nbytes = torch.clamp((full_bytes.double() * frac).long(), min=1)
+    monkeypatch.setenv("SPIHTB_FUSED_INV_F64", "1")   # by itself the library fuses only for float32 pixels
     for dtype in (torch.float64, torch.float32):
         fused, co = batch.decode_images(s, nbytes, max_n, c, g, st, dtype=dtype)
         monkeypatch.setenv("SPIHTB_NO_FUSED_INV", "1")
