@@ -58,7 +58,8 @@ def build(force=False, verbose=False, extra_flags=()):
     os.makedirs(objdir, exist_ok=True)
     hdr_t = max(os.path.getmtime(d) for d in _deps() if not d.endswith(".cu"))
     flag_tag = os.path.join(objdir, "flags.txt")
-    flags = NVCC_FLAGS + list(extra_flags) + (["-DSPIHTB_PROF"] if VARIANT == "prof" else [])
+    flags = NVCC_FLAGS + list(extra_flags) + (["-DSPIHTB_PROF"] if VARIANT == "prof" else []) + \
+        (["-DSPIHTB_NO_LAZY"] if VARIANT == "nolazy" else [])   # A-B build without the lazy zero fill in the decoder
     same_flags = os.path.exists(flag_tag) and open(flag_tag).read() == " ".join(flags)
     jobs, objs = [], []
     for src in sources():

@@ -295,6 +295,28 @@ __device__ __forceinline__ uint64_t dec_exscan(uint64_t v, uint64_t *warp_tot, u
     return base + inc - v;
 }
 
+// ---- lazy zero fill: zero the finest detail bands of one image (rows from fh on whole, rows above from column fw
+// on); t = index of the calling thread among the nt that call.  Out of line: it runs at most twice per image, and
+// inlined into the hot loops its address arithmetic cost the decoder registers it does not have (spills)
+__device__ __noinline__ void dec_zero_fine(int32_t *rec, uint32_t C, uint32_t H, uint32_t W, uint32_t fh, uint32_t fw,
+                                           int t, int nt)
+{
+    for (uint32_t kk = 0; kk < C; ++kk) {
+        int32_t *pl = rec + (size_t)kk * H * W;
+        const size_t lo = (size_t)fh * W, hi = (size_t)H * W;
+        // 16-byte stores over the aligned middle, scalar stores at the ends
+        int32_t *z0 = pl + lo;
+        const size_t head = min(hi - lo, (size_t)((16u - (uint32_t)((uintptr_t)z0 & 15u)) & 15u) >> 2);
+        const size_t nq = (hi - lo - head) >> 2, done = head + (nq << 2);
+        if ((size_t)t < head) z0[t] = 0;
+        int4 *zq = reinterpret_cast<int4 *>(z0 + head);
+        for (size_t q = t; q < nq; q += nt) zq[q] = make_int4(0, 0, 0, 0);
+        if (done + t < hi - lo) z0[done + t] = 0;
+        for (uint32_t r = (uint32_t)t >> 5; r < fh; r += nt / 32)
+            for (uint32_t cc = fw + (t & 31); cc < W; cc += 32) pl[(size_t)r * W + cc] = 0;
+    }
+}
+
 // ---- LIP parse: 2-state automaton over the bits of a pass -------------------
 // state s = 1: the next bit starts a record; s = 0: the next bit is a sign bit.
 // next(s, b) = !(s & b).  A transition function over a bit window is stored as
@@ -461,7 +483,8 @@ __global__ void __launch_bounds__(DEC_NT, META ? 1 : 2) spiht_decode_kernel(cons
     __shared__ uint32_t s_tmask[DEC_CH / 32 + 4];  // A sets with offspring (a fired record carries child bits)
     __shared__ __align__(16) uint8_t s_x2[2][DEC_CH];           // child-bit length of fired A sets, 0 elsewhere (double-buffered)
     __shared__ uint32_t s_grp2[2][DEC_CH / 32];    // exclusive prefix of s_x per 32 entries
-    __shared__ uint32_t s_cnt[5];                  // list counters (and the lazy-zero flag) handed back by the applying warps
+    __shared__ uint32_t s_cnt[4];                  // list counters handed back by the applying warps
+    __shared__ uint32_t s_fine_done;               // lazy zero fill: the image's finest detail bands are zeroed
     __shared__ uint64_t s_wtot[DEC_NW];
     __shared__ uint32_t s_wfn[DEC_NW];
     __shared__ uint64_t s_chain_p;
@@ -546,26 +569,7 @@ __global__ void __launch_bounds__(DEC_NT, META ? 1 : 2) spiht_decode_kernel(cons
         __syncthreads();
 
         uint64_t pos = 0;  // uniform: next unread bit
-        uint32_t fine_done = p.fine_h0 == 0 ? 1u : 0u;   // uniform: the finest detail bands of this image are zeroed
-        // zero them: rows below fine_h0 whole, rows above it from column fine_w0 on (t: index of the calling thread among
-        // the nt that call)
-        auto zero_fine = [&](int t, int nt) {
-            const uint32_t fh = (uint32_t)p.fine_h0, fw = (uint32_t)p.fine_w0;
-            for (uint32_t kk = 0; kk < C; ++kk) {
-                int32_t *pl = rec + (size_t)kk * H * W;
-                const size_t lo = (size_t)fh * W, hi = (size_t)H * W;
-                // 16-byte stores over the aligned middle, scalar stores at the ends
-                int32_t *z0 = pl + lo;
-                const size_t head = min(hi - lo, (size_t)((16u - (uint32_t)((uintptr_t)z0 & 15u)) & 15u) >> 2);
-                const size_t nq = (hi - lo - head) >> 2, done = head + (nq << 2);
-                if ((size_t)t < head) z0[t] = 0;
-                int4 *zq = reinterpret_cast<int4 *>(z0 + head);
-                for (size_t q = t; q < nq; q += nt) zq[q] = make_int4(0, 0, 0, 0);
-                if (done + t < hi - lo) z0[done + t] = 0;
-                for (uint32_t r = (uint32_t)t >> 5; r < fh; r += nt / 32)
-                    for (uint32_t cc = fw + (t & 31); cc < W; cc += 32) pl[(size_t)r * W + cc] = 0;
-            }
-        };
+        if (tid == 0) s_fine_done = p.fine_h0 == 0 ? 1u : 0u;   // the finest detail bands of this image are zeroed
         DEC_PROF_MARK(_timg);
 #ifdef SPIHTB_PROF
         unsigned long long walk_cycles = 0, last_walk = 0, prev_tb = 0;
@@ -859,6 +863,7 @@ __global__ void __launch_bounds__(DEC_NT, META ? 1 : 2) spiht_decode_kernel(cons
                         // ---- every entry: its own bit, then the fired sets' records
                         for (uint32_t eb = 0; eb < cnt; eb += NT) {
                             const uint32_t e = eb + tid;
+                            [[maybe_unused]] const bool lazy_live = !has_dups && s_fine_done == 0;   // uniform per batch
                             const bool valid = e < cnt;
                             // bit position: entries before e take one bit each plus the child bits of fired A sets
                             const uint32_t xe = valid ? sx[e] : 0u;
@@ -922,7 +927,9 @@ __global__ void __launch_bounds__(DEC_NT, META ? 1 : 2) spiht_decode_kernel(cons
                                     if (!cut && has_desc_past_offspring(i, j, H, W)) nnext = 1;
                                     // lazy zero fill: a record with a child in the finest detail bands (the field of the
                                     // ordered-write count is free: odd LL sizes never run lazily)
-                                    if (!fine_done && nread && (ci >= (uint32_t)p.fine_h0 || cj >= (uint32_t)p.fine_w0)) ndef = 1;
+#ifndef SPIHTB_NO_LAZY
+                                    if (lazy_live && nread && (ci >= (uint32_t)p.fine_h0 || cj >= (uint32_t)p.fine_w0)) ndef = 1;
+#endif
                                     if (has_dups && nlsp) {
                                         for (uint32_t c4 = 0; c4 < nread; ++c4)
                                             if ((sigmask & (1u << c4)) &&
@@ -939,13 +946,15 @@ __global__ void __launch_bounds__(DEC_NT, META ? 1 : 2) spiht_decode_kernel(cons
                                                   ((uint64_t)ndef << 36) | ((uint64_t)(avail && !fired) << 48);
                             uint64_t tot;
                             const uint64_t ex = dec_exscan<PIPE>(pack, s_wtot, tot);
-                            if (!fine_done && ((tot >> 36) & 0xfff)) {
+#ifndef SPIHTB_NO_LAZY
+                            if (lazy_live && ((tot >> 36) & 0xfff)) {
                                 // first coefficient of the image in the finest bands: zero them, all threads at work
-                                // here, then go on
-                                zero_fine(tid, NT);
+                                // here, then go on (the flag is only read between scans: the barriers inside them order it)
+                                dec_zero_fine(rec, C, H, W, (uint32_t)p.fine_h0, (uint32_t)p.fine_w0, tid, NT);
+                                if (tid == 0) s_fine_done = 1;
                                 dec_sync<PIPE>();
-                                fine_done = 1;
                             }
+#endif
                             if (avail && !fired) R[rkeep + (uint32_t)(ex >> 48)] = key;
                             if (fired) {
                                 uint32_t os = lsp_len + (uint32_t)(ex & 0xfff);
@@ -1006,7 +1015,6 @@ __global__ void __launch_bounds__(DEC_NT, META ? 1 : 2) spiht_decode_kernel(cons
                             s_cnt[1] = lip_len;
                             s_cnt[2] = nxt_len;
                             s_cnt[3] = rkeep;
-                            s_cnt[4] = fine_done;
                         }
                     };
                     bool pend = false;   // a walked round whose entries are not applied yet
@@ -1028,7 +1036,6 @@ __global__ void __launch_bounds__(DEC_NT, META ? 1 : 2) spiht_decode_kernel(cons
                                     lip_len = s_cnt[1];
                                     nxt_len = s_cnt[2];
                                     rkeep = s_cnt[3];
-                                    fine_done = s_cnt[4];
                                 }
                                 pend = true;
                                 pend_ebase = ebase;
@@ -1054,7 +1061,6 @@ __global__ void __launch_bounds__(DEC_NT, META ? 1 : 2) spiht_decode_kernel(cons
                             lip_len = s_cnt[1];
                             nxt_len = s_cnt[2];
                             rkeep = s_cnt[3];
-                            fine_done = s_cnt[4];
                         }
                     }
                     uint32_t *old = cur;
@@ -1135,7 +1141,8 @@ __global__ void __launch_bounds__(DEC_NT, META ? 1 : 2) spiht_decode_kernel(cons
             // lazy zero fill: the image never read a child past the zeroed corner, but a coefficient on the first row or
             // column of the finest bands (inside the corner) is non-zero, so the level-1 inverse will read those bands:
             // zero them now (nothing was ever written there)
-            if (!fine_done && __syncthreads_or(late)) zero_fine(tid, DEC_NT);
+            if (__syncthreads_or(late) && !s_fine_done)
+                dec_zero_fine(rec, C, H, W, (uint32_t)p.fine_h0, (uint32_t)p.fine_w0, tid, DEC_NT);
         }
         DEC_PROF_SINCE(5, _timg);
 #ifdef SPIHTB_PROF
