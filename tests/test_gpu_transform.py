@@ -411,3 +411,28 @@ def test_decode_images_fused_finest_level_same_pixels(torch_cuda, monkeypatch, s
     fh, fw = g.off_h[0], g.off_w[0]
     empty = [b for b in range(B) if int((co[b, :, fh:, :] != 0).sum() + (co[b, :, :fh, fw:] != 0).sum()) == 0]
     assert 0 in empty and 5 not in empty, "the batch should mix both kinds of image"
+
+
+@pytest.mark.parametrize("shape,level", [((2, 148, 140), 1), ((3, 122, 162), 2), ((1, 302, 260), 3)])
+def test_scratch_coefficients_shallow_transforms(torch_cuda, monkeypatch, shape, level):
+    """the scratch-coefficients option on one-, two- and three-level transforms: with one level the zeroed corner is the
+    LL band alone and every stream reaches the "finest" bands at once; pixels as without the option"""
+    import spiht_b200 as spiht
+    from spiht_b200 import _lib, batch
+    torch = torch_cuda
+    monkeypatch.setenv("SPIHTB_LAZY_ZERO", "1")
+    c, h, w = shape
+    B = 4
+    px = torch.from_numpy(np.stack([synth_image(c, h, w, 90 + s) for s in range(B)])).cuda()
+    st = spiht.SpihtSettings()
+    g = _lib.plan(h, w, "bior2.2", "reflect", level)
+    if (g.ll_h | g.ll_w) & 1:
+        pytest.skip("odd LL band: the option is ignored")
+    s, nbits, max_n, _, _ = batch.encode_images(px, g, st, 0)
+    full_bytes = (nbits + 7) // 8
+    nbytes = torch.clamp((full_bytes.double() * torch.tensor([0.002, 0.05, 0.5, 1.0], device="cuda")).long(), min=1)
+    for dtype in (torch.float32, torch.float64):
+        plain, _ = batch.decode_images(s, nbytes, max_n, c, g, st, dtype=dtype)
+        poison = torch.full((B, c, g.enc_h, g.enc_w), 0x7f7f7f7f, dtype=torch.int32, device="cuda")
+        lazy, _ = batch.decode_images(s, nbytes, max_n, c, g, st, dtype=dtype, coeffs=poison, scratch_coeffs=True)
+        assert torch.equal(lazy, plain), dtype
