@@ -118,11 +118,30 @@ def _to_device_pixels(image):
 _PIPE_CHUNK = 32   # images per host->device copy in the pipelined host path
 
 
+_pinned_cache = {}
+
+
+def _pinned(name, shape, dtype):
+    """A reusable pinned host buffer (page-locking memory costs milliseconds; the pipelined path below needs a few per
+    call).  One buffer per (name, shape, dtype); the caller copies what it keeps before the next call."""
+    torch = _torch()
+    key = (name, tuple(shape), dtype)
+    buf = _pinned_cache.get(key)
+    if buf is None:
+        if len(_pinned_cache) > 16:
+            _pinned_cache.clear()
+        buf = torch.empty(tuple(shape), dtype=dtype, pin_memory=True)
+        _pinned_cache[key] = buf
+    return buf
+
+
 def _encode_host_pipelined(images, g, spiht_settings, budget, level):
     """Host pixels in, host bytes out, for a large batch: the batch goes to the device in chunks on a copy
     stream (two device buffers) while the previous chunk is transformed and coded on the current stream, so
-    the PCIe transfer -- by far the longest part of an end-to-end encode -- hides everything else.  Pinned
-    host memory gives a truly asynchronous copy; pageable memory still works (the copy then blocks)."""
+    the PCIe transfer -- by far the longest part of an end-to-end encode -- hides everything else.  The streams of
+    a finished chunk come back on a third stream into pinned memory (the link is full duplex) and the host builds
+    that chunk's results while the later chunks are still in flight; only the last chunk's return trip is exposed.
+    Pinned host memory gives a truly asynchronous copy; pageable memory still works (the copy then blocks)."""
     from . import batch
     torch = _torch()
     t = images if isinstance(images, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(images))
@@ -136,11 +155,28 @@ def _encode_host_pipelined(images, g, spiht_settings, budget, level):
     bufs = [torch.empty((n, c, h, w), dtype=t.dtype, device=dev) for _ in range(2)]
     coeffs = torch.empty((n, c, g.enc_h, g.enc_w), dtype=torch.int32, device=dev)
     streams = torch.empty((B, stride), dtype=torch.uint8, device=dev)
+    rows_h = _pinned("rows", (B, stride), torch.uint8)
+    nbits_h = _pinned("nbits", (B,), torch.int64)
+    max_n_h = _pinned("max_n", (B,), torch.int32)
+    status_h = _pinned("status", (B,), torch.int32)
     main = torch.cuda.current_stream(dev)
     copy = torch.cuda.Stream(dev)
+    back = torch.cuda.Stream(dev)
     copy.wait_stream(main)
     done = [None, None]   # per device buffer: event after the chunk that last read it
-    parts = []
+    results: List[Optional[EncodingResult]] = [None] * B
+    pending = []          # (lo, hi, event after the chunk's results reached the host)
+
+    def harvest(lo, hi, ev):
+        ev.synchronize()
+        if int(status_h[lo:hi].max()) != 0:
+            raise _lib.SpihtB200Error(_lib.ECAP, "bitstream row too small")
+        nb = (nbits_h[lo:hi].numpy() + 7) // 8
+        rows = rows_h.numpy()
+        mx = max_n_h.numpy()
+        for b in range(lo, hi):
+            results[b] = EncodingResult(rows[b, :int(nb[b - lo])].tobytes(), h, w, c, int(mx[b]), level)
+
     for i, lo in enumerate(range(0, B, n)):
         hi = min(B, lo + n)
         buf = bufs[i & 1][:hi - lo]
@@ -153,16 +189,27 @@ def _encode_host_pipelined(images, g, spiht_settings, budget, level):
         main.wait_event(ready)
         _, nbits, max_n, status, _ = batch.encode_images(buf, g, spiht_settings, budget, out_stride=stride,
                                                          coeffs=coeffs[:hi - lo], out=streams[lo:hi])
-        parts.append((nbits, max_n, status))
         done[i & 1] = torch.cuda.Event()
         done[i & 1].record(main)
-    nbits_h = torch.cat([p[0] for p in parts]).cpu().numpy()
-    max_n_h = torch.cat([p[1] for p in parts]).cpu().numpy()
-    if int(torch.cat([p[2] for p in parts]).max().item()) != 0:
-        raise _lib.SpihtB200Error(_lib.ECAP, "bitstream row too small")
-    nbytes = (nbits_h + 7) // 8
-    rows = streams[:, :int(nbytes.max())].cpu().numpy()
-    return [EncodingResult(rows[b, :int(nbytes[b])].tobytes(), h, w, c, int(max_n_h[b]), level) for b in range(B)]
+        with torch.cuda.stream(back):
+            back.wait_event(done[i & 1])
+            rows_h[lo:hi].copy_(streams[lo:hi], non_blocking=True)
+            nbits_h[lo:hi].copy_(nbits, non_blocking=True)
+            max_n_h[lo:hi].copy_(max_n, non_blocking=True)
+            status_h[lo:hi].copy_(status, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(back)
+        # the tensors of this chunk must outlive their copies on the other stream
+        nbits.record_stream(back)
+        max_n.record_stream(back)
+        status.record_stream(back)
+        pending.append((lo, hi, ev))
+        if len(pending) > 1:             # build the previous chunk's results while this one is in flight
+            harvest(*pending.pop(0))
+    while pending:
+        harvest(*pending.pop(0))
+    main.wait_stream(back)
+    return results  # type: ignore[return-value]
 
 
 def encode_image(image: np.ndarray, spiht_settings: SpihtSettings = SpihtSettings(), level: Optional[int] = None,
