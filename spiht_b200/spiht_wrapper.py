@@ -115,7 +115,12 @@ def _to_device_pixels(image):
     return torch.from_numpy(np.ascontiguousarray(a)).cuda()
 
 
-_PIPE_CHUNK = 32   # images per host->device copy in the pipelined host path
+_PIPE_CHUNK = 32   # images per host->device copy in the pipelined host path, at most
+_PIPE_CHUNK_BYTES = 400 << 20   # ... and about this many bytes (32 float32 RGB images of 1024^2)
+
+
+def _pipe_chunk(per_image_bytes: int) -> int:
+    return max(1, min(_PIPE_CHUNK, _PIPE_CHUNK_BYTES // max(1, per_image_bytes)))
 
 
 _pinned_cache = {}
@@ -150,7 +155,7 @@ def _encode_host_pipelined(images, g, spiht_settings, budget, level):
     t = t.contiguous()
     B, c, h, w = t.shape
     dev = torch.device("cuda", torch.cuda.current_device())
-    n = _PIPE_CHUNK
+    n = _pipe_chunk(c * h * w * t.element_size())
     stride = batch.stream_stride(budget, c, g)
     bufs = [torch.empty((n, c, h, w), dtype=t.dtype, device=dev) for _ in range(2)]
     coeffs = torch.empty((n, c, g.enc_h, g.enc_w), dtype=torch.int32, device=dev)
@@ -273,7 +278,8 @@ def encode_images(images, spiht_settings: SpihtSettings = SpihtSettings(), level
     else:
         budget = int(max_bits)
         host_side = not (isinstance(images, torch.Tensor) and images.is_cuda)
-        if host_side and 0 < budget <= bound and B >= 2 * _PIPE_CHUNK:
+        if host_side and 0 < budget <= bound and B >= 2 * _pipe_chunk(
+                c * h * w * (images.element_size() if isinstance(images, torch.Tensor) else images.dtype.itemsize)):
             return _encode_host_pipelined(images, g, spiht_settings, budget, level)
         pixels = _to_device_pixels(images)
         if budget == 0 or budget > bound:
