@@ -9,6 +9,8 @@ same-shaped images; mixed shapes are grouped).
 from dataclasses import asdict, dataclass
 from typing import Any, List, Optional, Sequence, Tuple, Union
 
+import threading
+
 import numpy as np
 
 from . import _lib
@@ -130,7 +132,7 @@ def _pinned(name, shape, dtype):
     """A reusable pinned host buffer (page-locking memory costs milliseconds; the pipelined path below needs a few per
     call).  One buffer per (name, shape, dtype); the caller copies what it keeps before the next call."""
     torch = _torch()
-    key = (name, tuple(shape), dtype)
+    key = (threading.get_ident(), name, tuple(shape), dtype)   # one set per calling thread
     buf = _pinned_cache.get(key)
     if buf is None:
         if len(_pinned_cache) > 16:
