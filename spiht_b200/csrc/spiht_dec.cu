@@ -50,14 +50,22 @@ constexpr int DEC_CH = 2048;           // LIS entries per chain round
 constexpr int DEC_PLW = DEC_CH * 9 / 32 + 8;  // staged stream words per round (an entry takes at most 9 bits)
 constexpr int DEC_SLACK = 8 * DEC_NT + 64;
 constexpr int DEC_DQ = 4 * DEC_NT;     // ordered write queue (odd LL sizes only)
-// pipelined rounds: warp 0 walks; the warps that share its scheduler (4, 8, 12: warp w issues on scheduler w % 4) stay
-// idle meanwhile, the other twelve apply the previous round (all fifteen: 3.97 ms per 256 images; twelve: 3.86).
-// Giving the walker of an SM's second CTA another scheduler was measured again in this form: 3.92 ms -- two walkers
-// on one scheduler disturb each other less than a walker and three warps of parallel work.
-constexpr int DEC_PIPE_NW = DEC_NW - DEC_NW / 4;
+// pipelined rounds: warp w issues on scheduler (b + w) % 4, b = the hardware slot of the CTA's warp 0.  Warp 0 walks; the
+// warps that share its scheduler (4, 8, 12) stay idle meanwhile (all fifteen others applying: 3.97 ms per 256 images;
+// twelve: 3.86).  Two CTAs share an SM, and on this part the second one's slots start one scheduler further (hardware
+// warp ids 0..3 / 16..19 observed), so each CTA also idles the warps on the OTHER walker's scheduler -- residue 1 for
+// the first CTA, 3 for the second, told apart by the hardware warp id (3.77 -> 3.72 ms; with the wrong residue the result
+// is the same and only the gain is lost: 3.76).  Eight warps apply; that costs nothing (twelve or eight: 3.86 / 3.84).
+// Giving the second CTA's WALKER another warp instead was slower every time it was tried (3.92 .. 4.13 ms).
+constexpr int DEC_PIPE_NW = DEC_NW / 2;
 constexpr int DEC_PIPE_NT = DEC_PIPE_NW * 32;
-__device__ __forceinline__ bool dec_pipe_worker(int wid) { return (wid & 3) != 0; }
-__device__ __forceinline__ int dec_pipe_wid(int wid) { return wid - 1 - (wid >> 2); }   // 1,2,3,5,6,7,... -> 0,1,2,3,4,5,...
+__device__ __forceinline__ bool dec_pipe_worker2(int wid, int idle2) { return (wid & 3) != 0 && (wid & 3) != idle2; }
+__device__ __forceinline__ int dec_pipe_wid2(int wid, int idle2)
+{
+    // residues at work: idle2 == 1 -> {2, 3}; idle2 == 3 -> {1, 2}
+    const int r = wid & 3;
+    return ((wid >> 2) << 1) | (idle2 == 1 ? r - 2 : r - 1);
+}
 
 struct DecK {
     const uint32_t *in;
@@ -270,11 +278,11 @@ __device__ __forceinline__ void dec_sync()
         __syncthreads();
 }
 template <bool PIPE>
-__device__ __forceinline__ uint64_t dec_exscan(uint64_t v, uint64_t *warp_tot, uint64_t &total)
+__device__ __forceinline__ uint64_t dec_exscan(uint64_t v, uint64_t *warp_tot, uint64_t &total, int idle2 = 1)
 {
     if (!PIPE) return block_exscan<DEC_NT>(v, warp_tot, total);
     constexpr int NW = DEC_PIPE_NW;
-    const int lane = threadIdx.x & 31, wid = dec_pipe_wid((int)(threadIdx.x >> 5));
+    const int lane = threadIdx.x & 31, wid = dec_pipe_wid2((int)(threadIdx.x >> 5), idle2);
     uint64_t inc = v;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -521,6 +529,14 @@ __global__ void __launch_bounds__(DEC_NT, META ? 1 : 2) spiht_decode_kernel(cons
         s_len[tid] = (uint8_t)len;
     }
     if (tid == 0) s_na = 0;
+    __shared__ int s_idle2;
+    if (tid == 0) {
+        uint32_t hw;
+        asm("mov.u32 %0, %%warpid;" : "=r"(hw));
+        s_idle2 = hw < 16 ? 1 : 3;
+    }
+    __syncthreads();
+    const int idle2 = s_idle2;
     // the walk may run past the end of a short stream into words / table bytes no round has staged yet
     for (int w = tid; w < 2 * DEC_PLW; w += DEC_NT) (&s_sw2[0][0])[w] = 0;
     for (int w = tid; w < DEC_PLW * 8; w += DEC_NT) reinterpret_cast<uint32_t *>(s_lp)[w] = 0;
@@ -739,7 +755,7 @@ __global__ void __launch_bounds__(DEC_NT, META ? 1 : 2) spiht_decode_kernel(cons
                     uint32_t nxt_len = 0;
                     // One round = up to DEC_CH entries of the generation: stage (all threads), walk (one thread), apply (parallel).
                     // Pipelined form (even LL sizes, no metadata table): the staged words, child lengths and group prefixes are
-                    // double-buffered, and while thread 0 walks round r the twelve warps on the other three schedulers apply
+                    // double-buffered, and while thread 0 walks round r eight warps on the schedulers no walker uses apply
                     // round r-1 behind a named barrier of their own; the list counters they advance come back through
                     // shared memory.
                     auto stage_round = [&](uint32_t ebase, uint32_t cnt, int buf) {
@@ -841,7 +857,7 @@ __global__ void __launch_bounds__(DEC_NT, META ? 1 : 2) spiht_decode_kernel(cons
                         constexpr bool PIPE = decltype(pipe_c)::value;
                         constexpr int NT = PIPE ? DEC_PIPE_NT : DEC_NT;
                         // index among the threads at work here
-                        const int tid = PIPE ? dec_pipe_wid((int)(threadIdx.x >> 5)) * 32 + (int)(threadIdx.x & 31) : (int)threadIdx.x;
+                        const int tid = PIPE ? dec_pipe_wid2((int)(threadIdx.x >> 5), idle2) * 32 + (int)(threadIdx.x & 31) : (int)threadIdx.x;
                         const uint8_t *sx = s_x2[buf];
                         const uint32_t *ssw = s_sw2[buf];
                         uint32_t *sgrp = s_grp2[buf];
@@ -855,7 +871,7 @@ __global__ void __launch_bounds__(DEC_NT, META ? 1 : 2) spiht_decode_kernel(cons
                             }
                             static_assert(DEC_CH / 32 <= NT, "one thread per 32-entry group");
                             uint64_t tot;
-                            const uint64_t ex = dec_exscan<PIPE>((uint64_t)v, s_wtot, tot);
+                            const uint64_t ex = dec_exscan<PIPE>((uint64_t)v, s_wtot, tot, idle2);
                             if (tid < DEC_CH / 32) sgrp[tid] = (uint32_t)ex;
                         }
                         dec_sync<PIPE>();
@@ -945,7 +961,7 @@ __global__ void __launch_bounds__(DEC_NT, META ? 1 : 2) spiht_decode_kernel(cons
                             const uint64_t pack = (uint64_t)nlsp | ((uint64_t)nlip << 12) | ((uint64_t)nnext << 24) |
                                                   ((uint64_t)ndef << 36) | ((uint64_t)(avail && !fired) << 48);
                             uint64_t tot;
-                            const uint64_t ex = dec_exscan<PIPE>(pack, s_wtot, tot);
+                            const uint64_t ex = dec_exscan<PIPE>(pack, s_wtot, tot, idle2);
 #ifndef SPIHTB_NO_LAZY
                             if (lazy_live && ((tot >> 36) & 0xfff)) {
                                 // first coefficient of the image in the finest bands: zero them, all threads at work
@@ -1028,7 +1044,7 @@ __global__ void __launch_bounds__(DEC_NT, META ? 1 : 2) spiht_decode_kernel(cons
                             if (pipe) {
                                 if (tid < 32)
                                     walk_round(cnt, buf);
-                                else if (pend && dec_pipe_worker(wid))
+                                else if (pend && dec_pipe_worker2(wid, idle2))
                                     apply_round(std::true_type{}, pend_ebase, pend_cnt, pend_pbase, buf ^ 1);
                                 __syncthreads();
                                 if (pend) {
@@ -1055,7 +1071,7 @@ __global__ void __launch_bounds__(DEC_NT, META ? 1 : 2) spiht_decode_kernel(cons
                     }
                     if constexpr (!META) {
                         if (pend) {   // the last walked round of the generation
-                            if (dec_pipe_worker(wid)) apply_round(std::true_type{}, pend_ebase, pend_cnt, pend_pbase, buf ^ 1);
+                            if (dec_pipe_worker2(wid, idle2)) apply_round(std::true_type{}, pend_ebase, pend_cnt, pend_pbase, buf ^ 1);
                             __syncthreads();
                             lsp_len = s_cnt[0];
                             lip_len = s_cnt[1];
