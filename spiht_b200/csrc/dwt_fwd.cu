@@ -804,7 +804,7 @@ static int upload_fix_rects(spihtb_ctx *ctx, const spihtb_geom &g, bool fused12,
         key[8 + 4 * l] = g.off_h[l]; key[9 + 4 * l] = g.off_w[l];
     }
     key[30] = fused12 ? 1 : 0;
-    key[31] = 0x5eed;
+    key[31] = 0x5eee;
     std::vector<int32_t> &h = ctx->fix_host;
     const bool hit = h.size() >= 34 && memcmp(h.data(), key, sizeof(key)) == 0 && ctx->fix.p;
     if (!hit) {
@@ -827,6 +827,28 @@ static int upload_fix_rects(spihtb_ctx *ctx, const spihtb_geom &g, bool fused12,
             }
         }
         r.push_back(FixRect{0, std::min((g.ll_h + 1) / 2, NH), 0, std::min((g.ll_w + 1) / 2, NW)});  // LL block
+        // The edges of the gaps as well.  gap_fill_kernel writes the cells that lie inside ONE gap rectangle and the
+        // band rectangles above cover the cells a gap shares with a band, but a cell can also straddle two gaps of
+        // different levels: the gap below a level's 'ad' band starts at column off_w, and when that is odd the cell
+        // (off_w - 1, off_w) has its other column in a gap of the next coarser level (found by
+        // tools/fuzz_encode_paths.py on 3 x 45 x 113, bior6.8, 4 levels: off_w[1] = 75; no BASELINE shape has it).
+        auto gap_edges = [&](int r0, int r1, int c0, int c1) {
+            if (r0 >= r1 || c0 >= c1) return;
+            const int a0 = r0 >> 1, a1 = std::min(((r1 - 1) >> 1) + 1, NH), b0 = c0 >> 1, b1 = std::min(((c1 - 1) >> 1) + 1, NW);
+            auto add = [&](int x0, int x1, int y0, int y1) {
+                x1 = std::min(x1, NH);
+                y1 = std::min(y1, NW);
+                if (x0 < x1 && y0 < y1) r.push_back(FixRect{x0, x1, y0, y1});
+            };
+            if (r0 & 1) add(a0, a0 + 1, b0, b1);
+            if (!((r1 - 1) & 1)) add(a1 - 1, a1, b0, b1);
+            if (c0 & 1) add(a0, a1, b0, b0 + 1);
+            if (!((c1 - 1) & 1)) add(a0, a1, b1 - 1, b1);
+        };
+        for (int l = 0; l < g.levels; ++l) {
+            gap_edges(g.band_h[l], g.off_h[l], g.off_w[l], g.off_w[l] + g.band_w[l]);
+            gap_edges(g.off_h[l], g.off_h[l] + g.band_h[l], g.band_w[l], g.off_w[l]);
+        }
         h.assign(key, key + 32);
         h.push_back((int32_t)r.size());
         h.push_back(0);

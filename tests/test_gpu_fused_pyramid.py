@@ -34,6 +34,10 @@ CASES = [
     ((1, 320, 333), "bior6.8", "reflect", None, 0.5),
     ((3, 96, 96), "bior6.8", "periodization", 1, 0.5),
     ((1, 277, 405), "bior6.8", "symmetric", 2, 0.25),
+    # a cell that straddles two GAPS of different levels (the gap below the level-2 'ad' band starts at the odd column
+    # 75, next to the level-3 gap): found by tools/fuzz_encode_paths.py, written by nobody before round 2's fix
+    ((3, 45, 113), "bior6.8", "reflect", 4, 1.0),
+    ((2, 113, 45), "bior6.8", "reflect", 4, 1.0),
 ]
 
 
