@@ -44,8 +44,8 @@ static inline uint8_t plane1(uint32_t v) { return v ? (uint8_t)(32 - __builtin_c
 int spiht_model_geom_ok(uint64_t h, uint64_t w, uint64_t ll_h, uint64_t ll_w)
 {
     if (ll_h < 2 || ll_w < 2) return 0;
-    if (2 * ll_h + (ll_h & 1) > h) return 0;
-    if (2 * ll_w + (ll_w & 1) > w) return 0;
+    if (2 * ll_h > h + (ll_h & 1)) return 0;   /* lowest root offspring row: 2 ll_h - 1 (even) or 2 ll_h - 2 (odd) */
+    if (2 * ll_w > w + (ll_w & 1)) return 0;
     return 1;
 }
 
