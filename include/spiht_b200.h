@@ -44,6 +44,18 @@ extern "C" {
 #define SPIHTB_WAVELET_BIOR22 0
 #define SPIHTB_WAVELET_BIOR44 1
 #define SPIHTB_WAVELET_BIOR68 2
+/* the rest of PyWavelets' bior family (spline pairs; separable kernels with the taps as launch parameters) */
+#define SPIHTB_WAVELET_BIOR11 3
+#define SPIHTB_WAVELET_BIOR13 4
+#define SPIHTB_WAVELET_BIOR15 5
+#define SPIHTB_WAVELET_BIOR24 6
+#define SPIHTB_WAVELET_BIOR26 7
+#define SPIHTB_WAVELET_BIOR28 8
+#define SPIHTB_WAVELET_BIOR31 9
+#define SPIHTB_WAVELET_BIOR33 10
+#define SPIHTB_WAVELET_BIOR35 11
+#define SPIHTB_WAVELET_BIOR37 12
+#define SPIHTB_WAVELET_BIOR39 13
 /* boundary mode ids (PyWavelets names, spiht_wrapper.py:57 `mode`) */
 #define SPIHTB_MODE_REFLECT 0
 #define SPIHTB_MODE_SYMMETRIC 1
@@ -119,6 +131,10 @@ int spihtb_profile_read(spihtb_ctx *ctx, double *ms_out, int64_t *count_out, int
  *      and pywt's level=None -> dwtn_max_level) ----------------------------- */
 /* level < 0 means "max level" (Python level=None). */
 int spihtb_plan(int32_t h, int32_t w, int32_t wavelet, int32_t mode, int32_t level, spihtb_geom *out);
+/* The filter bank the kernels use for a wavelet id, in PyWavelets' layout (pywt.Wavelet(name).dec_lo / .rec_lo, zero
+ * padding included; dec_hi[i] = (-1)^(F-1-i) rec_lo[i], rec_hi[i] = (-1)^i dec_lo[i]).  Host only.  *flen = F (even,
+ * <= 20); dec_lo and rec_lo receive F values each (room for 20). */
+int spihtb_wavelet_filters(int32_t wavelet, int32_t *flen, double *dec_lo, double *rec_lo);
 
 /* ---- raw SPIHT coder, HOST buffers: replaces the pyo3 module ------------ */
 /* src/lib.rs:24-32  encode(x: int32[c,h,w], ll_h, ll_w, max_bits) -> (bytes, max_n)

@@ -57,6 +57,61 @@ _FILTERS = {
     ),
 }
 
+
+def _spline_bior(nr, nd):
+    """Cohen-Daubechies-Feauveau biorthogonal spline pair biorNr.Nd, derived (not recalled), laid out as PyWavelets
+    stores it.  rec_lo is the B-spline of order nr, sqrt2 ((1 + z) / 2)^nr; dec_lo is
+        sqrt2 ((1 + z) / 2)^nd  sum_{m < K} C(K-1+m, m) ((2 - z - 1/z) / 4)^m,   K = (nr + nd) / 2
+    (Daubechies, Ten Lectures, 8.3.4), nr + 2 nd - 1 taps.  Layout: even common length F; odd-length filters (even nr)
+    get a leading zero, dec_lo centred on F/2 and rec_lo on F/2 - 1; even-length ones (odd nr) are both centred on
+    (F-1)/2.  The derived bior2.2 equals the stored table; bior1.3, 2.4, 3.1, 3.3 equal the PyWavelets tables as far
+    as they are remembered; tests/test_oracle_dwt.py checks perfect reconstruction and the vanishing moments."""
+    from fractions import Fraction
+    from math import comb
+    assert (nr + nd) % 2 == 0
+    K = (nr + nd) // 2
+
+    def mul(a, b):
+        out = [Fraction(0)] * (len(a) + len(b) - 1)
+        for i, x in enumerate(a):
+            for j, y in enumerate(b):
+                out[i + j] += x * y
+        return out
+    half = [Fraction(1, 2), Fraction(1, 2)]
+    s2 = [Fraction(-1, 4), Fraction(1, 2), Fraction(-1, 4)]          # sin^2(w/2) as a polynomial in z, centred
+    rec = [Fraction(1)]
+    for _ in range(nr):
+        rec = mul(rec, half)
+    q = [Fraction(0)] * (2 * K - 1)                                  # centred at index K - 1
+    pw = [Fraction(1)]
+    for m in range(K):
+        off = K - 1 - m
+        for i, v in enumerate(pw):
+            q[off + i] += comb(K - 1 + m, m) * v
+        pw = mul(pw, s2)
+    dec = q
+    for _ in range(nd):
+        dec = mul(dec, half)
+    assert len(dec) == nr + 2 * nd - 1 and len(rec) == nr + 1
+    if nr % 2 == 0:
+        F = len(dec) + 1
+        d0, r0 = 1, F // 2 - 1 - nr // 2
+    else:
+        F = len(dec)
+        d0, r0 = 0, (F - len(rec)) // 2
+    dec_lo, rec_lo = [0.0] * F, [0.0] * F
+    for i, v in enumerate(dec):
+        dec_lo[d0 + i] = _S2 * v.numerator / v.denominator          # denominators are powers of two: one rounding
+    for i, v in enumerate(rec):
+        rec_lo[r0 + i] = _S2 * v.numerator / v.denominator
+    return dec_lo, rec_lo
+
+
+# the rest of PyWavelets' bior family (bior5.5 is not a spline pair and is not restated)
+for _nr, _nd in ((1, 1), (1, 3), (1, 5), (2, 4), (2, 6), (2, 8), (3, 1), (3, 3), (3, 5), (3, 7), (3, 9)):
+    _FILTERS["bior%d.%d" % (_nr, _nd)] = _spline_bior(_nr, _nd)
+WAVELETS = tuple(sorted(_FILTERS))
+
 MODES = ("reflect", "symmetric", "periodization")
 
 

@@ -12,7 +12,10 @@ from . import build as _build
 OK, EINVAL, ELL, EGEOM, ESHAPE, ECAP, ECUDA, ENOMEM, ELEVEL = range(9)
 MAX_LEVELS = 24
 
-WAVELET_IDS = {"bior2.2": 0, "bior4.4": 1, "bior6.8": 2}
+WAVELET_IDS = {"bior2.2": 0, "bior4.4": 1, "bior6.8": 2,
+               # the rest of PyWavelets' bior family (csrc/dwt_gen.cu); bior5.5 is not a spline pair and is not offered
+               "bior1.1": 3, "bior1.3": 4, "bior1.5": 5, "bior2.4": 6, "bior2.6": 7, "bior2.8": 8,
+               "bior3.1": 9, "bior3.3": 10, "bior3.5": 11, "bior3.7": 12, "bior3.9": 13}
 MODE_IDS = {"reflect": 0, "symmetric": 1, "periodization": 2}
 COLOR_NONE, COLOR_IPT = 0, 1
 F32, F64, U8 = 0, 1, 2   # U8: forward direction only (pixels / 255 in float64, as utils.imload)
@@ -51,7 +54,7 @@ EXPORTS = (
     "spihtb_encode_coeffs", "spihtb_decode_coeffs", "spihtb_forward", "spihtb_inverse",
     "spihtb_encode_images", "spihtb_decode_images", "spihtb_stream_bound",
     "spihtb_profile_enable", "spihtb_profile_read", "spihtb_max_abs", "spihtb_convert_color", "spihtb_forward_path", "spihtb_decode_with_metadata",
-    "spihtb_set_option",
+    "spihtb_set_option", "spihtb_wavelet_filters",
 )
 
 
@@ -83,6 +86,7 @@ def lib():
         L.spihtb_launch_count.restype = ctypes.c_int64
         L.spihtb_forward_path.argtypes = [vp]
         L.spihtb_plan.argtypes = [i32, i32, i32, i32, i32, P(Geom)]
+        L.spihtb_wavelet_filters.argtypes = [i32, P(i32), P(dbl), P(dbl)]
         L.spihtb_encode.argtypes = [vp, vp, i32, i32, i32, i32, i32, u64, P(vp), P(u64), P(i32)]
         L.spihtb_decode.argtypes = [vp, ctypes.c_char_p, u64, i32, i32, i32, i32, i32, i32, vp]
         L.spihtb_decode_with_metadata.argtypes = [vp, ctypes.c_char_p, u64, i32, i32, i32, i32, i32, i32, vp, vp, i32, vp, vp]

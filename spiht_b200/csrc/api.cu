@@ -419,6 +419,40 @@ int spihtb_plan(int32_t h, int32_t w, int32_t wavelet, int32_t mode, int32_t lev
     return SPIHTB_OK;
 }
 
+int spihtb_wavelet_filters(int32_t wavelet, int32_t *flen, double *dec_lo, double *rec_lo)
+{
+    const int F = wavelet_flen(wavelet);
+    if (!flen || !dec_lo || !rec_lo || F == 0) {
+        set_error(F == 0 ? "unknown wavelet id %d" : "null pointer (wavelet id %d)", wavelet);
+        return SPIHTB_EINVAL;
+    }
+    *flen = F;
+    switch (wavelet) {
+#define SPIHTB_COPY_FILTERS(WID)                     \
+    for (int i = 0; i < Wav<WID>::F; ++i) {          \
+        dec_lo[i] = Wav<WID>::dec_lo(i);             \
+        rec_lo[i] = Wav<WID>::rec_lo(i);             \
+    }
+        case SPIHTB_WAVELET_BIOR22: SPIHTB_COPY_FILTERS(SPIHTB_WAVELET_BIOR22) break;
+        case SPIHTB_WAVELET_BIOR44: SPIHTB_COPY_FILTERS(SPIHTB_WAVELET_BIOR44) break;
+        case SPIHTB_WAVELET_BIOR68: SPIHTB_COPY_FILTERS(SPIHTB_WAVELET_BIOR68) break;
+#undef SPIHTB_COPY_FILTERS
+        default: {
+            double dl[SPIHTB_GEN_MAXF], rl[SPIHTB_GEN_MAXF];
+            int f2 = 0;
+            if (!generic_wavelet_taps(wavelet, &f2, dl, rl) || f2 != F) {
+                set_error("no filter bank for wavelet id %d", wavelet);
+                return SPIHTB_EINVAL;
+            }
+            for (int i = 0; i < F; ++i) {
+                dec_lo[i] = dl[i];
+                rec_lo[i] = rl[i];
+            }
+        }
+    }
+    return SPIHTB_OK;
+}
+
 uint64_t spihtb_stream_bound(int32_t c, int32_t h, int32_t w, int32_t ll_h, int32_t ll_w)
 {
     const uint64_t bits = stream_bits_bound(c, h, w, ll_h, ll_w, 31);
@@ -805,6 +839,8 @@ int spihtb_encode_images(spihtb_ctx *ctx, const void *dev_pixels, int32_t pixel_
     PyrBufs pb;
     rc = alloc_pyr(ctx, B, C, geom->enc_h, geom->enc_w, geom->ll_h, geom->ll_w, &pb);
     if (rc) return rc;
+    // the pyramid's base pass rides on the transform's epilogue, except for the wavelets of dwt_gen.cu (stand-alone pass)
+    const bool fuse_base = !wavelet_is_generic(geom->wavelet);
     // ---- group pipeline (see spihtb_ctx::subs): groups of G images on alternating sub-contexts
     int G = 0, NS = 3;
     if (const char *e = getenv("SPIHTB_GROUP")) G = atoi(e);
@@ -833,9 +869,9 @@ int spihtb_encode_images(spihtb_ctx *ctx, const void *dev_pixels, int32_t pixel_
             pg.maxabs = pb.maxabs + b0;
             const PyrFuse pfg = {pg.dp, pg.maxabs};
             int32_t *cg = dev_coeffs_scratch + b0 * co_img;
-            rc = launch_forward(sc, static_cast<const char *>(dev_pixels) + b0 * px_img, xg, cg, &pfg);
+            rc = launch_forward(sc, static_cast<const char *>(dev_pixels) + b0 * px_img, xg, cg, fuse_base ? &pfg : nullptr);
             if (rc) return rc;
-            rc = encode_with_pyramid(sc, cg, nb, C, geom->enc_h, geom->enc_w, geom->ll_h, geom->ll_w, pg, true, max_bits,
+            rc = encode_with_pyramid(sc, cg, nb, C, geom->enc_h, geom->enc_w, geom->ll_h, geom->ll_w, pg, fuse_base, max_bits,
                                      dev_max_bits ? dev_max_bits + b0 : nullptr, dev_out + (size_t)b0 * out_stride,
                                      out_stride, dev_nbits + b0, dev_max_n + b0, dev_status ? dev_status + b0 : nullptr);
             if (rc) return rc;
@@ -846,10 +882,10 @@ int spihtb_encode_images(spihtb_ctx *ctx, const void *dev_pixels, int32_t pixel_
         return SPIHTB_OK;
     }
     const PyrFuse pf = {pb.dp, pb.maxabs};
-    rc = launch_forward(ctx, dev_pixels, x, dev_coeffs_scratch, &pf);
+    rc = launch_forward(ctx, dev_pixels, x, dev_coeffs_scratch, fuse_base ? &pf : nullptr);
     if (rc) return rc;
     return encode_with_pyramid(ctx, dev_coeffs_scratch, B, C, geom->enc_h, geom->enc_w, geom->ll_h, geom->ll_w, pb,
-                               true, max_bits, dev_max_bits, dev_out, out_stride, dev_nbits, dev_max_n, dev_status);
+                               fuse_base, max_bits, dev_max_bits, dev_out, out_stride, dev_nbits, dev_max_n, dev_status);
 }
 
 int spihtb_decode_images(spihtb_ctx *ctx, const uint8_t *dev_in, uint64_t in_stride, const uint64_t *dev_nbytes,

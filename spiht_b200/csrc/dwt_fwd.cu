@@ -884,6 +884,11 @@ int launch_forward(spihtb_ctx *ctx, const void *pixels, const XformArgs &x, int3
     const spihtb_geom &g = x.g;
     const int nz = x.B * x.C;
     const int L = g.levels;
+    const bool generic = wavelet_is_generic(g.wavelet);
+    if (generic && pf) {
+        set_error("the fused pyramid base pass is not available for wavelet id %d", g.wavelet);
+        return SPIHTB_EINVAL;
+    }
     // scratch: two float64 approximation planes (level 1 output is the largest)
     const size_t ll1 = (size_t)nz * g.band_h[0] * g.band_w[0] * sizeof(double);
     const size_t ll2 = L > 1 ? (size_t)nz * g.band_h[1] * g.band_w[1] * sizeof(double) : 0;
@@ -972,6 +977,21 @@ int launch_forward(spihtb_ctx *ctx, const void *pixels, const XformArgs &x, int3
         const bool in_u8 = !in_f64 && x.pixel_dtype == SPIHTB_U8;
         const FwdK k = make_k(l, z0);
         const int st = l == 0 ? 0 : 1;
+        if (generic) {   // the rest of the bior family: separable kernels with the taps as launch parameters (dwt_gen.cu)
+            GenFwdLevel a;
+            a.src = k.src;
+            a.src_dtype = in_f64 ? SPIHTB_F64 : (in_u8 ? SPIHTB_U8 : SPIHTB_F32);
+            a.src_h = k.src_h; a.src_w = k.src_w; a.bh = k.bh; a.bw = k.bw;
+            a.dst_ll = k.dst_ll;
+            a.coeffs = k.coeffs;
+            a.Hc = k.Hc; a.Wc = k.Wc; a.sh = k.sh; a.sw = k.sw; a.mode = k.mode; a.C = k.C; a.last = k.last;
+            for (int c = 0; c < 8; ++c) a.scale[c] = k.scale[c];
+            a.q = k.q;
+            ctx->stage_begin(st);
+            const int r = launch_gen_fwd_level(ctx, g.wavelet, a, nzg);
+            ctx->stage_end(st);
+            return r;
+        }
         ctx->stage_begin(st);
         const int r = in_f64 ? launch_level_w<double>(ctx, g.wavelet, k, nzg)
                              : (in_u8 ? launch_level_w<uint8_t>(ctx, g.wavelet, k, nzg)
@@ -995,10 +1015,12 @@ int launch_forward(spihtb_ctx *ctx, const void *pixels, const XformArgs &x, int3
     {
         const bool in_f64 = x.pixel_dtype == SPIHTB_F64 || x.color == SPIHTB_COLOR_IPT || conv;
         const int sdt = in_f64 ? SPIHTB_F64 : x.pixel_dtype;
-        ctx->stage_begin(0);
-        rc = launch_forward_fused12(ctx, src, sdt, x, coeffs, static_cast<double *>(ctx->tmpb.p), pf, u8lut, &fused12);
-        ctx->stage_end(0);
-        if (rc) return rc;
+        if (!generic) {
+            ctx->stage_begin(0);
+            rc = launch_forward_fused12(ctx, src, sdt, x, coeffs, static_cast<double *>(ctx->tmpb.p), pf, u8lut, &fused12);
+            ctx->stage_end(0);
+            if (rc) return rc;
+        }
     }
     ctx->last_forward_fused12 = fused12;
     if (fused12) {  // level 3 writes its approximation to the first scratch plane
@@ -1054,7 +1076,7 @@ int launch_forward(spihtb_ctx *ctx, const void *pixels, const XformArgs &x, int3
             const int rhmax = fw_rhmax(g.band_h[l]);
             return ((g.band_w[l] + nout - 1) / nout) * ((g.band_h[l] + rhmax - 1) / rhmax);
         };
-        const bool tail_on = getenv("SPIHTB_NO_TAIL") == nullptr;
+        const bool tail_on = getenv("SPIHTB_NO_TAIL") == nullptr && !generic;
         // opt-in (SPIHTB_TAIL_TASKS=n: levels with at most n tasks per plane go to the tail kernel): measured on B200
         // the tail is slower than one launch per level at every threshold -- a plane's coarse
         // levels are a serial chain of short, latency-bound streams, and one launch per level runs all planes abreast

@@ -1,0 +1,366 @@
+// The rest of PyWavelets' bior family (bior1.1 1.3 1.5 2.4 2.6 2.8 3.1 3.3 3.5 3.7 3.9): filter banks derived on the
+// host, and one pair of separable kernels per transform level with the filter length and the taps as launch
+// parameters ("remaining bior family"; the reference passes SpihtSettings.wavelet straight
+// to pywt.wavedec2 / waverec2, spiht_wrapper.py:163,276).
+//
+// The three wavelets BASELINE.json names (bior2.2, bior4.4, bior6.8) keep their register / shuffle kernels with the
+// taps as immediates (dwt_fwd.cu, dwt_inv.cu); those kernels rely on F/2 being odd (vector alignment of the
+// periodization shift, whole-lane halos), which half of this family is not.  Here every thread owns one output
+// column and the passes go through float64 scratch planes:
+//   forward level:  rows  (axis -2): lo/hi[i][x]   = sum_j f[j] X[ext(2i + s - j)][x]
+//                   cols  (axis -1): aa ad da dd[i][k] = sum_j f[j] lo/hi[i][ext(2k + s - j)]   -> quantise, place
+//   inverse level:  cols  (axis -1): Xlo/Xhi[i][n] from (aa, ad) / (da, dd)  (dequantised on load, block marks obeyed)
+//                   rows  (axis -2): out[r][n]     from Xlo, Xhi
+// with s = 1 (reflect, symmetric) or F/2 (periodization) and PyWavelets' order of the axes and of the taps, so the
+// float64 results agree with the float64 restatement in the tests to rounding.  Accesses are coalesced along x / k / n; the F row or column
+// reads of neighbouring outputs overlap in L1 / L2.  Algorithmic traffic per level is that of the specialised
+// kernels plus one write and one read of the two scratch planes.
+#include <algorithm>
+
+#include "common.cuh"
+#include "kernels.cuh"
+#include "wavelets.cuh"
+
+namespace spihtb {
+
+// ---------------------------------------------------------------- filter banks
+// Cohen-Daubechies-Feauveau spline pair biorNr.Nd in exact integer arithmetic:
+//   rec_lo = sqrt2 (1 + z)^nr / 2^nr
+//   dec_lo = sqrt2 (1 + z)^nd  sum_{m < K} C(K-1+m, m) (-1/z + 2 - z)^m 4^(K-1-m)  /  (2^nd 4^(K-1)),  K = (nr + nd) / 2
+// and PyWavelets' layout: even common length F; odd-length filters (even nr) get a leading zero, dec_lo centred on
+// F/2 and rec_lo on F/2 - 1; even-length ones (odd nr) are both centred on (F-1)/2.
+static bool spline_pair(int wid, int *nr, int *nd)
+{
+    switch (wid) {
+        case SPIHTB_WAVELET_BIOR11: *nr = 1; *nd = 1; return true;
+        case SPIHTB_WAVELET_BIOR13: *nr = 1; *nd = 3; return true;
+        case SPIHTB_WAVELET_BIOR15: *nr = 1; *nd = 5; return true;
+        case SPIHTB_WAVELET_BIOR24: *nr = 2; *nd = 4; return true;
+        case SPIHTB_WAVELET_BIOR26: *nr = 2; *nd = 6; return true;
+        case SPIHTB_WAVELET_BIOR28: *nr = 2; *nd = 8; return true;
+        case SPIHTB_WAVELET_BIOR31: *nr = 3; *nd = 1; return true;
+        case SPIHTB_WAVELET_BIOR33: *nr = 3; *nd = 3; return true;
+        case SPIHTB_WAVELET_BIOR35: *nr = 3; *nd = 5; return true;
+        case SPIHTB_WAVELET_BIOR37: *nr = 3; *nd = 7; return true;
+        case SPIHTB_WAVELET_BIOR39: *nr = 3; *nd = 9; return true;
+    }
+    return false;
+}
+
+bool wavelet_is_generic(int wid)
+{
+    int a, b;
+    return spline_pair(wid, &a, &b);
+}
+
+int generic_wavelet_flen(int wid)
+{
+    int nr, nd;
+    if (!spline_pair(wid, &nr, &nd)) return 0;
+    const int taps = nr + 2 * nd - 1;
+    return (nr & 1) ? taps : taps + 1;
+}
+
+static void poly_mul(std::vector<long long> &a, const std::vector<long long> &b)
+{
+    std::vector<long long> out(a.size() + b.size() - 1, 0);
+    for (size_t i = 0; i < a.size(); ++i)
+        for (size_t j = 0; j < b.size(); ++j) out[i + j] += a[i] * b[j];
+    a.swap(out);
+}
+
+static long long binom(int n, int k)
+{
+    long long r = 1;
+    for (int i = 1; i <= k; ++i) r = r * (n - k + i) / i;
+    return r;
+}
+
+bool generic_wavelet_taps(int wid, int *F_out, double *dec_lo, double *rec_lo)
+{
+    int nr, nd;
+    if (!spline_pair(wid, &nr, &nd)) return false;
+    const int K = (nr + nd) / 2;
+    const std::vector<long long> one_z = {1, 1}, s4 = {-1, 2, -1};
+    std::vector<long long> q(2 * K - 1, 0), pw = {1};
+    for (int m = 0; m < K; ++m) {
+        long long w4 = 1;
+        for (int t = 0; t < K - 1 - m; ++t) w4 *= 4;
+        const int off = K - 1 - m;
+        for (size_t i = 0; i < pw.size(); ++i) q[off + i] += binom(K - 1 + m, m) * w4 * pw[i];
+        poly_mul(pw, s4);
+    }
+    std::vector<long long> dec = q, rec = {1};
+    for (int t = 0; t < nd; ++t) poly_mul(dec, one_z);
+    for (int t = 0; t < nr; ++t) poly_mul(rec, one_z);
+    const double dden = ldexp(1.0, nd + 2 * (K - 1)), rden = ldexp(1.0, nr);
+    const int taps = (int)dec.size();
+    const int F = (nr & 1) ? taps : taps + 1;
+    const int d0 = (nr & 1) ? 0 : 1;
+    const int r0 = (nr & 1) ? (F - (nr + 1)) / 2 : F / 2 - 1 - nr / 2;
+    const double s2 = 1.4142135623730951;  // sqrt(2) rounded to float64
+    for (int i = 0; i < SPIHTB_GEN_MAXF; ++i) dec_lo[i] = rec_lo[i] = 0.0;
+    for (int i = 0; i < taps; ++i) dec_lo[d0 + i] = s2 * (double)dec[i] / dden;   // integer < 2^53, power of two: one rounding
+    for (int i = 0; i <= nr; ++i) rec_lo[r0 + i] = s2 * (double)rec[i] / rden;
+    *F_out = F;
+    return true;
+}
+
+// ---------------------------------------------------------------- forward
+struct GenTaps {
+    int F;
+    double lo[SPIHTB_GEN_MAXF], hi[SPIHTB_GEN_MAXF];
+};
+
+template <typename Tin>
+__device__ __forceinline__ double gen_px(Tin v) { return (double)v; }
+template <>
+__device__ __forceinline__ double gen_px<uint8_t>(uint8_t v) { return (double)v / 255.0; }  // utils.py:19  im / 255
+
+// rows: lo / hi [z][i][x], i < bh, x < src_w
+template <typename Tin>
+__global__ void __launch_bounds__(256) gen_fwd_rows_kernel(const __grid_constant__ GenTaps t, const Tin *__restrict__ src,
+                                                           int src_h, int src_w, int bh, int mode,
+                                                           double *__restrict__ lo, double *__restrict__ hi)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y;
+    if (x >= src_w) return;
+    const int s = mode == SPIHTB_MODE_PERIODIZATION ? t.F / 2 : 1;
+    const int z = blockIdx.z;
+    const Tin *plane = src + (size_t)z * src_h * src_w;
+    double a = 0.0, d = 0.0;
+    for (int j = 0; j < t.F; ++j) {
+        const int r = ext_index(2 * i + s - j, src_h, mode);
+        const double v = gen_px<Tin>(plane[(size_t)r * src_w + x]);
+        a = fma(t.lo[j], v, a);
+        d = fma(t.hi[j], v, d);
+    }
+    const size_t o = ((size_t)z * bh + i) * src_w + x;
+    lo[o] = a;
+    hi[o] = d;
+}
+
+struct GenFwdCols {
+    const double *lo, *hi;   // [nz][bh][src_w]
+    int src_w, bh, bw, mode, C, last;
+    double *dst_ll;          // [nz][bh][bw] or null (last level: the LL corner of the array)
+    int32_t *coeffs;         // [nz][Hc][Wc]
+    int Hc, Wc, sh, sw;
+    double scale[8];
+    double q;
+};
+
+__global__ void __launch_bounds__(256) gen_fwd_cols_kernel(const __grid_constant__ GenTaps t, const __grid_constant__ GenFwdCols p)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y, z = blockIdx.z;
+    if (k >= p.bw) return;
+    const int s = p.mode == SPIHTB_MODE_PERIODIZATION ? t.F / 2 : 1;
+    const double *rl = p.lo + ((size_t)z * p.bh + i) * p.src_w;
+    const double *rh = p.hi + ((size_t)z * p.bh + i) * p.src_w;
+    double aa = 0.0, ad = 0.0, da = 0.0, dd = 0.0;
+    for (int j = 0; j < t.F; ++j) {
+        const int c = ext_index(2 * k + s - j, p.src_w, p.mode);
+        const double vl = rl[c], vh = rh[c];
+        aa = fma(t.lo[j], vl, aa);
+        ad = fma(t.hi[j], vl, ad);
+        da = fma(t.lo[j], vh, da);
+        dd = fma(t.hi[j], vh, dd);
+    }
+    // spiht_wrapper.py:9-11,167-172: ((m_c * x) * q).astype(int32); coeffs_to_array: 'ad' top right, 'da' bottom left
+    const double m = p.scale[z % p.C], q = p.q;
+    int32_t *arr = p.coeffs + (size_t)z * p.Hc * p.Wc;
+    arr[(size_t)i * p.Wc + p.sw + k] = __double2int_rz((m * ad) * q);
+    arr[(size_t)(p.sh + i) * p.Wc + k] = __double2int_rz((m * da) * q);
+    arr[(size_t)(p.sh + i) * p.Wc + p.sw + k] = __double2int_rz((m * dd) * q);
+    if (p.last)
+        arr[(size_t)i * p.Wc + k] = __double2int_rz((m * aa) * q);
+    else
+        p.dst_ll[((size_t)z * p.bh + i) * p.bw + k] = aa;
+}
+
+static int fill_taps_dec(int wid, GenTaps *t)
+{
+    double dl[SPIHTB_GEN_MAXF], rl[SPIHTB_GEN_MAXF];
+    if (!generic_wavelet_taps(wid, &t->F, dl, rl)) {
+        set_error("unknown wavelet id %d", wid);
+        return SPIHTB_EINVAL;
+    }
+    for (int i = 0; i < SPIHTB_GEN_MAXF; ++i) {
+        t->lo[i] = dl[i];
+        t->hi[i] = i < t->F ? (((t->F - 1 - i) & 1) ? -1.0 : 1.0) * rl[i] : 0.0;   // dec_hi[i] = (-1)^(F-1-i) rec_lo[i]
+    }
+    return SPIHTB_OK;
+}
+
+static int fill_taps_rec(int wid, GenTaps *t)
+{
+    double dl[SPIHTB_GEN_MAXF], rl[SPIHTB_GEN_MAXF];
+    if (!generic_wavelet_taps(wid, &t->F, dl, rl)) {
+        set_error("unknown wavelet id %d", wid);
+        return SPIHTB_EINVAL;
+    }
+    for (int i = 0; i < SPIHTB_GEN_MAXF; ++i) {
+        t->lo[i] = rl[i];
+        t->hi[i] = i < t->F ? ((i & 1) ? -1.0 : 1.0) * dl[i] : 0.0;                  // rec_hi[i] = (-1)^i dec_lo[i]
+    }
+    return SPIHTB_OK;
+}
+
+int launch_gen_fwd_level(spihtb_ctx *ctx, int wid, const GenFwdLevel &a, int nz)
+{
+    GenTaps t;
+    int rc = fill_taps_dec(wid, &t);
+    if (rc) return rc;
+    if (a.bh > 65535 || nz > 65535) {
+        set_error("generic-wavelet transform: more than 65535 band rows or planes");
+        return SPIHTB_ESHAPE;
+    }
+    const size_t plane = (size_t)nz * a.bh * a.src_w;
+    rc = ctx->ensure(ctx->tail, 2 * plane * sizeof(double) + 256);
+    if (rc) return rc;
+    double *lo = static_cast<double *>(ctx->tail.p), *hi = lo + plane;
+    const dim3 g1((a.src_w + 255) / 256, a.bh, nz), g2((a.bw + 255) / 256, a.bh, nz);
+    switch (a.src_dtype) {
+        case SPIHTB_F64:
+            gen_fwd_rows_kernel<double><<<g1, 256, 0, ctx->stream>>>(t, static_cast<const double *>(a.src), a.src_h, a.src_w,
+                                                                    a.bh, a.mode, lo, hi);
+            break;
+        case SPIHTB_F32:
+            gen_fwd_rows_kernel<float><<<g1, 256, 0, ctx->stream>>>(t, static_cast<const float *>(a.src), a.src_h, a.src_w,
+                                                                   a.bh, a.mode, lo, hi);
+            break;
+        case SPIHTB_U8:
+            gen_fwd_rows_kernel<uint8_t><<<g1, 256, 0, ctx->stream>>>(t, static_cast<const uint8_t *>(a.src), a.src_h,
+                                                                     a.src_w, a.bh, a.mode, lo, hi);
+            break;
+        default:
+            set_error("unknown pixel dtype %d", a.src_dtype);
+            return SPIHTB_EINVAL;
+    }
+    GenFwdCols p;
+    p.lo = lo; p.hi = hi;
+    p.src_w = a.src_w; p.bh = a.bh; p.bw = a.bw; p.mode = a.mode; p.C = a.C; p.last = a.last;
+    p.dst_ll = a.dst_ll;
+    p.coeffs = a.coeffs;
+    p.Hc = a.Hc; p.Wc = a.Wc; p.sh = a.sh; p.sw = a.sw;
+    for (int c = 0; c < 8; ++c) p.scale[c] = a.scale[c];
+    p.q = a.q;
+    gen_fwd_cols_kernel<<<g2, 256, 0, ctx->stream>>>(t, p);
+    ctx->launches += 2;
+    SPIHTB_CUDA_CHECK(cudaGetLastError());
+    return SPIHTB_OK;
+}
+
+// ---------------------------------------------------------------- inverse
+struct GenInvCols {
+    const double *src_a;     // [nz][a_h][a_w] or null (coarsest level: LL corner of the array, dequantised)
+    int a_h, a_w;
+    const int32_t *coeffs;
+    int Hc, Wc, sh, sw, bh, bw, ow, mode, C;
+    double rscale[8];
+    double rq;
+    const uint8_t *blk;      // optional marks of the 64x64 blocks of the array that were written (others read as zero)
+    int BH, BW;
+    double *xlo, *xhi;       // [nz][bh][ow]
+};
+
+// synthesis (non-periodization): rec[n] = sum_t g[t] c[(n + F-2 - t)/2]   for even n+F-2-t, 0 <= k < m
+// periodization:                 rec[n] = sum_t g[t] c[((n + F/2-1 - t)/2) mod m]
+__global__ void __launch_bounds__(256) gen_inv_cols_kernel(const __grid_constant__ GenTaps t, const __grid_constant__ GenInvCols p)
+{
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y, z = blockIdx.z;
+    if (n >= p.ow) return;
+    const bool per = p.mode == SPIHTB_MODE_PERIODIZATION;
+    const int base = n + (per ? t.F / 2 - 1 : t.F - 2);
+    const double rm = p.rscale[z % p.C], rq = p.rq;
+    const int32_t *arr = p.coeffs + (size_t)z * p.Hc * p.Wc;
+    const uint8_t *bm = p.blk ? p.blk + (size_t)z * p.BH * p.BW : nullptr;
+    auto coef = [&](int r, int c) -> double {
+        if (bm && !bm[(size_t)(r >> 6) * p.BW + (c >> 6)]) return 0.0;
+        return ((double)arr[(size_t)r * p.Wc + c] * rm) * rq;   // spiht_wrapper.py:270-274, as in dwt_inv.cu
+    };
+    double lo = 0.0, hi = 0.0;
+    for (int tt = (base & 1); tt < t.F; tt += 2) {   // the taps with even base - tt
+        int k = (base - tt) / 2;                    // exact (also when negative: periodization only)
+        if (per) {
+            k %= p.bw;
+            if (k < 0) k += p.bw;
+        } else if (k < 0 || k >= p.bw) {
+            continue;
+        }
+        const double aa = p.src_a ? p.src_a[((size_t)z * p.a_h + i) * p.a_w + k] : ((double)arr[(size_t)i * p.Wc + k] * rm) * rq;
+        const double ad = coef(i, p.sw + k), da = coef(p.sh + i, k), dd = coef(p.sh + i, p.sw + k);
+        lo = fma(t.lo[tt], aa, lo);
+        lo = fma(t.hi[tt], ad, lo);
+        hi = fma(t.lo[tt], da, hi);
+        hi = fma(t.hi[tt], dd, hi);
+    }
+    const size_t o = ((size_t)z * p.bh + i) * p.ow + n;
+    p.xlo[o] = lo;
+    p.xhi[o] = hi;
+}
+
+template <typename Tout>
+__global__ void __launch_bounds__(256) gen_inv_rows_kernel(const __grid_constant__ GenTaps t, const double *__restrict__ xlo,
+                                                           const double *__restrict__ xhi, int bh, int oh, int ow, int mode,
+                                                           Tout *__restrict__ dst)
+{
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y, z = blockIdx.z;
+    if (n >= ow) return;
+    const bool per = mode == SPIHTB_MODE_PERIODIZATION;
+    const int base = r + (per ? t.F / 2 - 1 : t.F - 2);
+    double v = 0.0;
+    for (int tt = (base & 1); tt < t.F; tt += 2) {
+        int k = (base - tt) / 2;
+        if (per) {
+            k %= bh;
+            if (k < 0) k += bh;
+        } else if (k < 0 || k >= bh) {
+            continue;
+        }
+        const size_t o = ((size_t)z * bh + k) * ow + n;
+        v = fma(t.lo[tt], xlo[o], v);
+        v = fma(t.hi[tt], xhi[o], v);
+    }
+    dst[((size_t)z * oh + r) * ow + n] = (Tout)v;
+}
+
+int launch_gen_inv_level(spihtb_ctx *ctx, int wid, const GenInvLevel &a, int nz)
+{
+    GenTaps t;
+    int rc = fill_taps_rec(wid, &t);
+    if (rc) return rc;
+    if (a.bh > 65535 || a.oh > 65535 || nz > 65535) {
+        set_error("generic-wavelet transform: more than 65535 rows or planes");
+        return SPIHTB_ESHAPE;
+    }
+    const size_t plane = (size_t)nz * a.bh * a.ow;
+    rc = ctx->ensure(ctx->tail, 2 * plane * sizeof(double) + 256);
+    if (rc) return rc;
+    GenInvCols p;
+    p.src_a = a.src_a; p.a_h = a.a_h; p.a_w = a.a_w;
+    p.coeffs = a.coeffs;
+    p.Hc = a.Hc; p.Wc = a.Wc; p.sh = a.sh; p.sw = a.sw; p.bh = a.bh; p.bw = a.bw; p.ow = a.ow; p.mode = a.mode; p.C = a.C;
+    for (int c = 0; c < 8; ++c) p.rscale[c] = a.rscale[c];
+    p.rq = a.rq;
+    p.blk = a.blk; p.BH = a.BH; p.BW = a.BW;
+    p.xlo = static_cast<double *>(ctx->tail.p);
+    p.xhi = p.xlo + plane;
+    gen_inv_cols_kernel<<<dim3((a.ow + 255) / 256, a.bh, nz), 256, 0, ctx->stream>>>(t, p);
+    const dim3 g2((a.ow + 255) / 256, a.oh, nz);
+    if (a.out_f32)
+        gen_inv_rows_kernel<float><<<g2, 256, 0, ctx->stream>>>(t, p.xlo, p.xhi, a.bh, a.oh, a.ow, a.mode,
+                                                               static_cast<float *>(a.dst));
+    else
+        gen_inv_rows_kernel<double><<<g2, 256, 0, ctx->stream>>>(t, p.xlo, p.xhi, a.bh, a.oh, a.ow, a.mode,
+                                                                static_cast<double *>(a.dst));
+    ctx->launches += 2;
+    SPIHTB_CUDA_CHECK(cudaGetLastError());
+    return SPIHTB_OK;
+}
+
+}  // namespace spihtb

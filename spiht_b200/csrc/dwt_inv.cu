@@ -495,7 +495,23 @@ int launch_inverse(spihtb_ctx *ctx, const int32_t *coeffs, const XformArgs &x, v
             case SPIHTB_WAVELET_BIOR22: rc = launch_inv_level<SPIHTB_WAVELET_BIOR22>(ctx, k, nz, out_f32, fuse, pix_f32); break;
             case SPIHTB_WAVELET_BIOR44: rc = launch_inv_level<SPIHTB_WAVELET_BIOR44>(ctx, k, nz, out_f32); break;
             case SPIHTB_WAVELET_BIOR68: rc = launch_inv_level<SPIHTB_WAVELET_BIOR68>(ctx, k, nz, out_f32); break;
-            default: set_error("unknown wavelet id %d", g.wavelet); rc = SPIHTB_EINVAL;
+            default:
+                if (wavelet_is_generic(g.wavelet)) {   // the rest of the bior family (dwt_gen.cu)
+                    GenInvLevel a;
+                    a.src_a = k.src_a; a.a_h = k.a_h; a.a_w = k.a_w;
+                    a.coeffs = k.coeffs;
+                    a.Hc = k.Hc; a.Wc = k.Wc; a.sh = k.sh; a.sw = k.sw; a.bh = k.bh; a.bw = k.bw; a.oh = k.oh; a.ow = k.ow;
+                    a.mode = k.mode; a.C = k.C;
+                    for (int c = 0; c < 8; ++c) a.rscale[c] = k.rscale[c];
+                    a.rq = k.rq;
+                    a.blk = k.blk; a.BH = k.BH; a.BW = k.BW;
+                    a.dst = k.dst;
+                    a.out_f32 = out_f32;
+                    rc = launch_gen_inv_level(ctx, g.wavelet, a, nz);
+                } else {
+                    set_error("unknown wavelet id %d", g.wavelet);
+                    rc = SPIHTB_EINVAL;
+                }
         }
         if (rc) return rc;
         src = static_cast<const double *>(k.dst);

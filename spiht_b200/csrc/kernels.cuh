@@ -97,6 +97,36 @@ struct PyrFuse {
 int launch_forward(spihtb_ctx *ctx, const void *pixels, const XformArgs &x, int32_t *coeffs,
                    const PyrFuse *pf = nullptr);
 int launch_inverse(spihtb_ctx *ctx, const int32_t *coeffs, const XformArgs &x, void *pixels_out);
+// ---- dwt_gen.cu: the rest of the bior family (filter length and taps as launch parameters)
+#define SPIHTB_GEN_MAXF 20
+bool wavelet_is_generic(int wid);
+// PyWavelets' dec_lo / rec_lo of a generic wavelet (zero padding included), SPIHTB_GEN_MAXF entries each
+bool generic_wavelet_taps(int wid, int *F, double *dec_lo, double *rec_lo);
+struct GenFwdLevel {
+    const void *src;       // [nz][src_h][src_w] of src_dtype
+    int src_dtype;
+    int src_h, src_w, bh, bw;
+    double *dst_ll;        // [nz][bh][bw] float64 scratch (unused at the last level)
+    int32_t *coeffs;       // [nz][Hc][Wc]
+    int Hc, Wc, sh, sw, mode, C, last;
+    double scale[8];
+    double q;
+};
+int launch_gen_fwd_level(spihtb_ctx *ctx, int wid, const GenFwdLevel &a, int nz);
+struct GenInvLevel {
+    const double *src_a;   // [nz][a_h][a_w], or null at the coarsest level (LL corner of the array)
+    int a_h, a_w;
+    const int32_t *coeffs;
+    int Hc, Wc, sh, sw, bh, bw, oh, ow, mode, C;
+    double rscale[8];
+    double rq;
+    const uint8_t *blk;    // optional block marks (see DecArgs)
+    int BH, BW;
+    void *dst;             // [nz][oh][ow] float64, or float32 when out_f32
+    bool out_f32;
+};
+int launch_gen_inv_level(spihtb_ctx *ctx, int wid, const GenInvLevel &a, int nz);
+
 // dwt_fwd2.cu: levels 1 and 2 fused (TMA-staged tiles); *done = false when the geometry takes the other path
 int launch_forward_fused12(spihtb_ctx *ctx, const void *src, int pixel_dtype, const XformArgs &x, int32_t *coeffs,
                            double *ll2, const PyrFuse *pf, const double *u8lut, bool *done);

@@ -125,6 +125,18 @@ static inline int wavelet_flen(int wid)
         case SPIHTB_WAVELET_BIOR22: return 6;
         case SPIHTB_WAVELET_BIOR44: return 10;
         case SPIHTB_WAVELET_BIOR68: return 18;
+        // biorNr.Nd, the rest of the family (dwt_gen.cu): Nr + 2 Nd - 1 taps, padded to an even length
+        case SPIHTB_WAVELET_BIOR11: return 2;
+        case SPIHTB_WAVELET_BIOR13: return 6;
+        case SPIHTB_WAVELET_BIOR15: return 10;
+        case SPIHTB_WAVELET_BIOR24: return 10;
+        case SPIHTB_WAVELET_BIOR26: return 14;
+        case SPIHTB_WAVELET_BIOR28: return 18;
+        case SPIHTB_WAVELET_BIOR31: return 4;
+        case SPIHTB_WAVELET_BIOR33: return 8;
+        case SPIHTB_WAVELET_BIOR35: return 12;
+        case SPIHTB_WAVELET_BIOR37: return 16;
+        case SPIHTB_WAVELET_BIOR39: return 20;
         default: return 0;
     }
 }

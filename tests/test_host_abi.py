@@ -27,7 +27,7 @@ def test_geom_struct_matches_header():
     assert ctypes.sizeof(_lib.Geom) == 4 * (11 + 6 * _lib.MAX_LEVELS)
 
 
-@pytest.mark.parametrize("wavelet", ["bior2.2", "bior4.4", "bior6.8"])
+@pytest.mark.parametrize("wavelet", sorted(__import__("spiht_b200")._lib.WAVELET_IDS))
 @pytest.mark.parametrize("mode", ["reflect", "symmetric", "periodization"])
 def test_plan_matches_oracle_geometry(wavelet, mode):
     from oracle import dwt_ref
@@ -132,3 +132,28 @@ def test_spiht_alias_package_matches_reference_imports():
     assert spiht_rs.encode is spiht_b200.encode and hasattr(spiht_rs, "decode_with_metadata")
     with pytest.raises(ValueError):
         convert(np.zeros((3, 4, 4)), "RGB", "CIE Lab")     # color_models.py:7-10
+
+
+def test_library_filter_banks_equal_the_oracle_tables():
+    """spihtb_wavelet_filters: the filter bank the kernels use, per wavelet id, against oracle/dwt_ref.py -- the three
+    stored tables digit for digit, the derived spline pairs to rounding (two independent derivations: exact integer
+    polynomials in C++, Fractions in Python)."""
+    import ctypes
+    import numpy as np
+    from oracle import dwt_ref
+    from spiht_b200 import _lib
+    assert set(_lib.WAVELET_IDS) == set(dwt_ref.WAVELETS)
+    L = _lib.lib()
+    for name, wid in _lib.WAVELET_IDS.items():
+        F = ctypes.c_int32()
+        dl = (ctypes.c_double * 20)()
+        rl = (ctypes.c_double * 20)()
+        assert L.spihtb_wavelet_filters(wid, ctypes.byref(F), dl, rl) == 0, name
+        wv = dwt_ref.Wavelet(name)
+        assert F.value == wv.dec_len
+        got_d, got_r = np.array(dl[:F.value]), np.array(rl[:F.value])
+        tol = 0.0 if name in ("bior2.2", "bior4.4", "bior6.8") else 4e-16
+        assert np.abs(got_d - wv.dec_lo).max() <= tol and np.abs(got_r - wv.rec_lo).max() <= tol, name
+        assert np.array_equal(got_d == 0.0, wv.dec_lo == 0.0) and np.array_equal(got_r == 0.0, wv.rec_lo == 0.0)
+    F = ctypes.c_int32()
+    assert L.spihtb_wavelet_filters(99, ctypes.byref(F), dl, rl) != 0

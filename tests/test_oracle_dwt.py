@@ -7,7 +7,7 @@ import pytest
 from oracle import dwt_ref as d, ipt_ref, wrapper_ref
 
 
-@pytest.mark.parametrize("name", ["bior2.2", "bior4.4", "bior6.8"])
+@pytest.mark.parametrize("name", d.WAVELETS)
 def test_filter_identities(name):
     wv = d.Wavelet(name)
     assert abs(wv.dec_lo.sum() - 2 ** 0.5) < 1e-12
@@ -16,7 +16,7 @@ def test_filter_identities(name):
     assert abs(wv.rec_hi.sum()) < 1e-11
 
 
-@pytest.mark.parametrize("name", ["bior2.2", "bior4.4", "bior6.8"])
+@pytest.mark.parametrize("name", d.WAVELETS)
 @pytest.mark.parametrize("mode", d.MODES)
 def test_perfect_reconstruction_1d(name, mode):
     rng = np.random.default_rng(0)
@@ -143,7 +143,7 @@ def test_lifting_factorisation_reproduces_the_filter_bank(name, lift, shift, tol
     assert np.abs(hi[0][idx + shift] + dd[idx]).max() < tol
 
 
-@pytest.mark.parametrize("name,nr,nd", [("bior2.2", 2, 2), ("bior4.4", 4, 4), ("bior6.8", 6, 8)])
+@pytest.mark.parametrize("name,nr,nd", [(n, int(n[4]), int(n[6])) for n in d.WAVELETS])
 def test_filter_tables_have_the_vanishing_moments_their_name_states(name, nr, nd):
     """biorNr.Nd: dec_lo has Nd zeros at z = -1 and rec_lo has Nr (so that the decomposition / reconstruction
     wavelets have Nd / Nr vanishing moments) -- and not one more.  Together with perfect reconstruction,
@@ -157,3 +157,34 @@ def test_filter_tables_have_the_vanishing_moments_their_name_states(name, nr, nd
         assert max(moms[:nz]) < 1e-9, moms
         assert moms[nz] > 1e-2, moms
         assert np.allclose(f[np.abs(f) > 0], f[np.abs(f) > 0][::-1], atol=0, rtol=0)   # exactly symmetric
+
+
+def test_derived_spline_pair_equals_the_stored_bior22_table_and_remembered_pywavelets_values():
+    """oracle/dwt_ref._spline_bior derives the spline members of the family from the CDF construction; the derivation
+    reproduces the stored bior2.2 table exactly and the PyWavelets values of other members as far as they are
+    remembered (4 digits) -- layout (zero padding, centring) included."""
+    dl, rl = d._spline_bior(2, 2)
+    assert dl == list(d._FILTERS["bior2.2"][0]) and rl == list(d._FILTERS["bior2.2"][1])
+    known = {
+        "bior1.3": ([-0.0884, 0.0884, 0.7071, 0.7071, 0.0884, -0.0884], [0, 0, 0.7071, 0.7071, 0, 0]),
+        "bior3.1": ([-0.3536, 1.0607, 1.0607, -0.3536], [0.1768, 0.5303, 0.5303, 0.1768]),
+        "bior2.4": ([0, 0.0331, -0.0663, -0.1768, 0.4198, 0.9944, 0.4198, -0.1768, -0.0663, 0.0331],
+                    [0, 0, 0, 0.3536, 0.7071, 0.3536, 0, 0, 0, 0]),
+        "bior3.3": ([0.0663, -0.1989, -0.1547, 0.9944, 0.9944, -0.1547, -0.1989, 0.0663],
+                    [0, 0, 0.1768, 0.5303, 0.5303, 0.1768, 0, 0]),
+    }
+    for name, (kd, kr) in known.items():
+        wv = d.Wavelet(name)
+        assert np.abs(wv.dec_lo - np.array(kd)).max() < 6e-5 and np.abs(wv.rec_lo - np.array(kr)).max() < 6e-5, name
+    assert {d.Wavelet(n).dec_len for n in ("bior1.1", "bior1.5", "bior2.6", "bior2.8", "bior3.5", "bior3.7", "bior3.9")} \
+        == {2, 10, 14, 18, 12, 16, 20}
+
+
+@pytest.mark.parametrize("name", d.WAVELETS)
+def test_two_dimensional_round_trip_every_wavelet(name):
+    rng = np.random.default_rng(5)
+    x = rng.normal(size=(2, 45, 70))
+    for mode in d.MODES:
+        co = d.wavedec2(x, name, mode, 2)
+        r = d.waverec2(co, name, mode)
+        assert np.abs(r[:, :45, :70] - x).max() < 1e-10
