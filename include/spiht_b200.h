@@ -44,7 +44,7 @@ extern "C" {
 #define SPIHTB_WAVELET_BIOR22 0
 #define SPIHTB_WAVELET_BIOR44 1
 #define SPIHTB_WAVELET_BIOR68 2
-/* the rest of PyWavelets' bior family (spline pairs; separable kernels with the taps as launch parameters) */
+/* the rest of PyWavelets' bior family (spline pairs derived on the host; separable kernels with the taps as launch parameters) */
 #define SPIHTB_WAVELET_BIOR11 3
 #define SPIHTB_WAVELET_BIOR13 4
 #define SPIHTB_WAVELET_BIOR15 5
@@ -56,6 +56,7 @@ extern "C" {
 #define SPIHTB_WAVELET_BIOR35 11
 #define SPIHTB_WAVELET_BIOR37 12
 #define SPIHTB_WAVELET_BIOR39 13
+#define SPIHTB_WAVELET_BIOR55 14   /* not a spline pair: stored table */
 /* boundary mode ids (PyWavelets names, spiht_wrapper.py:57 `mode`) */
 #define SPIHTB_MODE_REFLECT 0
 #define SPIHTB_MODE_SYMMETRIC 1

@@ -13,9 +13,9 @@ OK, EINVAL, ELL, EGEOM, ESHAPE, ECAP, ECUDA, ENOMEM, ELEVEL = range(9)
 MAX_LEVELS = 24
 
 WAVELET_IDS = {"bior2.2": 0, "bior4.4": 1, "bior6.8": 2,
-               # the rest of PyWavelets' bior family (csrc/dwt_gen.cu); bior5.5 is not a spline pair and is not offered
+               # the rest of PyWavelets' bior family (csrc/dwt_gen.cu)
                "bior1.1": 3, "bior1.3": 4, "bior1.5": 5, "bior2.4": 6, "bior2.6": 7, "bior2.8": 8,
-               "bior3.1": 9, "bior3.3": 10, "bior3.5": 11, "bior3.7": 12, "bior3.9": 13}
+               "bior3.1": 9, "bior3.3": 10, "bior3.5": 11, "bior3.7": 12, "bior3.9": 13, "bior5.5": 14}
 MODE_IDS = {"reflect": 0, "symmetric": 1, "periodization": 2}
 COLOR_NONE, COLOR_IPT = 0, 1
 F32, F64, U8 = 0, 1, 2   # U8: forward direction only (pixels / 255 in float64, as utils.imload)

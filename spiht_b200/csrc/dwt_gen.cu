@@ -1,4 +1,4 @@
-// The rest of PyWavelets' bior family (bior1.1 1.3 1.5 2.4 2.6 2.8 3.1 3.3 3.5 3.7 3.9): filter banks derived on the
+// The rest of PyWavelets' bior family (bior1.1 1.3 1.5 2.4 2.6 2.8 3.1 3.3 3.5 3.7 3.9 derived, 5.5 stored): filter banks on the
 // host, and one pair of separable kernels per transform level with the filter length and the taps as launch
 // parameters ("remaining bior family"; the reference passes SpihtSettings.wavelet straight
 // to pywt.wavedec2 / waverec2, spiht_wrapper.py:163,276).
@@ -50,15 +50,7 @@ static bool spline_pair(int wid, int *nr, int *nd)
 bool wavelet_is_generic(int wid)
 {
     int a, b;
-    return spline_pair(wid, &a, &b);
-}
-
-int generic_wavelet_flen(int wid)
-{
-    int nr, nd;
-    if (!spline_pair(wid, &nr, &nd)) return 0;
-    const int taps = nr + 2 * nd - 1;
-    return (nr & 1) ? taps : taps + 1;
+    return wid == SPIHTB_WAVELET_BIOR55 || spline_pair(wid, &a, &b);
 }
 
 static void poly_mul(std::vector<long long> &a, const std::vector<long long> &b)
@@ -79,6 +71,21 @@ static long long binom(int n, int k)
 bool generic_wavelet_taps(int wid, int *F_out, double *dec_lo, double *rec_lo)
 {
     int nr, nd;
+    if (wid == SPIHTB_WAVELET_BIOR55) {   // not a spline pair: PyWavelets' table (9 / 11 taps in a length of 12)
+        static const double dl[12] = {0.0, 0.0, 0.03968708834740544, 0.007948108637240322, -0.05446378846823691,
+                                      0.34560528195603346, 0.7366601814282105, 0.34560528195603346,
+                                      -0.05446378846823691, 0.007948108637240322, 0.03968708834740544, 0.0};
+        static const double rl[12] = {0.013456709459118716, -0.002694966880111507, -0.13670658466432914,
+                                      -0.09350469740093886, 0.47680326579848425, 0.8995061097486484,
+                                      0.47680326579848425, -0.09350469740093886, -0.13670658466432914,
+                                      -0.002694966880111507, 0.013456709459118716, 0.0};
+        for (int i = 0; i < SPIHTB_GEN_MAXF; ++i) {
+            dec_lo[i] = i < 12 ? dl[i] : 0.0;
+            rec_lo[i] = i < 12 ? rl[i] : 0.0;
+        }
+        *F_out = 12;
+        return true;
+    }
     if (!spline_pair(wid, &nr, &nd)) return false;
     const int K = (nr + nd) / 2;
     const std::vector<long long> one_z = {1, 1}, s4 = {-1, 2, -1};

@@ -137,6 +137,7 @@ static inline int wavelet_flen(int wid)
         case SPIHTB_WAVELET_BIOR35: return 12;
         case SPIHTB_WAVELET_BIOR37: return 16;
         case SPIHTB_WAVELET_BIOR39: return 20;
+        case SPIHTB_WAVELET_BIOR55: return 12;
         default: return 0;
     }
 }

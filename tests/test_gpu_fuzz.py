@@ -35,7 +35,7 @@ def _family_cases():
     rng = np.random.default_rng(77)
     out = []
     for wavelet in ["bior1.1", "bior1.3", "bior1.5", "bior2.4", "bior2.6", "bior2.8", "bior3.1", "bior3.3", "bior3.5",
-                    "bior3.7", "bior3.9"]:
+                    "bior3.7", "bior3.9", "bior5.5"]:
         for mode in ["reflect", "symmetric", "periodization"]:
             c = int(rng.integers(1, 4))
             h, w = int(rng.integers(60, 200)), int(rng.integers(60, 200))

@@ -152,7 +152,7 @@ def test_library_filter_banks_equal_the_oracle_tables():
         wv = dwt_ref.Wavelet(name)
         assert F.value == wv.dec_len
         got_d, got_r = np.array(dl[:F.value]), np.array(rl[:F.value])
-        tol = 0.0 if name in ("bior2.2", "bior4.4", "bior6.8") else 4e-16
+        tol = 0.0 if name in ("bior2.2", "bior4.4", "bior6.8", "bior5.5") else 4e-16
         assert np.abs(got_d - wv.dec_lo).max() <= tol and np.abs(got_r - wv.rec_lo).max() <= tol, name
         assert np.array_equal(got_d == 0.0, wv.dec_lo == 0.0) and np.array_equal(got_r == 0.0, wv.rec_lo == 0.0)
     F = ctypes.c_int32()
