@@ -332,13 +332,23 @@ struct GenInvCols {
 
 // synthesis (non-periodization): rec[n] = sum_t g[t] c[(n + F-2 - t)/2]   for even n+F-2-t, 0 <= k < m
 // periodization:                 rec[n] = sum_t g[t] c[((n + F/2-1 - t)/2) mod m]
+// A thread takes GEN_C consecutive outputs of one band row: the GEN_C / 2 + F / 2 (or so) coefficients per band they
+// need are loaded and dequantised once (one output per thread dequantised every coefficient F times: the kernel was
+// bound by the int -> float64 conversions and multiplies, not by memory).  blockDim (64, 4): 64 x GEN_C outputs of four
+// band rows, so that the short rows of the coarse levels still fill a block.  Indexing as in gen_inv_rows_kernel.
+constexpr int GEN_C = 4;
+template <int F, bool PER>
 __global__ void __launch_bounds__(256) gen_inv_cols_kernel(const __grid_constant__ GenTaps t, const __grid_constant__ GenInvCols p)
 {
-    const int n = blockIdx.x * blockDim.x + threadIdx.x;
-    const int i = blockIdx.y, z = blockIdx.z;
-    if (n >= p.ow) return;
-    const bool per = p.mode == SPIHTB_MODE_PERIODIZATION;
-    const int base = n + (per ? t.F / 2 - 1 : t.F - 2);
+    static_assert(GEN_C % 2 == 0, "n0 must be even");
+    const int n0 = (blockIdx.x * 64 + threadIdx.x) * GEN_C;
+    const int i = blockIdx.y * 4 + threadIdx.y, z = blockIdx.z;
+    if (n0 >= p.ow || i >= p.bh) return;
+    constexpr int OFF = PER ? F / 2 - 1 : F - 2;
+    constexpr int DMIN = OFF - (F - 1), DMAX = OFF + GEN_C - 1;
+    constexpr int KLO = DMIN >= 0 ? DMIN / 2 : -((-DMIN) / 2);
+    constexpr int KHI = DMAX / 2;
+    constexpr int NK = KHI - KLO + 1;
     const double rm = p.rscale[z % p.C], rq = p.rq;
     const int32_t *arr = p.coeffs + (size_t)z * p.Hc * p.Wc;
     const uint8_t *bm = p.blk ? p.blk + (size_t)z * p.BH * p.BW : nullptr;
@@ -351,25 +361,43 @@ __global__ void __launch_bounds__(256) gen_inv_cols_kernel(const __grid_constant
         return ((double)row[c] * rm) * rq;   // spiht_wrapper.py:270-274, as in dwt_inv.cu
     };
     const double *row_a = p.src_a ? p.src_a + ((size_t)z * p.a_h + i) * p.a_w : nullptr;
-    double lo = 0.0, hi = 0.0;
-    for (int tt = (base & 1); tt < t.F; tt += 2) {   // the taps with even base - tt
-        int k = (base - tt) / 2;                    // exact (also when negative: periodization only)
-        if (per) {
+    double aa[NK], ad[NK], da[NK], dd[NK];
+#pragma unroll
+    for (int m = 0; m < NK; ++m) {
+        int k = n0 / 2 + KLO + m;
+        bool in = true;
+        if (PER) {
             k %= p.bw;
             if (k < 0) k += p.bw;
-        } else if (k < 0 || k >= p.bw) {
-            continue;
+        } else {
+            in = k >= 0 && k < p.bw;   // taps outside the band contribute nothing
         }
-        const double aa = row_a ? row_a[k] : ((double)row_t[k] * rm) * rq;
-        const double ad = coef(row_t, bm_t, p.sw + k), da = coef(row_b, bm_b, k), dd = coef(row_b, bm_b, p.sw + k);
-        lo = fma(t.lo[tt], aa, lo);
-        lo = fma(t.hi[tt], ad, lo);
-        hi = fma(t.lo[tt], da, hi);
-        hi = fma(t.hi[tt], dd, hi);
+        aa[m] = ad[m] = da[m] = dd[m] = 0.0;
+        if (in) {
+            aa[m] = row_a ? row_a[k] : ((double)row_t[k] * rm) * rq;
+            ad[m] = coef(row_t, bm_t, p.sw + k);
+            da[m] = coef(row_b, bm_b, k);
+            dd[m] = coef(row_b, bm_b, p.sw + k);
+        }
     }
-    const size_t o = ((size_t)z * p.bh + i) * p.ow + n;
-    p.xlo[o] = lo;
-    p.xhi[o] = hi;
+    const size_t o = ((size_t)z * p.bh + i) * p.ow + n0;
+#pragma unroll
+    for (int u = 0; u < GEN_C; ++u) {
+        if (n0 + u >= p.ow) break;
+        double lo = 0.0, hi = 0.0;
+#pragma unroll
+        for (int tt = 0; tt < F; ++tt) {
+            if (((OFF + u - tt) & 1) == 0) {
+                const int m = (OFF + u - tt) / 2 - KLO;   // exact: the numerator is even
+                lo = fma(t.lo[tt], aa[m], lo);
+                lo = fma(t.hi[tt], ad[m], lo);
+                hi = fma(t.lo[tt], da[m], hi);
+                hi = fma(t.hi[tt], dd[m], hi);
+            }
+        }
+        p.xlo[o + u] = lo;
+        p.xhi[o + u] = hi;
+    }
 }
 
 // GEN_R consecutive output rows of one column per thread: the GEN_R / 2 + F / 2 (or so) rows of xlo / xhi they need are
@@ -441,9 +469,23 @@ int launch_gen_inv_level(spihtb_ctx *ctx, int wid, const GenInvLevel &a, int nz)
     p.blk = a.blk; p.BH = a.BH; p.BW = a.BW;
     p.xlo = static_cast<double *>(ctx->tail.p);
     p.xhi = p.xlo + plane;
-    gen_inv_cols_kernel<<<dim3((a.ow + 255) / 256, a.bh, nz), 256, 0, ctx->stream>>>(t, p);
-    const dim3 g2((a.ow + 255) / 256, (a.oh + GEN_R - 1) / GEN_R, nz);
     const bool per = a.mode == SPIHTB_MODE_PERIODIZATION;
+    {
+        const dim3 g1((a.ow + 64 * GEN_C - 1) / (64 * GEN_C), (a.bh + 3) / 4, nz);
+        auto cols = [&](auto fc) {
+            constexpr int F = decltype(fc)::value;
+            if (per)
+                gen_inv_cols_kernel<F, true><<<g1, dim3(64, 4), 0, ctx->stream>>>(t, p);
+            else
+                gen_inv_cols_kernel<F, false><<<g1, dim3(64, 4), 0, ctx->stream>>>(t, p);
+            return true;
+        };
+        if (!for_flen(t.F, cols)) {
+            set_error("generic-wavelet transform: filter length %d not supported", t.F);
+            return SPIHTB_EINVAL;
+        }
+    }
+    const dim3 g2((a.ow + 255) / 256, (a.oh + GEN_R - 1) / GEN_R, nz);
     auto rows = [&](auto fc) {
         constexpr int F = decltype(fc)::value;
         auto go = [&](auto *out, auto per_c) {
