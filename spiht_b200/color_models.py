@@ -1,8 +1,9 @@
 """spiht/color_models.py of the reference.  Only RGB <-> IPT is supported: it is the one colour model on the
 accelerated path (north star).  `convert(im, src, dest)` keeps the reference's signature (color_models.py:6-13,
 CHW in, CHW out) and raises the reference's ValueError for every other model; the arithmetic runs on the GPU
-(spihtb_convert_color).  Inside encode_image / decode_image the conversion is fused into the transform
-kernels' level-1 loads and stores, not run as a separate pass.
+(spihtb_convert_color).  Inside encode_image / decode_image the library runs the same kernels as a pass of its own
+before the level-1 analysis / behind the level-1 synthesis (csrc/color.cu; not fused into the transform kernels,
+DESIGN.md 4.8), without leaving the device.
 """
 import ctypes
 

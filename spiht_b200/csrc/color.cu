@@ -1,7 +1,9 @@
-// RGB <-> IPT as stand-alone passes (spihtb_convert_color; replaces spiht/color_models.py:6-13 ->
-// colour.convert(.., 'RGB', 'IPT') and back, colour-science 0.4.4).  The image path does not launch these:
-// there the forward transform converts as it loads the level-1 rows and the inverse transform as it stores
-// them (ipt.cuh holds the per-pixel arithmetic all of them share).
+// RGB <-> IPT as stand-alone passes (replaces spiht/color_models.py:6-13 -> colour.convert(.., 'RGB', 'IPT') and
+// back, colour-science 0.4.4).  Called by spihtb_convert_color and by the image path: launch_forward runs
+// rgb_to_ipt_kernel into a float64 scratch image before the level-1 transform (dwt_fwd.cu) and launch_inverse runs
+// ipt_to_rgb_kernel behind the level-1 synthesis (dwt_inv.cu).  The passes are NOT fused into the transform kernels
+// (a warp of the transform owns one plane, the powers need all three); ipt.cuh holds the per-pixel
+// arithmetic.
 #include <algorithm>
 
 #include "common.cuh"
