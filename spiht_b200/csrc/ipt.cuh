@@ -1,5 +1,5 @@
-// Per-pixel RGB <-> IPT arithmetic (float64), shared by the stand-alone colour kernels (color.cu) and the
-// transform kernels that fuse the conversion into their level-1 loads / stores.
+// Per-pixel RGB <-> IPT arithmetic (float64) of the colour kernels (color.cu), which the image path runs as a pass of
+// its own in front of / behind the transform.
 //   colour.convert(x, 'RGB', 'IPT') (colour-science 0.4.4, called at spiht/color_models.py:12):
 //   linear sRGB -> CIE XYZ (4-digit IEC 61966-2-1 matrix; no CCTF decoding, D65 -> D65 adaptation is the
 //   identity) -> LMS -> sign(x) |x|^0.43 -> IPT (Ebner & Fairchild 1998).
