@@ -30,15 +30,16 @@ def test_random_geometry_end_to_end(oracle, case):
     _check_case(oracle, case)
 
 
-def _family_cases():
-    """the rest of the bior family (csrc/dwt_gen.cu): every wavelet in every mode, odd and even sizes, one to three levels"""
-    rng = np.random.default_rng(77)
+def _family_cases(seed=77, lo=60, hi=200):
+    """the rest of the bior family (csrc/dwt_gen.cu): every wavelet in every mode, odd and even sizes, one to three levels
+    or as deep as the size allows"""
+    rng = np.random.default_rng(seed)
     out = []
     for wavelet in ["bior1.1", "bior1.3", "bior1.5", "bior2.4", "bior2.6", "bior2.8", "bior3.1", "bior3.3", "bior3.5",
                     "bior3.7", "bior3.9", "bior5.5"]:
         for mode in ["reflect", "symmetric", "periodization"]:
             c = int(rng.integers(1, 4))
-            h, w = int(rng.integers(60, 200)), int(rng.integers(60, 200))
+            h, w = int(rng.integers(lo, hi)), int(rng.integers(lo, hi))
             level = [None, 1, 2, 3][int(rng.integers(0, 4))]
             out.append((c, h, w, wavelet, mode, level, float(rng.choice([0.0, 0.3, 2.0]))))
     return out
@@ -46,6 +47,13 @@ def _family_cases():
 
 @pytest.mark.parametrize("case", _family_cases())
 def test_rest_of_the_bior_family_end_to_end(oracle, case):
+    _check_case(oracle, case)
+
+
+@pytest.mark.parametrize("case", _family_cases(seed=78, lo=24, hi=340))
+def test_rest_of_the_bior_family_second_draw(oracle, case):
+    """other sizes (down to bands shorter than the filter, up to several row / column groups of the register-window
+    kernels: eight output rows and four output columns per thread)"""
     _check_case(oracle, case)
 
 
