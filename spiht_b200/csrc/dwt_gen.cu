@@ -178,19 +178,24 @@ struct GenFwdCols {
     double q;
 };
 
+// F is a template parameter so that the tap loop unrolls and the taps become constant-bank operands of the DFMAs
+// (with a run-time F the loop spent 4.5 x the instructions of its arithmetic on indexing: ncu, profiles/)
+template <int F>
 __global__ void __launch_bounds__(256) gen_fwd_cols_kernel(const __grid_constant__ GenTaps t, const __grid_constant__ GenFwdCols p)
 {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    const int i = blockIdx.y, z = blockIdx.z;
-    if (k >= p.bw) return;
-    const int s = p.mode == SPIHTB_MODE_PERIODIZATION ? t.F / 2 : 1;
+    // blockDim (64, 4): 64 output columns of four band rows (a band of 517 columns fills 256-wide blocks to 67 %)
+    const int k = blockIdx.x * 64 + threadIdx.x;
+    const int i = blockIdx.y * 4 + threadIdx.y, z = blockIdx.z;
+    if (k >= p.bw || i >= p.bh) return;
+    const int s = p.mode == SPIHTB_MODE_PERIODIZATION ? F / 2 : 1;
     const double *rl = p.lo + ((size_t)z * p.bh + i) * p.src_w;
     const double *rh = p.hi + ((size_t)z * p.bh + i) * p.src_w;
     double aa = 0.0, ad = 0.0, da = 0.0, dd = 0.0;
     const int top = 2 * k + s;   // the column tap 0 reads
-    if (top - (t.F - 1) >= 0 && top < p.src_w) {   // interior columns: no extension map
+    if (top - (F - 1) >= 0 && top < p.src_w) {   // interior columns: no extension map
         const double *ql = rl + top, *qh = rh + top;
-        for (int j = 0; j < t.F; ++j) {
+#pragma unroll
+        for (int j = 0; j < F; ++j) {
             const double vl = ql[-j], vh = qh[-j];
             aa = fma(t.lo[j], vl, aa);
             ad = fma(t.hi[j], vl, ad);
@@ -198,7 +203,8 @@ __global__ void __launch_bounds__(256) gen_fwd_cols_kernel(const __grid_constant
             dd = fma(t.hi[j], vh, dd);
         }
     } else {
-        for (int j = 0; j < t.F; ++j) {
+#pragma unroll
+        for (int j = 0; j < F; ++j) {
             const int c = ext_index(top - j, p.src_w, p.mode);
             const double vl = rl[c], vh = rh[c];
             aa = fma(t.lo[j], vl, aa);
@@ -279,7 +285,7 @@ int launch_gen_fwd_level(spihtb_ctx *ctx, int wid, const GenFwdLevel &a, int nz)
     rc = ctx->ensure(ctx->tail, 2 * plane * sizeof(double) + 256);
     if (rc) return rc;
     double *lo = static_cast<double *>(ctx->tail.p), *hi = lo + plane;
-    const dim3 g1((a.src_w + 255) / 256, (a.bh + GEN_R - 1) / GEN_R, nz), g2((a.bw + 255) / 256, a.bh, nz);
+    const dim3 g1((a.src_w + 255) / 256, (a.bh + GEN_R - 1) / GEN_R, nz), g2((a.bw + 63) / 64, (a.bh + 3) / 4, nz);
     auto rows = [&](auto fc) {
         constexpr int F = decltype(fc)::value;
         switch (a.src_dtype) {
@@ -311,7 +317,10 @@ int launch_gen_fwd_level(spihtb_ctx *ctx, int wid, const GenFwdLevel &a, int nz)
     p.Hc = a.Hc; p.Wc = a.Wc; p.sh = a.sh; p.sw = a.sw;
     for (int c = 0; c < 8; ++c) p.scale[c] = a.scale[c];
     p.q = a.q;
-    gen_fwd_cols_kernel<<<g2, 256, 0, ctx->stream>>>(t, p);
+    for_flen(t.F, [&](auto fc) {   // (t.F was accepted by the row pass above)
+        gen_fwd_cols_kernel<decltype(fc)::value><<<g2, dim3(64, 4), 0, ctx->stream>>>(t, p);
+        return true;
+    });
     ctx->launches += 2;
     SPIHTB_CUDA_CHECK(cudaGetLastError());
     return SPIHTB_OK;
