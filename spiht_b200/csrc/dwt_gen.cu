@@ -352,60 +352,80 @@ __global__ void __launch_bounds__(256) gen_inv_cols_kernel(const __grid_constant
     static_assert(GEN_C % 2 == 0, "n0 must be even");
     const int n0 = (blockIdx.x * 64 + threadIdx.x) * GEN_C;
     const int i = blockIdx.y * 4 + threadIdx.y, z = blockIdx.z;
-    if (n0 >= p.ow || i >= p.bh) return;
+    // no early return: the whole block meets at the barrier before the write-out
+    const bool active = n0 < p.ow && i < p.bh;
+    // results cross the block through shared memory so that the global stores are whole lines: a thread's four
+    // consecutive float64 outputs stored directly are 8-byte pieces at a 32-byte lane stride, four L2 transactions per
+    // sector -- the pass was bound by exactly that (6.4 GB of level-1 intermediates).  [row][u][thread], rows padded to 68
+    // doubles: conflict-free both ways (writes: consecutive threads; reads: banks 8 u + 2 q per half-warp).
+    __shared__ double s_lo[4][GEN_C][68], s_hi[4][GEN_C][68];
     constexpr int OFF = PER ? F / 2 - 1 : F - 2;
     constexpr int DMIN = OFF - (F - 1), DMAX = OFF + GEN_C - 1;
     constexpr int KLO = DMIN >= 0 ? DMIN / 2 : -((-DMIN) / 2);
     constexpr int KHI = DMAX / 2;
     constexpr int NK = KHI - KLO + 1;
-    const double rm = p.rscale[z % p.C], rq = p.rq;
-    const int32_t *arr = p.coeffs + (size_t)z * p.Hc * p.Wc;
-    const uint8_t *bm = p.blk ? p.blk + (size_t)z * p.BH * p.BW : nullptr;
-    // the two array rows this output row reads (details above / beside / below the approximation) and their mark rows
-    const int32_t *row_t = arr + (size_t)i * p.Wc, *row_b = arr + (size_t)(p.sh + i) * p.Wc;
-    const uint8_t *bm_t = bm ? bm + (size_t)(i >> 6) * p.BW : nullptr;
-    const uint8_t *bm_b = bm ? bm + (size_t)((p.sh + i) >> 6) * p.BW : nullptr;
-    auto coef = [&](const int32_t *row, const uint8_t *marks, int c) -> double {
-        if (marks && !marks[c >> 6]) return 0.0;
-        return ((double)row[c] * rm) * rq;   // spiht_wrapper.py:270-274, as in dwt_inv.cu
-    };
-    const double *row_a = p.src_a ? p.src_a + ((size_t)z * p.a_h + i) * p.a_w : nullptr;
-    double aa[NK], ad[NK], da[NK], dd[NK];
-#pragma unroll
-    for (int m = 0; m < NK; ++m) {
-        int k = n0 / 2 + KLO + m;
-        bool in = true;
-        if (PER) {
-            k %= p.bw;
-            if (k < 0) k += p.bw;
-        } else {
-            in = k >= 0 && k < p.bw;   // taps outside the band contribute nothing
-        }
-        aa[m] = ad[m] = da[m] = dd[m] = 0.0;
-        if (in) {
-            aa[m] = row_a ? row_a[k] : ((double)row_t[k] * rm) * rq;
-            ad[m] = coef(row_t, bm_t, p.sw + k);
-            da[m] = coef(row_b, bm_b, k);
-            dd[m] = coef(row_b, bm_b, p.sw + k);
-        }
-    }
-    const size_t o = ((size_t)z * p.bh + i) * p.ow + n0;
-#pragma unroll
-    for (int u = 0; u < GEN_C; ++u) {
-        if (n0 + u >= p.ow) break;
-        double lo = 0.0, hi = 0.0;
-#pragma unroll
-        for (int tt = 0; tt < F; ++tt) {
-            if (((OFF + u - tt) & 1) == 0) {
-                const int m = (OFF + u - tt) / 2 - KLO;   // exact: the numerator is even
-                lo = fma(t.lo[tt], aa[m], lo);
-                lo = fma(t.hi[tt], ad[m], lo);
-                hi = fma(t.lo[tt], da[m], hi);
-                hi = fma(t.hi[tt], dd[m], hi);
+    if (active) {
+        const double rm = p.rscale[z % p.C], rq = p.rq;
+        const int32_t *arr = p.coeffs + (size_t)z * p.Hc * p.Wc;
+        const uint8_t *bm = p.blk ? p.blk + (size_t)z * p.BH * p.BW : nullptr;
+        // the two array rows this output row reads (details above / beside / below the approximation) and their mark rows
+        const int32_t *row_t = arr + (size_t)i * p.Wc, *row_b = arr + (size_t)(p.sh + i) * p.Wc;
+        const uint8_t *bm_t = bm ? bm + (size_t)(i >> 6) * p.BW : nullptr;
+        const uint8_t *bm_b = bm ? bm + (size_t)((p.sh + i) >> 6) * p.BW : nullptr;
+        auto coef = [&](const int32_t *row, const uint8_t *marks, int c) -> double {
+            if (marks && !marks[c >> 6]) return 0.0;
+            return ((double)row[c] * rm) * rq;   // spiht_wrapper.py:270-274, as in dwt_inv.cu
+        };
+        const double *row_a = p.src_a ? p.src_a + ((size_t)z * p.a_h + i) * p.a_w : nullptr;
+        double aa[NK], ad[NK], da[NK], dd[NK];
+    #pragma unroll
+        for (int m = 0; m < NK; ++m) {
+            int k = n0 / 2 + KLO + m;
+            bool in = true;
+            if (PER) {
+                k %= p.bw;
+                if (k < 0) k += p.bw;
+            } else {
+                in = k >= 0 && k < p.bw;   // taps outside the band contribute nothing
+            }
+            aa[m] = ad[m] = da[m] = dd[m] = 0.0;
+            if (in) {
+                aa[m] = row_a ? row_a[k] : ((double)row_t[k] * rm) * rq;
+                ad[m] = coef(row_t, bm_t, p.sw + k);
+                da[m] = coef(row_b, bm_b, k);
+                dd[m] = coef(row_b, bm_b, p.sw + k);
             }
         }
-        p.xlo[o + u] = lo;
-        p.xhi[o + u] = hi;
+        // outputs n0 + u
+#pragma unroll
+        for (int u = 0; u < GEN_C; ++u) {
+            double lo = 0.0, hi = 0.0;
+#pragma unroll
+            for (int tt = 0; tt < F; ++tt) {
+                if (((OFF + u - tt) & 1) == 0) {
+                    const int m = (OFF + u - tt) / 2 - KLO;   // exact: the numerator is even
+                    lo = fma(t.lo[tt], aa[m], lo);
+                    lo = fma(t.hi[tt], ad[m], lo);
+                    hi = fma(t.lo[tt], da[m], hi);
+                    hi = fma(t.hi[tt], dd[m], hi);
+                }
+            }
+            s_lo[threadIdx.y][u][threadIdx.x] = lo;
+            s_hi[threadIdx.y][u][threadIdx.x] = hi;
+        }
+    }
+    __syncthreads();
+    if (i < p.bh) {   // write-out: thread x of a row stores outputs x, x + 64, x + 128, x + 192 of the row's 256
+        const int nb = blockIdx.x * 64 * GEN_C;
+        const size_t o = ((size_t)z * p.bh + i) * p.ow + nb;
+#pragma unroll
+        for (int v = 0; v < GEN_C; ++v) {
+            const int g = threadIdx.x + 64 * v;
+            if (nb + g < p.ow) {
+                p.xlo[o + g] = s_lo[threadIdx.y][g % GEN_C][g / GEN_C];
+                p.xhi[o + g] = s_hi[threadIdx.y][g % GEN_C][g / GEN_C];
+            }
+        }
     }
 }
 
