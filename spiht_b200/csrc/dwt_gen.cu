@@ -186,27 +186,30 @@ __global__ void __launch_bounds__(256) gen_fwd_cols_kernel(const __grid_constant
     // blockDim (64, 4): 64 output columns of four band rows (a band of 517 columns fills 256-wide blocks to 67 %)
     const int k = blockIdx.x * 64 + threadIdx.x;
     const int i = blockIdx.y * 4 + threadIdx.y, z = blockIdx.z;
-    if (k >= p.bw || i >= p.bh) return;
     const int s = p.mode == SPIHTB_MODE_PERIODIZATION ? F / 2 : 1;
-    const double *rl = p.lo + ((size_t)z * p.bh + i) * p.src_w;
-    const double *rh = p.hi + ((size_t)z * p.bh + i) * p.src_w;
+    // the block's segment of the low and the high row goes through shared memory: coalesced loads (the extension map
+    // applied once per sample), then the taps read it at a two-sample lane stride
+    constexpr int NSEG = 2 * 64 + F - 2;
+    __shared__ double s_l[4][NSEG], s_h[4][NSEG];
+    const int cb = 2 * (blockIdx.x * 64) + s - (F - 1);   // column of segment slot 0; output 64 bx + x, tap j reads slot F-1 + 2x - j
+    if (i < p.bh) {
+        const double *rl = p.lo + ((size_t)z * p.bh + i) * p.src_w;
+        const double *rh = p.hi + ((size_t)z * p.bh + i) * p.src_w;
+        for (int m = threadIdx.x; m < NSEG; m += 64) {
+            int c = cb + m;
+            if (c < 0 || c >= p.src_w) c = ext_index(c, p.src_w, p.mode);
+            s_l[threadIdx.y][m] = rl[c];
+            s_h[threadIdx.y][m] = rh[c];
+        }
+    }
+    __syncthreads();
+    if (k >= p.bw || i >= p.bh) return;
     double aa = 0.0, ad = 0.0, da = 0.0, dd = 0.0;
-    const int top = 2 * k + s;   // the column tap 0 reads
-    if (top - (F - 1) >= 0 && top < p.src_w) {   // interior columns: no extension map
-        const double *ql = rl + top, *qh = rh + top;
+    {
+        const double *ql = &s_l[threadIdx.y][F - 1 + 2 * threadIdx.x], *qh = &s_h[threadIdx.y][F - 1 + 2 * threadIdx.x];
 #pragma unroll
         for (int j = 0; j < F; ++j) {
             const double vl = ql[-j], vh = qh[-j];
-            aa = fma(t.lo[j], vl, aa);
-            ad = fma(t.hi[j], vl, ad);
-            da = fma(t.lo[j], vh, da);
-            dd = fma(t.hi[j], vh, dd);
-        }
-    } else {
-#pragma unroll
-        for (int j = 0; j < F; ++j) {
-            const int c = ext_index(top - j, p.src_w, p.mode);
-            const double vl = rl[c], vh = rh[c];
             aa = fma(t.lo[j], vl, aa);
             ad = fma(t.hi[j], vl, ad);
             da = fma(t.lo[j], vh, da);
